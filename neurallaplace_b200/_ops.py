@@ -1,0 +1,180 @@
+"""Thin Python wrappers over the C ABI + the autograd glue.
+
+Everything here launches hand-written CUDA through ``libnl_b200.so`` on the current torch stream;
+torch is only used for device memory and autograd bookkeeping.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import NlDesc
+
+_stats = {"launches": 0}
+
+
+def launches():
+  """Kernel launches issued through the fused entry points since import (bench.py reads this)."""
+  return _stats["launches"]
+
+
+def _desc(consts, dtype, B=0, T=0, K=1, H=1, D=1, t_mode=0, head=0, impl=0, n=None):
+  d = NlDesc()
+  d.B, d.T, d.K, d.H, d.D = int(B), int(T), int(K), int(H), int(D)
+  d.n = int(consts.n if n is None else n)
+  d.family = consts.family
+  d.t_mode = t_mode
+  d.head = head
+  d.dtype = _lib.dtype_code(dtype)
+  d.impl = impl
+  d.alpha, d.log_tol, d.scale = consts.alpha, consts.log_tol, consts.scale
+  return d
+
+
+def _workspace(lib, d, which, device):
+  nbytes = lib.nl_workspace_bytes(ctypes.byref(d), which)
+  return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device), nbytes
+
+
+# ------------------------------------------------------------------------------------------
+# fused reconstruct
+# ------------------------------------------------------------------------------------------
+class ReconstructFn(torch.autograd.Function):
+  """x = laplace_reconstruct(canonical MLP, p, t) as ONE fused forward and ONE fused backward."""
+
+  @staticmethod
+  def forward(ctx, p, t, W1, b1, W2, b2, W3, b3, consts, D, t_mode, head, impl):
+    lib = _lib.load()
+    dev = p.device
+    B, K = p.shape
+    T = t.shape[-1] if t_mode == _lib.NL_T_PER_ROW else t.numel()
+    H = W1.shape[0]
+    d = _desc(consts, p.dtype, B, T, K, H, D, t_mode, head, impl)
+    ws, nbytes = _workspace(lib, d, 0, dev)
+    beta, eta = consts.tables_on(dev)
+    weights = [w.contiguous() for w in (W1, b1, W2, b2, W3, b3)]
+    x = torch.empty((B, T, D), dtype=p.dtype, device=dev)
+    pc, tc = p.contiguous(), t.contiguous()
+    st = lib.nl_reconstruct_forward(ctypes.byref(d), _lib.ptr(pc), _lib.ptr(tc), _lib.ptr_array(weights),
+                                    _lib.ptr(beta), _lib.ptr(eta), _lib.ptr(x), _lib.ptr(ws), nbytes,
+                                    _lib.stream_ptr())
+    _lib.check(st)
+    _stats["launches"] += lib.nl_last_launch_count()
+    ctx.save_for_backward(pc, tc, *weights)
+    ctx.meta = (consts, D, t_mode, head, impl)
+    return x
+
+  @staticmethod
+  def backward(ctx, gx):
+    lib = _lib.load()
+    pc, tc, *weights = ctx.saved_tensors
+    consts, D, t_mode, head, impl = ctx.meta
+    dev = pc.device
+    B, K = pc.shape
+    T = tc.shape[-1] if t_mode == _lib.NL_T_PER_ROW else tc.numel()
+    H = weights[0].shape[0]
+    d = _desc(consts, pc.dtype, B, T, K, H, D, t_mode, head, impl)
+    ws, nbytes = _workspace(lib, d, 1, dev)
+    beta, eta = consts.tables_on(dev)
+    grads = [torch.empty_like(w) for w in weights] + [torch.empty_like(pc)]
+    gxc = gx.contiguous()
+    st = lib.nl_reconstruct_backward(ctypes.byref(d), _lib.ptr(pc), _lib.ptr(tc), _lib.ptr_array(weights),
+                                     _lib.ptr(beta), _lib.ptr(eta), _lib.ptr(gxc), _lib.ptr_array(grads),
+                                     _lib.ptr(ws), nbytes, _lib.stream_ptr())
+    _lib.check(st)
+    _stats["launches"] += lib.nl_last_launch_count()
+    gW1, gb1, gW2, gb2, gW3, gb3, gp = grads
+    return gp, None, gW1, gb1, gW2, gb2, gW3, gb3, None, None, None, None, None
+
+
+def fused_supported(consts, dtype, B, T, K, H, D, t_mode, head, impl=0):
+  lib = _lib.load()
+  d = _desc(consts, dtype, B, T, K, H, D, t_mode, head, impl)
+  return lib.nl_selected_impl(ctypes.byref(d), 0) != 0 and lib.nl_selected_impl(ctypes.byref(d), 1) != 0
+
+
+def selected_impl(consts, dtype, B, T, K, H, D, t_mode, head, which=0, impl=0):
+  lib = _lib.load()
+  d = _desc(consts, dtype, B, T, K, H, D, t_mode, head, impl)
+  return lib.nl_selected_impl(ctypes.byref(d), which)
+
+
+# ------------------------------------------------------------------------------------------
+# split path
+# ------------------------------------------------------------------------------------------
+def query_points(consts, t_flat, head, want_s, want_feat, Tper=None):
+  """compute_s (+ sphere projection) for a flat vector of time points (no grad)."""
+  lib = _lib.load()
+  dev, dtype = t_flat.device, t_flat.dtype
+  rows = t_flat.numel()
+  d = _desc(consts, dtype, head=head)
+  beta, _ = consts.tables_on(dev)
+  s = torch.empty((rows, consts.n, 2), dtype=dtype, device=dev) if want_s else None
+  feat = torch.empty((rows, 2 * consts.n), dtype=dtype, device=dev) if want_feat else None
+  tc = t_flat.contiguous()
+  Tc = Tper.contiguous() if Tper is not None else None
+  st = lib.nl_query_points(ctypes.byref(d), rows, _lib.ptr(tc), _lib.ptr(Tc), _lib.ptr(beta), _lib.ptr(s),
+                           _lib.ptr(feat), _lib.stream_ptr())
+  _lib.check(st)
+  return (torch.view_as_complex(s) if want_s else None), feat
+
+
+class LineIntegrateFn(torch.autograd.Function):
+  """x[B,T,D] from F[B,T,D,n] given as (theta, phi) / (re, im) planes or an interleaved complex."""
+
+  @staticmethod
+  def forward(ctx, fa, fb, t, Tper, consts, layout, t_mode, eta_override):
+    lib = _lib.load()
+    dev, dtype = fa.device, fa.dtype
+    if layout == _lib.NL_F_COMPLEX_INTERLEAVED:
+      B, T, D, n, _two = fa.shape
+    else:
+      B, T, D, n = fa.shape
+    d = _desc(consts, dtype, B, T, 1, 1, D, t_mode, 0, 0, n=n)
+    if eta_override is not None:
+      eta = eta_override
+    else:
+      _, eta = consts.tables_on(dev)
+    fac = fa.contiguous()
+    fbc = fb.contiguous() if fb is not None else None
+    tc = t.contiguous()
+    Tc = Tper.contiguous() if Tper is not None else None
+    x = torch.empty((B, T, D), dtype=dtype, device=dev)
+    st = lib.nl_line_integrate_forward(ctypes.byref(d), layout, _lib.ptr(fac), _lib.ptr(fbc), _lib.ptr(tc),
+                                       _lib.ptr(Tc), _lib.ptr(eta), _lib.ptr(x), _lib.stream_ptr())
+    _lib.check(st)
+    ctx.save_for_backward(fac, fbc, tc, Tc, eta)
+    ctx.meta = (consts, layout, t_mode, d)
+    return x
+
+  @staticmethod
+  def backward(ctx, gx):
+    lib = _lib.load()
+    fac, fbc, tc, Tc, eta = ctx.saved_tensors
+    consts, layout, t_mode, d = ctx.meta
+    ga = torch.empty_like(fac)
+    gb = torch.empty_like(fbc) if fbc is not None else None
+    gxc = gx.contiguous()
+    st = lib.nl_line_integrate_backward(ctypes.byref(d), layout, _lib.ptr(fac), _lib.ptr(fbc), _lib.ptr(tc),
+                                        _lib.ptr(Tc), _lib.ptr(eta), _lib.ptr(gxc), _lib.ptr(ga), _lib.ptr(gb),
+                                        _lib.stream_ptr())
+    _lib.check(st)
+    return ga, gb, None, None, None, None, None, None
+
+
+def line_integrate(consts, fa, fb, t, Tper, layout, t_mode, eta_override=None):
+  return LineIntegrateFn.apply(fa, fb, t, Tper, consts, layout, t_mode, eta_override)
+
+
+def sphere_map(which, a, b):
+  """which=0: (s_re, s_im) -> (theta, phi);  which=1: (theta, phi) -> (s_re, s_im).  Flat, no grad."""
+  lib = _lib.load()
+  ac, bc = a.contiguous(), b.contiguous()
+  o0, o1 = torch.empty_like(ac), torch.empty_like(bc)
+  fn = lib.nl_complex_to_sphere if which == 0 else lib.nl_sphere_to_complex
+  st = fn(_lib.dtype_code(ac.dtype), ac.numel(), _lib.ptr(ac), _lib.ptr(bc), _lib.ptr(o0), _lib.ptr(o1),
+          _lib.stream_ptr())
+  _lib.check(st)
+  return o0, o1

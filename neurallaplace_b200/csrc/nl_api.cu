@@ -1,0 +1,187 @@
+// C ABI of the library (see include/nl_b200.h for the contract and the reference lines each
+// entry point replaces).  Thin: validate, pick the kernel family, launch on the caller's stream.
+#include <cstdio>
+#include <cstring>
+
+#include "nl_kernels.h"
+
+namespace {
+thread_local char g_cuda_err[256] = "";
+thread_local int g_launches = 0;
+
+int cuda_fail(cudaError_t e) {
+  std::snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", cudaGetErrorName(e), cudaGetErrorString(e));
+  return NL_ERR_CUDA;
+}
+
+int check_desc(const nl_desc* d) {
+  if (!d) return NL_ERR_NULL;
+  if (d->dtype != NL_F32 && d->dtype != NL_F64) return NL_ERR_ENUM;
+  if (d->family < NL_FOURIER || d->family > NL_DEHOOG) return NL_ERR_ENUM;
+  if (d->t_mode != NL_T_SHARED && d->t_mode != NL_T_PER_ROW) return NL_ERR_ENUM;
+  if (d->head != NL_HEAD_SPHERE && d->head != NL_HEAD_RAW) return NL_ERR_ENUM;
+  if (d->impl < 0 || d->impl > 2) return NL_ERR_ENUM;
+  return NL_OK;
+}
+
+int check_fused(const nl_desc* d) {
+  int s = check_desc(d);
+  if (s) return s;
+  if (d->B < 0 || d->T < 0 || d->K < 1 || d->H < 1 || d->D < 1 || d->n < 1) return NL_ERR_SHAPE;
+  return NL_OK;
+}
+
+// 1 = SIMT, 2 = tcgen05, 0 = neither covers the shape
+int pick_impl(const nl_desc* d, int pass) {
+  if (d->impl == 1) return nl::simt_plan(d, pass).ok ? 1 : 0;
+  if (d->impl == 2) return nl::tc_plan(d, pass).ok ? 2 : 0;
+  if (nl::tc_plan(d, pass).ok) return 2;
+  if (nl::simt_plan(d, pass).ok) return 1;
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int nl_abi_version(void) { return NL_B200_ABI_VERSION; }
+
+const char* nl_strerror(int status) {
+  switch (status) {
+    case NL_OK: return "ok";
+    case NL_ERR_NULL: return "required pointer is NULL";
+    case NL_ERR_SHAPE: return "invalid dimension";
+    case NL_ERR_UNSUPPORTED: return "shape not covered by the fused kernels (use the split path)";
+    case NL_ERR_WORKSPACE: return "workspace too small";
+    case NL_ERR_CUDA: return "CUDA runtime error";
+    case NL_ERR_ENUM: return "invalid enum value in nl_desc";
+    default: return "unknown nl_status";
+  }
+}
+
+const char* nl_last_cuda_error(void) { return g_cuda_err; }
+int nl_last_launch_count(void) { return g_launches; }
+
+size_t nl_workspace_bytes(const nl_desc* d, int pass) {
+  if (check_fused(d)) return 0;
+  size_t a = 0, b = 0;
+  nl::SimtPlan sp = nl::simt_plan(d, pass);
+  if (sp.ok) a = sp.ws_bytes;
+  nl::TcPlan tp = nl::tc_plan(d, pass);
+  if (tp.ok) b = tp.ws_bytes;
+  return (a > b ? a : b) + 256;
+}
+
+int nl_selected_impl(const nl_desc* d, int pass) {
+  if (check_fused(d)) return 0;
+  return pick_impl(d, pass);
+}
+
+static int reconstruct(const nl_desc* d, bool bwd, const void* p, const void* t, const void* const* weights,
+                       const void* beta, const void* eta, void* x, const void* gx, void* const* grads, void* ws,
+                       size_t ws_bytes, void* stream) {
+  g_launches = 0;
+  int s = check_fused(d);
+  if (s) return s;
+  if (!p || !t || !weights) return NL_ERR_NULL;
+  for (int i = 0; i < 6; ++i)
+    if (!weights[i]) return NL_ERR_NULL;
+  if (d->family == NL_AW && (!beta || !eta)) return NL_ERR_NULL;
+  if (bwd) {
+    if (!gx || !grads) return NL_ERR_NULL;
+    for (int i = 0; i < 7; ++i)
+      if (!grads[i]) return NL_ERR_NULL;
+  } else if (!x) {
+    return NL_ERR_NULL;
+  }
+  const int pass = bwd ? 1 : 0;
+  const int impl = pick_impl(d, pass);
+  if (impl == 0) return NL_ERR_UNSUPPORTED;
+  const size_t need = nl_workspace_bytes(d, pass);
+  if (need > 0 && (!ws || ws_bytes < need)) return NL_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e;
+  if (impl == 2) {
+    e = nl::launch_fused_tc(d, bwd, p, t, weights, beta, eta, x, gx, grads, ws, st, &g_launches);
+  } else if (d->dtype == NL_F64) {
+    e = nl::launch_fused_simt<double>(d, bwd, p, t, weights, beta, eta, x, gx, grads, ws, st, &g_launches);
+  } else {
+    e = nl::launch_fused_simt<float>(d, bwd, p, t, weights, beta, eta, x, gx, grads, ws, st, &g_launches);
+  }
+  if (e != cudaSuccess) return cuda_fail(e);
+  return NL_OK;
+}
+
+int nl_reconstruct_forward(const nl_desc* d, const void* p, const void* t, const void* const* weights,
+                           const void* beta, const void* eta, void* x, void* ws, size_t ws_bytes, void* stream) {
+  return reconstruct(d, false, p, t, weights, beta, eta, x, nullptr, nullptr, ws, ws_bytes, stream);
+}
+
+int nl_reconstruct_backward(const nl_desc* d, const void* p, const void* t, const void* const* weights,
+                            const void* beta, const void* eta, const void* grad_x, void* const* grads, void* ws,
+                            size_t ws_bytes, void* stream) {
+  return reconstruct(d, true, p, t, weights, beta, eta, nullptr, grad_x, grads, ws, ws_bytes, stream);
+}
+
+int nl_query_points(const nl_desc* d, int64_t rows, const void* t, const void* Tper, const void* beta, void* s_out,
+                    void* feat_out, void* stream) {
+  int s = check_desc(d);
+  if (s) return s;
+  if (rows < 0 || d->n < 1) return NL_ERR_SHAPE;
+  if (!t) return NL_ERR_NULL;
+  if (d->family == NL_AW && !beta) return NL_ERR_NULL;
+  cudaError_t e = d->dtype == NL_F64
+                      ? nl::launch_query_points<double>(d, rows, t, Tper, beta, s_out, feat_out, (cudaStream_t)stream)
+                      : nl::launch_query_points<float>(d, rows, t, Tper, beta, s_out, feat_out, (cudaStream_t)stream);
+  return e == cudaSuccess ? NL_OK : cuda_fail(e);
+}
+
+static int line_integrate(const nl_desc* d, int layout, bool bwd, const void* fa, const void* fb, const void* t,
+                          const void* Tper, const void* eta, const void* gx, void* x, void* ga, void* gb,
+                          void* stream) {
+  int s = check_desc(d);
+  if (s) return s;
+  if (layout < NL_F_SPHERE_PLANAR || layout > NL_F_COMPLEX_INTERLEAVED) return NL_ERR_ENUM;
+  if (d->B < 0 || d->T < 0 || d->D < 1 || d->n < 1) return NL_ERR_SHAPE;
+  if (d->family == NL_DEHOOG && (d->n < 3 || d->n % 2 == 0)) return NL_ERR_SHAPE;
+  const bool planar = layout != NL_F_COMPLEX_INTERLEAVED;
+  if (!fa || !t || (planar && !fb)) return NL_ERR_NULL;
+  if (d->family == NL_AW && !eta) return NL_ERR_NULL;
+  if (bwd ? (!gx || !ga || (planar && !gb)) : !x) return NL_ERR_NULL;
+  cudaError_t e =
+      d->dtype == NL_F64
+          ? nl::launch_line_integrate<double>(d, layout, bwd, fa, fb, t, Tper, eta, gx, x, ga, gb, (cudaStream_t)stream)
+          : nl::launch_line_integrate<float>(d, layout, bwd, fa, fb, t, Tper, eta, gx, x, ga, gb, (cudaStream_t)stream);
+  return e == cudaSuccess ? NL_OK : cuda_fail(e);
+}
+
+int nl_line_integrate_forward(const nl_desc* d, int f_layout, const void* fa, const void* fb, const void* t,
+                              const void* Tper, const void* eta, void* x, void* stream) {
+  return line_integrate(d, f_layout, false, fa, fb, t, Tper, eta, nullptr, x, nullptr, nullptr, stream);
+}
+
+int nl_line_integrate_backward(const nl_desc* d, int f_layout, const void* fa, const void* fb, const void* t,
+                               const void* Tper, const void* eta, const void* grad_x, void* grad_fa, void* grad_fb,
+                               void* stream) {
+  return line_integrate(d, f_layout, true, fa, fb, t, Tper, eta, grad_x, nullptr, grad_fa, grad_fb, stream);
+}
+
+static int sphere(int which, int dtype, int64_t count, const void* a, const void* b, void* c, void* e, void* stream) {
+  if (dtype != NL_F32 && dtype != NL_F64) return NL_ERR_ENUM;
+  if (count < 0) return NL_ERR_SHAPE;
+  if (count > 0 && (!a || !b || !c || !e)) return NL_ERR_NULL;
+  cudaError_t err = dtype == NL_F64 ? nl::launch_sphere<double>(which, count, a, b, c, e, (cudaStream_t)stream)
+                                    : nl::launch_sphere<float>(which, count, a, b, c, e, (cudaStream_t)stream);
+  return err == cudaSuccess ? NL_OK : cuda_fail(err);
+}
+
+int nl_complex_to_sphere(int dtype, int64_t count, const void* s_re, const void* s_im, void* theta, void* phi,
+                         void* stream) {
+  return sphere(0, dtype, count, s_re, s_im, theta, phi, stream);
+}
+
+int nl_sphere_to_complex(int dtype, int64_t count, const void* theta, const void* phi, void* s_re, void* s_im,
+                         void* stream) {
+  return sphere(1, dtype, count, theta, phi, s_re, s_im, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,647 @@
+// Fused laplace_reconstruct forward / backward on CUDA cores (FFMA / DFMA), any dtype, any ILT
+// family, shared or per-row time grids.  This is the float64 path (tcgen05 has no fp64 kind) and
+// the general-shape path; the float32 canonical shape runs on tensor cores (nl_fused_tc.cu).
+//
+// One persistent CTA (256 threads) walks tiles of `TT x BB` (time x batch) rows.  Per tile it
+//   1. generates the s points of its time slots, projects them on the Riemann sphere and applies
+//      the s-part of layer 1 (S1 = W1s . u_t) -- amortised over the BB batch rows of a slot;
+//   2. evaluates layers 1..2 of the canonical laplace_rep_func into shared memory;
+//   3. for each d_obs evaluates the 2n outputs of layer 3, the tanh heads, the sphere->complex map
+//      and the complex-weighted reduction over terms (or the De Hoog recurrence) without the
+//      (batch x time x terms x d_obs) complex intermediate ever leaving the SM;
+//   4. (backward) recomputes 1-3, and back-propagates: weight gradients go to a CTA-private slab
+//      in the workspace (plain read-modify-write by an owning thread -> deterministic), reduced
+//      over CTAs by a second tiny kernel; dp uses atomics.
+// Rows are mapped to lanes (row = lane + 32*i), output columns to warps, so weight reads are
+// warp-uniform (one L1 transaction) and activation reads from shared memory are conflict-free.
+//
+// Math: SURVEY.md App. A/B; reference core.py:104-150, inverse_laplace.py, transformations.py.
+#include <algorithm>
+
+#include "nl_dehoog.cuh"
+#include "nl_kernels.h"
+
+namespace nl {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kKCU = 32;  // s points per feature chunk of layer 1
+
+template <typename R>
+struct FusedArgs {
+  IltParams<R> P;
+  int B, T, K, H, D, n, t_mode;
+  int BB, TT, nbt, ntt;
+  const R* p;
+  const R* t;
+  const R *W1, *b1, *W2, *b2, *W3, *b3;
+  R* x;
+  const R* gx;
+  R* slab;
+  int64_t slab_len;
+  R* dp;
+  Cx<R>* scratch;
+  int64_t scratch_stride;
+};
+
+struct SmemLayout {
+  int ldh, ldo, ldu;
+  size_t H1, H2, G, S1, O, U, Coef, Ctx, Pm, X, total;  // offsets in units of R
+};
+
+__host__ __device__ inline SmemLayout smem_layout(int rmax, int H, int n, int K, bool bwd, bool fourier_coef,
+                                                  int ctx_reals) {
+  SmemLayout L;
+  L.ldh = H + 1;
+  L.ldo = 2 * n + 1;
+  L.ldu = 2 * kKCU + 1;
+  size_t o = 0;
+  L.H1 = o; o += (size_t)rmax * L.ldh;
+  L.H2 = o; o += (size_t)rmax * L.ldh;
+  L.G = o;  o += bwd ? (size_t)rmax * L.ldh : 0;
+  L.S1 = o; o += (size_t)rmax * L.ldh;
+  L.O = o;  o += (size_t)rmax * L.ldo;
+  L.U = o;  o += (size_t)rmax * L.ldu;
+  L.Coef = o; o += fourier_coef ? (size_t)rmax * n * 2 : 0;
+  L.Ctx = o; o += (size_t)rmax * ctx_reals;
+  L.Pm = o; o += (size_t)rmax * K;
+  L.X = o;  o += (size_t)rmax * 2;
+  L.total = o;
+  return L;
+}
+
+// C[r][c] = sum_k A[r][k] * W[c*sc + k*sk]; rows r = lane + 32*i, columns split over warps.
+template <typename R, int RP, int CB, typename Epi>
+__device__ __forceinline__ void gemm_rows(const R* __restrict__ sA, int lda, int Kdim, int rows,
+                                          const R* __restrict__ W, int64_t sc, int64_t sk, int NC, Epi epi) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int c0 = warp * CB; c0 < NC; c0 += kWarps * CB) {
+    R acc[RP][CB];
+#pragma unroll
+    for (int i = 0; i < RP; ++i)
+#pragma unroll
+      for (int j = 0; j < CB; ++j) acc[i][j] = R(0);
+    const R* Wc = W + (int64_t)c0 * sc;
+    const int cb = min(CB, NC - c0);
+    if (cb == CB) {
+#pragma unroll 2
+      for (int k = 0; k < Kdim; ++k) {
+        R a[RP];
+#pragma unroll
+        for (int i = 0; i < RP; ++i) a[i] = sA[(lane + 32 * i) * lda + k];
+#pragma unroll
+        for (int j = 0; j < CB; ++j) {
+          R w = __ldg(Wc + j * sc + k * sk);
+#pragma unroll
+          for (int i = 0; i < RP; ++i) acc[i][j] = fma(a[i], w, acc[i][j]);
+        }
+      }
+    } else {
+      for (int k = 0; k < Kdim; ++k) {
+        R a[RP];
+#pragma unroll
+        for (int i = 0; i < RP; ++i) a[i] = sA[(lane + 32 * i) * lda + k];
+#pragma unroll
+        for (int j = 0; j < CB; ++j) {
+          if (j < cb) {
+            R w = __ldg(Wc + j * sc + k * sk);
+#pragma unroll
+            for (int i = 0; i < RP; ++i) acc[i][j] = fma(a[i], w, acc[i][j]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < RP; ++i) {
+      const int r = lane + 32 * i;
+      if (r < rows) {
+#pragma unroll
+        for (int j = 0; j < CB; ++j)
+          if (j < cb) epi(r, c0 + j, acc[i][j]);
+      }
+    }
+  }
+}
+
+// out[j*ldo + c] += sum_{r<rows} A1[r*ld1 + j] * A2[r*ld2 + c]   (weight gradients; lanes <-> c)
+template <typename R>
+__device__ __forceinline__ void gemm_tn_accum(const R* __restrict__ sA1, int ld1, int NJ,
+                                              const R* __restrict__ sA2, int ld2, int NC, int rows, R* out,
+                                              int64_t ldo) {
+  constexpr int JB = 8, CP = 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int j0 = warp * JB; j0 < NJ; j0 += kWarps * JB) {
+    const int jb = min(JB, NJ - j0);
+    for (int c0 = 0; c0 < NC; c0 += 32 * CP) {
+      R acc[JB][CP];
+#pragma unroll
+      for (int j = 0; j < JB; ++j)
+#pragma unroll
+        for (int q = 0; q < CP; ++q) acc[j][q] = R(0);
+      for (int r = 0; r < rows; ++r) {
+        R a2[CP];
+#pragma unroll
+        for (int q = 0; q < CP; ++q) {
+          int c = c0 + lane + 32 * q;
+          a2[q] = (c < NC) ? sA2[r * ld2 + c] : R(0);
+        }
+#pragma unroll
+        for (int j = 0; j < JB; ++j) {
+          R a1 = (j < jb) ? sA1[r * ld1 + j0 + j] : R(0);
+#pragma unroll
+          for (int q = 0; q < CP; ++q) acc[j][q] = fma(a1, a2[q], acc[j][q]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < JB; ++j) {
+        if (j < jb) {
+#pragma unroll
+          for (int q = 0; q < CP; ++q) {
+            int c = c0 + lane + 32 * q;
+            if (c < NC) out[(int64_t)(j0 + j) * ldo + c] += acc[j][q];
+          }
+        }
+      }
+    }
+  }
+}
+
+// out[c] += sum_{r<rows} A[r*ld + c]
+template <typename R>
+__device__ __forceinline__ void colsum_accum(const R* __restrict__ sA, int ld, int NC, int rows, R* out) {
+  for (int c = threadIdx.x; c < NC; c += kThreads) {
+    R s = R(0);
+    for (int r = 0; r < rows; ++r) s += sA[r * ld + c];
+    out[c] += s;
+  }
+}
+
+__device__ __forceinline__ void atomic_add(float* a, float v) { atomicAdd(a, v); }
+__device__ __forceinline__ void atomic_add(double* a, double v) { atomicAdd(a, v); }
+
+// per-slot context kept in shared memory
+template <typename R>
+struct SlotCtx {
+  R t, T, gamma, inv, ratio, pref, zc, zs;
+};
+
+template <typename R, int RP, bool BWD>
+__global__ void __launch_bounds__(kThreads, 1) fused_simt_kernel(FusedArgs<R> A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  R* sm = reinterpret_cast<R*>(smem_raw);
+  constexpr int RMAX = 32 * RP;
+  const IltParams<R> P = A.P;
+  const int H = A.H, n = A.n, K = A.K, D = A.D;
+  const bool dehoog = P.family == NL_DEHOOG;
+  const bool fourier_coef = P.family == NL_FOURIER;
+  const SmemLayout L = smem_layout(RMAX, H, n, K, BWD, fourier_coef, (int)(sizeof(SlotCtx<R>) / sizeof(R)));
+  R* sH1 = sm + L.H1;
+  R* sH2 = sm + L.H2;
+  R* sG = sm + L.G;
+  R* sS1 = sm + L.S1;
+  R* sO = sm + L.O;
+  R* sU = sm + L.U;
+  R* sCoef = sm + L.Coef;
+  SlotCtx<R>* sCtx = reinterpret_cast<SlotCtx<R>*>(sm + L.Ctx);
+  R* sP = sm + L.Pm;
+  R* sX = sm + L.X;   // [RMAX] accumulators / upstream grads
+  R* sGp = sX + RMAX; // [RMAX] g * pref
+  const int ldh = L.ldh, ldo = L.ldo, ldu = L.ldu;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ldw1 = 2 * n + K;
+  const bool per_row = A.t_mode == NL_T_PER_ROW;
+  const int rows = A.TT * A.BB;
+  const int NS = per_row ? rows : A.TT;
+  const int ntiles = A.nbt * A.ntt;
+
+  // slab sections (backward)
+  R* slab = BWD ? A.slab + (int64_t)blockIdx.x * A.slab_len : nullptr;
+  R* gW1 = slab;
+  R* gb1 = gW1 + (int64_t)H * ldw1;
+  R* gW2 = gb1 + H;
+  R* gb2 = gW2 + (int64_t)H * H;
+  R* gW3 = gb2 + H;
+  R* gb3 = gW3 + (int64_t)2 * D * n * H;
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int b0 = (tile % A.nbt) * A.BB;
+    const int t0 = (tile / A.nbt) * A.TT;
+    auto row_b = [&](int r) { return b0 + r % A.BB; };
+    auto row_t = [&](int r) { return t0 + r / A.BB; };
+    auto row_valid = [&](int r) { return r < rows && row_b(r) < A.B && row_t(r) < A.T; };
+    auto row_slot = [&](int r) { return per_row ? r : r / A.BB; };
+
+    // ---- 0. slot contexts, p rows
+    for (int s = tid; s < NS; s += kThreads) {
+      R tv = R(1);
+      if (per_row) {
+        if (row_valid(s)) tv = A.t[(int64_t)row_b(s) * A.T + row_t(s)];
+      } else if (t0 + s < A.T) {
+        tv = A.t[t0 + s];
+      }
+      TimeCtx<R> c = make_time_ctx<R>(P, tv, nullptr, 0);
+      SlotCtx<R> sc;
+      sc.t = c.t; sc.T = c.T; sc.gamma = c.gamma; sc.inv = c.inv; sc.ratio = c.ratio; sc.pref = c.pref;
+      sc.zc = R(1); sc.zs = R(0);
+      if (dehoog) m_sincos((R(kPi) * c.t) / c.T, &sc.zs, &sc.zc);
+      sCtx[s] = sc;
+    }
+    for (int i = tid; i < rows * K; i += kThreads) {
+      int r = i / K, j = i - r * K;
+      sP[i] = row_valid(r) ? A.p[(int64_t)row_b(r) * K + j] : R(0);
+    }
+    for (int i = tid; i < NS * ldh; i += kThreads) sS1[i] = R(0);
+    __syncthreads();
+
+    // ---- 1. s points -> sphere features -> S1 = W1s . u   (chunks of kKCU terms)
+    auto fill_features = [&](int kc0) {
+      for (int i = tid; i < NS * kKCU; i += kThreads) {
+        int s = i / kKCU, kk = i - s * kKCU, k = kc0 + kk;
+        R f0 = R(0), f1 = R(0);
+        if (k < n) {
+          SlotCtx<R> sc = sCtx[s];
+          TimeCtx<R> c{sc.t, sc.T, sc.gamma, sc.inv, sc.ratio, sc.pref};
+          s_features(P, s_point(P, c, k), &f0, &f1);
+          if (fourier_coef) {
+            Cx<R> w = reduce_coef(P, c, k);
+            sCoef[((int64_t)s * n + k) * 2] = w.re;
+            sCoef[((int64_t)s * n + k) * 2 + 1] = w.im;
+          }
+        }
+        sU[s * ldu + kk] = f0;
+        sU[s * ldu + kKCU + kk] = f1;
+      }
+    };
+    for (int kc0 = 0; kc0 < n; kc0 += kKCU) {
+      fill_features(kc0);
+      __syncthreads();
+      const int kc = min(kKCU, n - kc0);
+      gemm_rows<R, RP, 8>(sU, ldu, kc, NS, A.W1 + kc0, ldw1, 1, H,
+                          [&](int r, int c, R v) { sS1[r * ldh + c] += v; });
+      gemm_rows<R, RP, 8>(sU + kKCU, ldu, kc, NS, A.W1 + n + kc0, ldw1, 1, H,
+                          [&](int r, int c, R v) { sS1[r * ldh + c] += v; });
+      __syncthreads();
+    }
+
+    // ---- 2. h1 = tanh(S1[slot] + W1p.p + b1)
+    for (int i = tid; i < rows * H; i += kThreads) {
+      int r = i / H, c = i - r * H;
+      R z = sS1[row_slot(r) * ldh + c] + __ldg(A.b1 + c);
+      for (int j = 0; j < K; ++j) z = fma(__ldg(A.W1 + (int64_t)c * ldw1 + 2 * n + j), sP[r * K + j], z);
+      sH1[r * ldh + c] = m_tanh(z);
+    }
+    __syncthreads();
+    // ---- 3. h2 = tanh(W2.h1 + b2)
+    gemm_rows<R, RP, 8>(sH1, ldh, H, rows, A.W2, H, 1, H,
+                        [&](int r, int c, R v) { sH2[r * ldh + c] = m_tanh(v + __ldg(A.b2 + c)); });
+    if (BWD) {
+      for (int i = tid; i < rows * ldh; i += kThreads) sG[i] = R(0);
+    }
+    __syncthreads();
+
+    // ---- 4. per d_obs: layer 3, heads, reduction over terms
+    for (int d = 0; d < D; ++d) {
+      const int ja = d * n, jb = (D + d) * n;
+      gemm_rows<R, RP, 8>(sH2, ldh, H, rows, A.W3 + (int64_t)ja * H, H, 1, n,
+                          [&](int r, int c, R v) { sO[r * ldo + c] = v + __ldg(A.b3 + ja + c); });
+      gemm_rows<R, RP, 8>(sH2, ldh, H, rows, A.W3 + (int64_t)jb * H, H, 1, n,
+                          [&](int r, int c, R v) { sO[r * ldo + n + c] = v + __ldg(A.b3 + jb + c); });
+      for (int r = tid; r < RMAX; r += kThreads) {
+        sX[r] = R(0);
+        if (BWD) {
+          R g = row_valid(r) ? A.gx[((int64_t)row_b(r) * A.T + row_t(r)) * D + d] : R(0);
+          sGp[r] = g * sCtx[row_slot(r < rows ? r : 0)].pref;
+        }
+      }
+      __syncthreads();
+
+      if (!dehoog) {
+        R acc[RP];
+#pragma unroll
+        for (int i = 0; i < RP; ++i) acc[i] = R(0);
+        for (int k = warp; k < n; k += kWarps) {
+#pragma unroll
+          for (int i = 0; i < RP; ++i) {
+            const int r = lane + 32 * i;
+            if (r < rows) {
+              HeadOut<R> h = head_forward<R>(P.head, sO[r * ldo + k], sO[r * ldo + n + k]);
+              Cx<R> w;
+              if (fourier_coef) {
+                const int s = row_slot(r);
+                w.re = sCoef[((int64_t)s * n + k) * 2];
+                w.im = sCoef[((int64_t)s * n + k) * 2 + 1];
+              } else {
+                w.re = __ldg(P.eta + 2 * k);
+                w.im = __ldg(P.eta + 2 * k + 1);
+              }
+              if (!BWD) {
+                acc[i] += h.fre * w.re - h.fim * w.im;
+              } else {
+                R g = sGp[r], goa, gob;
+                head_backward<R>(P.head, h, g * w.re, -g * w.im, &goa, &gob);
+                sO[r * ldo + k] = goa;
+                sO[r * ldo + n + k] = gob;
+              }
+            }
+          }
+        }
+        if (!BWD) {
+#pragma unroll
+          for (int i = 0; i < RP; ++i) {
+            const int r = lane + 32 * i;
+            if (r < rows) atomic_add(&sX[r], acc[i]);
+          }
+        }
+      } else {
+        // De Hoog: F -> scratch, one thread per row runs the recurrence, then (bwd) dF -> dO.
+        const int M = (n - 1) / 2;
+        const int ent = dehoog_scratch_entries(n, BWD);
+        for (int k = warp; k < n; k += kWarps) {
+#pragma unroll
+          for (int i = 0; i < RP; ++i) {
+            const int r = lane + 32 * i;
+            if (r < rows) {
+              HeadOut<R> h = head_forward<R>(P.head, sO[r * ldo + k], sO[r * ldo + n + k]);
+              Scratch<R> scr{A.scratch, A.scratch_stride, (int64_t)blockIdx.x * RMAX + r};
+              scr[ent + k] = Cx<R>{h.fre, h.fim};
+            }
+          }
+        }
+        __syncthreads();
+        if (tid < rows) {
+          const int r = tid;
+          Scratch<R> scr{A.scratch, A.scratch_stride, (int64_t)blockIdx.x * RMAX + r};
+          SlotCtx<R> sc = sCtx[row_slot(r)];
+          Cx<R> z{sc.zc, sc.zs};
+          auto a = [&](int k) { return scr[ent + k]; };
+          if (!BWD) {
+            Cx<R> w = dehoog_forward<R>(M, z, a, scr);
+            sX[r] = w.re;
+          } else {
+            auto emit = [&](int k, Cx<R> dw) { scr[ent + n + k] = dw; };
+            if (row_valid(r)) {
+              dehoog_forward_backward<R>(M, z, a, emit, scr);
+            } else {
+              for (int k = 0; k < n; ++k) scr[ent + n + k] = Cx<R>{R(0), R(0)};
+            }
+          }
+        }
+        if (BWD) {
+          __syncthreads();
+          for (int k = warp; k < n; k += kWarps) {
+#pragma unroll
+            for (int i = 0; i < RP; ++i) {
+              const int r = lane + 32 * i;
+              if (r < rows) {
+                HeadOut<R> h = head_forward<R>(P.head, sO[r * ldo + k], sO[r * ldo + n + k]);
+                Scratch<R> scr{A.scratch, A.scratch_stride, (int64_t)blockIdx.x * RMAX + r};
+                Cx<R> dw = scr[ent + n + k];
+                R g = sGp[r], goa, gob;
+                head_backward<R>(P.head, h, g * dw.re, -g * dw.im, &goa, &gob);
+                sO[r * ldo + k] = goa;
+                sO[r * ldo + n + k] = gob;
+              }
+            }
+          }
+        }
+      }
+      __syncthreads();
+
+      if (!BWD) {
+        for (int r = tid; r < rows; r += kThreads) {
+          if (row_valid(r)) A.x[((int64_t)row_b(r) * A.T + row_t(r)) * D + d] = sCtx[row_slot(r)].pref * sX[r];
+        }
+      } else {
+        // dH2 += dO . W3[rows of d]   ;   dW3 / db3 slabs
+        gemm_rows<R, RP, 8>(sO, ldo, n, rows, A.W3 + (int64_t)ja * H, 1, H, H,
+                            [&](int r, int c, R v) { sG[r * ldh + c] += v; });
+        gemm_rows<R, RP, 8>(sO + n, ldo, n, rows, A.W3 + (int64_t)jb * H, 1, H, H,
+                            [&](int r, int c, R v) { sG[r * ldh + c] += v; });
+        gemm_tn_accum<R>(sO, ldo, n, sH2, ldh, H, rows, gW3 + (int64_t)ja * H, H);
+        gemm_tn_accum<R>(sO + n, ldo, n, sH2, ldh, H, rows, gW3 + (int64_t)jb * H, H);
+        colsum_accum<R>(sO, ldo, n, rows, gb3 + ja);
+        colsum_accum<R>(sO + n, ldo, n, rows, gb3 + jb);
+      }
+      __syncthreads();
+    }  // d
+
+    if (BWD) {
+      // ---- 5. layer 2 / layer 1 backward
+      for (int i = tid; i < rows * H; i += kThreads) {
+        int r = i / H, c = i - r * H;
+        R h2 = sH2[r * ldh + c];
+        sG[r * ldh + c] *= (R(1) - h2 * h2);
+      }
+      __syncthreads();
+      gemm_tn_accum<R>(sG, ldh, H, sH1, ldh, H, rows, gW2, H);
+      colsum_accum<R>(sG, ldh, H, rows, gb2);
+      // dz1 -> sH2 (h2 is dead)
+      gemm_rows<R, RP, 8>(sG, ldh, H, rows, A.W2, 1, H, H, [&](int r, int c, R v) {
+        R h1 = sH1[r * ldh + c];
+        sH2[r * ldh + c] = v * (R(1) - h1 * h1);
+      });
+      __syncthreads();
+      R* sZ1 = sH2;
+      colsum_accum<R>(sZ1, ldh, H, rows, gb1);
+      gemm_tn_accum<R>(sZ1, ldh, H, sP, K, K, rows, gW1 + 2 * n, ldw1);
+      for (int i = tid; i < rows * K; i += kThreads) {
+        int r = i / K, j = i - r * K;
+        if (row_valid(r)) {
+          R s = R(0);
+          for (int c = 0; c < H; ++c) s = fma(sZ1[r * ldh + c], __ldg(A.W1 + (int64_t)c * ldw1 + 2 * n + j), s);
+          atomic_add(A.dp + (int64_t)row_b(r) * K + j, s);
+        }
+      }
+      // G1[slot] = sum over the rows of the slot
+      const R* sG1 = sZ1;
+      if (!per_row) {
+        for (int i = tid; i < NS * H; i += kThreads) {
+          int s = i / H, c = i - s * H;
+          R acc = R(0);
+          for (int bb = 0; bb < A.BB; ++bb) acc += sZ1[(s * A.BB + bb) * ldh + c];
+          sS1[s * ldh + c] = acc;
+        }
+        sG1 = sS1;
+      }
+      __syncthreads();
+      for (int kc0 = 0; kc0 < n; kc0 += kKCU) {
+        fill_features(kc0);
+        __syncthreads();
+        const int kc = min(kKCU, n - kc0);
+        gemm_tn_accum<R>(sG1, ldh, H, sU, ldu, kc, NS, gW1 + kc0, ldw1);
+        gemm_tn_accum<R>(sG1, ldh, H, sU + kKCU, ldu, kc, NS, gW1 + n + kc0, ldw1);
+        __syncthreads();
+      }
+    }
+    __syncthreads();
+  }  // tiles
+}
+
+// grads[i] = sum over CTA slabs (deterministic order)
+template <typename R>
+__global__ void reduce_slabs_kernel(const R* __restrict__ slab, int64_t slab_len, int nslabs, R* gW1, R* gb1, R* gW2,
+                                    R* gb2, R* gW3, R* gb3, int64_t nW1, int64_t nb1, int64_t nW2, int64_t nb2,
+                                    int64_t nW3, int64_t nb3) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= slab_len) return;
+  R s = R(0);
+  for (int c = 0; c < nslabs; ++c) s += slab[(int64_t)c * slab_len + i];
+  int64_t o = i;
+  if (o < nW1) { gW1[o] = s; return; }
+  o -= nW1;
+  if (o < nb1) { gb1[o] = s; return; }
+  o -= nb1;
+  if (o < nW2) { gW2[o] = s; return; }
+  o -= nW2;
+  if (o < nb2) { gb2[o] = s; return; }
+  o -= nb2;
+  if (o < nW3) { gW3[o] = s; return; }
+  o -= nW3;
+  if (o < nb3) gb3[o] = s;
+}
+
+// ---------------------------------------------------------------------------------------
+int device_sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+SimtPlan simt_plan(const nl_desc* d, int pass) {
+  SimtPlan pl{};
+  const bool bwd = pass != 0;
+  const size_t rs = d->dtype == NL_F64 ? 8 : 4;
+  if (d->H < 1 || d->H > 256 || d->K < 1 || d->K > 64 || d->n < 1 || d->D < 1) return pl;
+  if (d->family == NL_DEHOOG && (d->n < 3 || d->n % 2 == 0)) return pl;
+  const int ctx_reals = 8;
+  const size_t limit = 227 * 1024;
+  int rp = 0;
+  for (int cand = (d->dtype == NL_F64 ? 1 : 2); cand >= 1; --cand) {
+    SmemLayout L = smem_layout(32 * cand, d->H, d->n, d->K, bwd, d->family == NL_FOURIER, ctx_reals);
+    if (L.total * rs <= limit) {
+      rp = cand;
+      pl.smem = L.total * rs;
+      break;
+    }
+  }
+  if (rp == 0) return pl;
+  const int rmax = 32 * rp;
+  pl.rp = rp;
+  if (d->t_mode == NL_T_PER_ROW || d->B >= rmax) {
+    pl.BB = std::min(d->B, rmax);
+    pl.TT = std::max(1, std::min(d->T, rmax / pl.BB));
+  } else {
+    pl.BB = d->B;
+    pl.TT = std::max(1, std::min(d->T, rmax / pl.BB));
+  }
+  const int64_t nbt = (d->B + pl.BB - 1) / pl.BB, ntt = (d->T + pl.TT - 1) / pl.TT;
+  const int64_t ntiles = nbt * ntt;
+  pl.grid = (int)std::min<int64_t>(ntiles, device_sm_count());
+  if (pl.grid < 1) pl.grid = 1;
+  const int64_t ldw1 = 2 * d->n + d->K;
+  pl.slab_len = (size_t)d->H * ldw1 + d->H + (size_t)d->H * d->H + d->H + (size_t)2 * d->D * d->n * d->H +
+                (size_t)2 * d->D * d->n;
+  size_t ws = 0;
+  if (bwd) ws += align_up(pl.slab_len * rs * pl.grid, 256);
+  if (d->family == NL_DEHOOG)
+    ws += align_up((size_t)(dehoog_scratch_entries(d->n, bwd) + 2 * d->n) * (size_t)pl.grid * rmax * 2 * rs, 256);
+  pl.ws_bytes = ws + 256;
+  pl.ok = 1;
+  return pl;
+}
+
+template <typename R, int RP>
+static cudaError_t launch_rp(const FusedArgs<R>& A, bool bwd, int grid, size_t smem, cudaStream_t st) {
+  cudaError_t e;
+  if (bwd) {
+    e = cudaFuncSetAttribute(fused_simt_kernel<R, RP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    fused_simt_kernel<R, RP, true><<<grid, kThreads, smem, st>>>(A);
+  } else {
+    e = cudaFuncSetAttribute(fused_simt_kernel<R, RP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    fused_simt_kernel<R, RP, false><<<grid, kThreads, smem, st>>>(A);
+  }
+  return cudaGetLastError();
+}
+
+template <typename R>
+cudaError_t launch_fused_simt(const nl_desc* d, bool bwd, const void* p, const void* t, const void* const* weights,
+                              const void* beta, const void* eta, void* x, const void* gx, void* const* grads,
+                              void* ws, cudaStream_t st, int* launches) {
+  SimtPlan pl = simt_plan(d, bwd ? 1 : 0);
+  if (!pl.ok) return cudaErrorInvalidValue;
+  if ((int64_t)d->B * d->T == 0) return cudaSuccess;
+  FusedArgs<R> A{};
+  A.P.family = d->family;
+  A.P.n = d->n;
+  A.P.head = d->head;
+  A.P.alpha = (R)d->alpha;
+  A.P.log_tol = (R)d->log_tol;
+  A.P.scale = (R)d->scale;
+  A.P.beta = (const R*)beta;
+  A.P.eta = (const R*)eta;
+  A.B = d->B; A.T = d->T; A.K = d->K; A.H = d->H; A.D = d->D; A.n = d->n; A.t_mode = d->t_mode;
+  A.BB = pl.BB; A.TT = pl.TT;
+  A.nbt = (d->B + pl.BB - 1) / pl.BB;
+  A.ntt = (d->T + pl.TT - 1) / pl.TT;
+  A.p = (const R*)p; A.t = (const R*)t;
+  A.W1 = (const R*)weights[0]; A.b1 = (const R*)weights[1]; A.W2 = (const R*)weights[2];
+  A.b2 = (const R*)weights[3]; A.W3 = (const R*)weights[4]; A.b3 = (const R*)weights[5];
+  A.x = (R*)x; A.gx = (const R*)gx;
+  unsigned char* w = (unsigned char*)ws;
+  w = (unsigned char*)align_up((size_t)w, 256);
+  cudaError_t e;
+  const int rmax = 32 * pl.rp;
+  if (bwd) {
+    A.slab = (R*)w;
+    A.slab_len = (int64_t)pl.slab_len;
+    size_t bytes = align_up(pl.slab_len * sizeof(R) * pl.grid, 256);
+    e = cudaMemsetAsync(w, 0, bytes, st);
+    if (e != cudaSuccess) return e;
+    w += bytes;
+    A.dp = (R*)grads[6];
+    e = cudaMemsetAsync(A.dp, 0, (size_t)d->B * d->K * sizeof(R), st);
+    if (e != cudaSuccess) return e;
+  }
+  if (d->family == NL_DEHOOG) {
+    A.scratch = (Cx<R>*)w;
+    A.scratch_stride = (int64_t)pl.grid * rmax;
+  }
+  if (pl.rp == 2)
+    e = launch_rp<R, 2>(A, bwd, pl.grid, pl.smem, st);
+  else
+    e = launch_rp<R, 1>(A, bwd, pl.grid, pl.smem, st);
+  if (e != cudaSuccess) return e;
+  if (launches) *launches += 1;
+  if (bwd) {
+    const int64_t ldw1 = 2 * d->n + d->K;
+    const int64_t nW1 = (int64_t)d->H * ldw1, nb1 = d->H, nW2 = (int64_t)d->H * d->H, nb2 = d->H,
+                  nW3 = (int64_t)2 * d->D * d->n * d->H, nb3 = (int64_t)2 * d->D * d->n;
+    int threads = 256;
+    int64_t blocks = ((int64_t)pl.slab_len + threads - 1) / threads;
+    reduce_slabs_kernel<R><<<(unsigned)blocks, threads, 0, st>>>(A.slab, A.slab_len, pl.grid, (R*)grads[0],
+                                                               (R*)grads[1], (R*)grads[2], (R*)grads[3],
+                                                               (R*)grads[4], (R*)grads[5], nW1, nb1, nW2, nb2, nW3,
+                                                               nb3);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (launches) *launches += 1;
+  }
+  return cudaSuccess;
+}
+
+template cudaError_t launch_fused_simt<float>(const nl_desc*, bool, const void*, const void*, const void* const*,
+                                              const void*, const void*, void*, const void*, void* const*, void*,
+                                              cudaStream_t, int*);
+template cudaError_t launch_fused_simt<double>(const nl_desc*, bool, const void*, const void*, const void* const*,
+                                               const void*, const void*, void*, const void*, void* const*, void*,
+                                               cudaStream_t, int*);
+
+}  // namespace nl

@@ -1,0 +1,51 @@
+// Internal launcher declarations shared by the .cu translation units (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/nl_b200.h"
+
+namespace nl {
+
+template <typename R>
+cudaError_t launch_query_points(const nl_desc* d, int64_t rows, const void* t, const void* Tper, const void* beta,
+                                void* s_out, void* feat_out, cudaStream_t st);
+template <typename R>
+cudaError_t launch_sphere(int which, int64_t count, const void* a, const void* b, void* c, void* e, cudaStream_t st);
+template <typename R>
+cudaError_t launch_line_integrate(const nl_desc* d, int layout, bool bwd, const void* fa, const void* fb,
+                                  const void* t, const void* Tper, const void* eta, const void* gx, void* x,
+                                  void* ga, void* gb, cudaStream_t st);
+
+// ---- fused SIMT path (any dtype / family / t_mode; nl_fused_simt.cu) ----
+struct SimtPlan {
+  int ok;            // 0 => shape not supported by the fused SIMT kernels
+  int rp;            // rows per lane (tile rows = 32*rp)
+  int BB, TT;        // tile geometry
+  int grid;          // persistent CTAs
+  size_t smem;       // dynamic shared memory bytes
+  size_t slab_len;   // reals per CTA gradient slab (backward)
+  size_t ws_bytes;   // workspace bytes
+};
+SimtPlan simt_plan(const nl_desc* d, int pass);
+template <typename R>
+cudaError_t launch_fused_simt(const nl_desc* d, bool bwd, const void* p, const void* t, const void* const* weights,
+                              const void* beta, const void* eta, void* x, const void* gx, void* const* grads,
+                              void* ws, cudaStream_t st, int* launches);
+
+// ---- fused tcgen05 path (f32, canonical H=64; nl_fused_tc.cu) ----
+struct TcPlan {
+  int ok;
+  int grid;
+  size_t smem;
+  size_t ws_bytes;
+};
+TcPlan tc_plan(const nl_desc* d, int pass);
+cudaError_t launch_fused_tc(const nl_desc* d, bool bwd, const void* p, const void* t, const void* const* weights,
+                            const void* beta, const void* eta, void* x, const void* gx, void* const* grads, void* ws,
+                            cudaStream_t st, int* launches);
+
+int device_sm_count();
+
+}  // namespace nl

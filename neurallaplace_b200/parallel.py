@@ -1,0 +1,85 @@
+"""Batch-sharded data parallelism for the reconstruction path (one process per GPU).
+
+Every (batch, time) point of ``laplace_reconstruct`` is independent (core.py:112-127 builds the
+MLP input row by row), so the minibatch is sharded over ranks with NO communication in the
+forward pass; ``p`` gradients stay local to the shard.  The backward pass needs exactly one
+exchange: a sum all-reduce of the ``laplace_rep_func`` parameter gradients (12 866 floats = 51 KB
+at d_obs=1 / 33 terms ... 289 184 floats = 1.16 MB at d_obs=16 / 129 terms), done here on ONE
+flat buffer so NCCL sees a single latency-bound message over NVLink / NVSwitch.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_rows, rank=None, world_size=None):
+  """Contiguous [lo, hi) slice of the batch owned by ``rank`` (balanced to within one row)."""
+  if world_size is None:
+    world_size = dist.get_world_size() if dist.is_initialized() else 1
+  if rank is None:
+    rank = dist.get_rank() if dist.is_initialized() else 0
+  base, rem = divmod(n_rows, world_size)
+  lo = rank * base + min(rank, rem)
+  return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_batch(p, t=None, rank=None, world_size=None):
+  """Slice ``p`` (and a per-row ``t``; a shared ``t`` is replicated) for this rank."""
+  lo, hi = shard_range(p.shape[0], rank, world_size)
+  ps = p[lo:hi]
+  if t is not None and t.dim() == 2 and t.shape[0] == p.shape[0] and p.shape[0] != 1:
+    return ps, t[lo:hi]
+  return ps, t
+
+
+class GradientAllReducer:
+  """Sum-all-reduce the gradients of a parameter list through one persistent flat buffer."""
+
+  def __init__(self, params, group=None, average=False):
+    self.params = [q for q in params if q.requires_grad]
+    self.group = group
+    self.average = average
+    self._flat = None
+
+  def _buffer(self):
+    n = sum(q.numel() for q in self.params)
+    ref = self.params[0]
+    if self._flat is None or self._flat.numel() != n or self._flat.device != ref.device or \
+        self._flat.dtype != ref.dtype:
+      self._flat = torch.empty(n, dtype=ref.dtype, device=ref.device)
+    return self._flat
+
+  def __call__(self):
+    if not self.params:
+      return
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+      return
+    flat = self._buffer()
+    off = 0
+    for q in self.params:
+      g = q.grad
+      k = q.numel()
+      if g is None:
+        flat[off:off + k].zero_()
+      else:
+        flat[off:off + k].copy_(g.reshape(-1))
+      off += k
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+    if self.average:
+      flat.div_(dist.get_world_size(self.group))
+    off = 0
+    for q in self.params:
+      k = q.numel()
+      if q.grad is None:
+        q.grad = flat[off:off + k].view_as(q).clone()
+      else:
+        q.grad.copy_(flat[off:off + k].view_as(q))
+      off += k
+
+
+def allreduce_gradients(module_or_params, group=None, average=False):
+  """One-shot helper: all-reduce ``.grad`` of a module's (or an iterable's) parameters."""
+  params = list(module_or_params.parameters()) if isinstance(module_or_params, torch.nn.Module) else list(
+      module_or_params)
+  GradientAllReducer(params, group, average)()

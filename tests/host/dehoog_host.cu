@@ -1,0 +1,65 @@
+// Host-side harness: runs the SAME De Hoog / head device functions the CUDA kernels use, compiled
+// for the CPU, so the recurrence and its hand-written reverse sweep can be checked against the
+// oracle without a GPU (tests/test_host_math.py).
+#include <vector>
+
+#include "../../neurallaplace_b200/csrc/nl_dehoog.cuh"
+
+using namespace nl;
+
+extern "C" {
+
+// a: [n] complex interleaved; returns w (2 doubles) and dw/da_k (n complex interleaved)
+int nlh_dehoog(int n, double zr, double zi, const double* a, double* w_out, double* dw_out, double* w_fwd_only) {
+  const int M = (n - 1) / 2;
+  std::vector<Cx<double>> buf((size_t)dehoog_scratch_entries(n, true) + 8);
+  Scratch<double> scr{buf.data(), 1, 0};
+  auto acc = [&](int k) { return Cx<double>{a[2 * k], a[2 * k + 1]}; };
+  auto emit = [&](int k, Cx<double> g) {
+    dw_out[2 * k] = g.re;
+    dw_out[2 * k + 1] = g.im;
+  };
+  Cx<double> w = dehoog_forward_backward<double>(M, Cx<double>{zr, zi}, acc, emit, scr);
+  w_out[0] = w.re;
+  w_out[1] = w.im;
+  std::vector<Cx<double>> buf2((size_t)dehoog_scratch_entries(n, false) + 8);
+  Scratch<double> scr2{buf2.data(), 1, 0};
+  Cx<double> w2 = dehoog_forward<double>(M, Cx<double>{zr, zi}, acc, scr2);
+  w_fwd_only[0] = w2.re;
+  w_fwd_only[1] = w2.im;
+  return 0;
+}
+
+int nlh_dehoog_f32(int n, float zr, float zi, const float* a, float* w_out) {
+  const int M = (n - 1) / 2;
+  std::vector<Cx<float>> buf((size_t)dehoog_scratch_entries(n, false) + 8);
+  Scratch<float> scr{buf.data(), 1, 0};
+  auto acc = [&](int k) { return Cx<float>{a[2 * k], a[2 * k + 1]}; };
+  Cx<float> w = dehoog_forward<float>(M, Cx<float>{zr, zi}, acc, scr);
+  w_out[0] = w.re;
+  w_out[1] = w.im;
+  return 0;
+}
+
+// head forward/backward:  in (oa, ob, gre, gim) -> out (fre, fim, goa, gob)
+int nlh_head(int head, double oa, double ob, double gre, double gim, double* out) {
+  HeadOut<double> h = head_forward<double>(head, oa, ob);
+  out[0] = h.fre;
+  out[1] = h.fim;
+  head_backward<double>(head, h, gre, gim, &out[2], &out[3]);
+  return 0;
+}
+
+// s point, features and reduction coefficient for (family, k, t)
+int nlh_query(int family, int head, int n, double alpha, double log_tol, double scale, const double* beta,
+              const double* eta, double t, int k, double* out) {
+  IltParams<double> P{family, n, head, alpha, log_tol, scale, beta, eta};
+  TimeCtx<double> c = make_time_ctx<double>(P, t, nullptr, 0);
+  Cx<double> s = s_point(P, c, k);
+  double f0, f1;
+  s_features(P, s, &f0, &f1);
+  Cx<double> w = reduce_coef(P, c, k);
+  out[0] = s.re; out[1] = s.im; out[2] = f0; out[3] = f1; out[4] = w.re; out[5] = w.im; out[6] = c.pref;
+  return 0;
+}
+}
