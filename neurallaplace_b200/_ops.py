@@ -6,6 +6,7 @@ torch is only used for device memory and autograd bookkeeping.
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 
@@ -28,7 +29,8 @@ def _desc(consts, dtype, B=0, T=0, K=1, H=1, D=1, t_mode=0, head=0, impl=0, n=No
   d.t_mode = t_mode
   d.head = head
   d.dtype = _lib.dtype_code(dtype)
-  d.impl = impl
+  # NL_B200_IMPL=simt|tc forces a kernel family (benchmarks / debugging); default: library picks
+  d.impl = impl or {"auto": 0, "simt": 1, "tc": 2}.get(os.environ.get("NL_B200_IMPL", "auto"), 0)
   d.alpha, d.log_tol, d.scale = consts.alpha, consts.log_tol, consts.scale
   return d
 

@@ -191,8 +191,12 @@ def laplace_reconstruct(
     feat = feat.view(1, time_dim, 2 * n).expand(batch_dim, time_dim, 2 * n)
   inputs = torch.cat((feat, pd.view(batch_dim, 1, -1).expand(batch_dim, time_dim, pd.shape[1])), 2)
   a, b = laplace_rep_func(inputs)
-  a = a.reshape(batch_dim, time_dim, recon_dim, n)
-  b = b.reshape(batch_dim, time_dim, recon_dim, n)
+  # like core.py:130 (`sr.view(-1, time_dim, recon_dim, s_terms_dim)`): the leading dimension is
+  # whatever is left, which differs from B when the module's output_dim != recon_dim.
+  a = a.reshape(-1, time_dim, recon_dim, n)
+  b = b.reshape(-1, time_dim, recon_dim, n)
+  if per_row and a.shape[0] != batch_dim:
+    raise ValueError("laplace_rep_func output does not match (batch, time, recon_dim, terms) for per-row times")
   layout = _lib.NL_F_SPHERE_PLANAR if use_sphere_projection else _lib.NL_F_COMPLEX_PLANAR
   x = _ops.line_integrate(consts, a, b, td, None, layout, t_mode)
   return x if home == dev else x.to(home)

@@ -1,0 +1,11 @@
+#!/usr/bin/env bash
+# One GPU visit: smoke, parity tests, short bench.  Everything under a timeout; logs to gpurun_out/.
+set -uo pipefail
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" | tee -a gpurun_out/summary.txt
+timeout 1500 python -m pytest tests -q -m gpu -x --timeout=600 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/summary.txt
+tail -25 gpurun_out/pytest_gpu.log
+timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?" | tee -a gpurun_out/summary.txt
+cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
+tail -8 gpurun_out/smoke.log
