@@ -82,15 +82,18 @@ static int reconstruct(const nl_desc* d, bool bwd, const void* p, const void* t,
   g_launches = 0;
   int s = check_fused(d);
   if (s) return s;
-  if (!p || !t || !weights) return NL_ERR_NULL;
+  const bool empty = (int64_t)d->B * d->T == 0;  // empty tensors legitimately have NULL data pointers
+  if (!weights) return NL_ERR_NULL;
+  if (!empty && (!p || !t)) return NL_ERR_NULL;
   for (int i = 0; i < 6; ++i)
     if (!weights[i]) return NL_ERR_NULL;
   if (d->family == NL_AW && (!beta || !eta)) return NL_ERR_NULL;
   if (bwd) {
-    if (!gx || !grads) return NL_ERR_NULL;
-    for (int i = 0; i < 7; ++i)
+    if (!grads || (!empty && !gx)) return NL_ERR_NULL;
+    for (int i = 0; i < 6; ++i)
       if (!grads[i]) return NL_ERR_NULL;
-  } else if (!x) {
+    if (d->B > 0 && !grads[6]) return NL_ERR_NULL;
+  } else if (!empty && !x) {
     return NL_ERR_NULL;
   }
   const int pass = bwd ? 1 : 0;
@@ -127,6 +130,7 @@ int nl_query_points(const nl_desc* d, int64_t rows, const void* t, const void* T
   int s = check_desc(d);
   if (s) return s;
   if (rows < 0 || d->n < 1) return NL_ERR_SHAPE;
+  if (rows == 0) return NL_OK;
   if (!t) return NL_ERR_NULL;
   if (d->family == NL_AW && !beta) return NL_ERR_NULL;
   cudaError_t e = d->dtype == NL_F64
@@ -144,6 +148,7 @@ static int line_integrate(const nl_desc* d, int layout, bool bwd, const void* fa
   if (d->B < 0 || d->T < 0 || d->D < 1 || d->n < 1) return NL_ERR_SHAPE;
   if (d->family == NL_DEHOOG && (d->n < 3 || d->n % 2 == 0)) return NL_ERR_SHAPE;
   const bool planar = layout != NL_F_COMPLEX_INTERLEAVED;
+  if ((int64_t)d->B * d->T == 0) return NL_OK;
   if (!fa || !t || (planar && !fb)) return NL_ERR_NULL;
   if (d->family == NL_AW && !eta) return NL_ERR_NULL;
   if (bwd ? (!gx || !ga || (planar && !gb)) : !x) return NL_ERR_NULL;

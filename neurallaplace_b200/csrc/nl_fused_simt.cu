@@ -533,13 +533,8 @@ SimtPlan simt_plan(const nl_desc* d, int pass) {
   if (rp == 0) return pl;
   const int rmax = 32 * rp;
   pl.rp = rp;
-  if (d->t_mode == NL_T_PER_ROW || d->B >= rmax) {
-    pl.BB = std::min(d->B, rmax);
-    pl.TT = std::max(1, std::min(d->T, rmax / pl.BB));
-  } else {
-    pl.BB = d->B;
-    pl.TT = std::max(1, std::min(d->T, rmax / pl.BB));
-  }
+  pl.BB = std::max(1, std::min(d->B, rmax));
+  pl.TT = std::max(1, std::min(d->T, rmax / pl.BB));
   const int64_t nbt = (d->B + pl.BB - 1) / pl.BB, ntt = (d->T + pl.TT - 1) / pl.TT;
   const int64_t ntiles = nbt * ntt;
   pl.grid = (int)std::min<int64_t>(ntiles, device_sm_count());
@@ -577,7 +572,19 @@ cudaError_t launch_fused_simt(const nl_desc* d, bool bwd, const void* p, const v
                               void* ws, cudaStream_t st, int* launches) {
   SimtPlan pl = simt_plan(d, bwd ? 1 : 0);
   if (!pl.ok) return cudaErrorInvalidValue;
-  if ((int64_t)d->B * d->T == 0) return cudaSuccess;
+  if ((int64_t)d->B * d->T == 0) {
+    if (bwd) {  // empty batch: every gradient is zero
+      const int64_t ldw1e = 2 * d->n + d->K;
+      const size_t cnt[7] = {(size_t)d->H * ldw1e, (size_t)d->H, (size_t)d->H * d->H, (size_t)d->H,
+                             (size_t)2 * d->D * d->n * d->H, (size_t)2 * d->D * d->n, (size_t)d->B * d->K};
+      for (int i = 0; i < 7; ++i) {
+        if (cnt[i] == 0) continue;
+        cudaError_t e0 = cudaMemsetAsync(grads[i], 0, cnt[i] * sizeof(R), st);
+        if (e0 != cudaSuccess) return e0;
+      }
+    }
+    return cudaSuccess;
+  }
   FusedArgs<R> A{};
   A.P.family = d->family;
   A.P.n = d->n;
