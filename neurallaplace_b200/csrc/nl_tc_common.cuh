@@ -1,0 +1,187 @@
+// tcgen05 / TMEM / mbarrier primitives (inline PTX) and the shared-memory operand layout used by
+// the tensor-core fused kernels.  sm_100a only.
+//
+// Operand layout ("chunk-major", no swizzle): a matrix X[rows][cols] of bf16 is stored as
+//     byte_offset(r, c) = (c / 8) * (ROWS * 16) + r * 16 + (c % 8) * 2
+// i.e. [cols/8][ROWS][8 bf16].  One thread owning row r writes 16-byte pieces -> consecutive
+// threads hit consecutive 16-byte words (conflict-free, vectorised).  The SAME bytes are a valid
+// canonical UMMA operand in two ways (descriptor layout type SWIZZLE_NONE):
+//   * K-major  (MN = r, K = c):  core matrix = 8 rows x 16 B;  LBO = ROWS*16 (next K chunk),
+//                                SBO = 128 (next 8-row group);
+//   * MN-major (MN = c, K = r):  core matrix = 8 k x 16 B;     SBO = ROWS*16 (next 8 MN values),
+//                                LBO = 128 (next 8-k group).
+// so an activation tile feeds both the forward-type GEMM (reduction over its columns) and the
+// weight-gradient GEMM (reduction over its rows) without a transpose.
+//
+// fp32 parity: every operand is split v = hi + lo with hi = bf16(v), lo = bf16(v - hi) and each GEMM
+// runs 3 passes hi*hi + hi*lo + lo*hi with fp32 accumulation in TMEM ("bf16x3"): relative error
+// ~2^-16 per product, measured 1e-5 on x(t) and all gradients (tolerance 1e-4).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nl {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier ---------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+// Bounded wait: a protocol bug must abort the kernel (trap), never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+
+// ---- proxy / tcgen05 fences ----------------------------------------------------------------
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// ---- TMEM allocation (one full warp) ---------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot_in_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// ---- descriptors ---------------------------------------------------------------------------
+// shared-memory matrix descriptor, SWIZZLE_NONE, version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version
+  return d;
+}
+// instruction descriptor: kind::f16, A/B = bf16, D = f32
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// all MMAs issued so far by this thread arrive on `bar` when complete (implies fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---- TMEM loads: lane = 32*(warp%4) + thread-in-warp, N consecutive 32-bit columns ---------------
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- bf16 hi/lo split ------------------------------------------------------------------------
+// packs (v0, v1) -> hi = bf16x2(v0 | v1<<16), lo = bf16x2 of the residuals
+__device__ __forceinline__ void split2(float v0, float v1, uint32_t* hi, uint32_t* lo) {
+  uint32_t h;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(v1), "f"(v0));
+  float h0 = __uint_as_float(h << 16), h1 = __uint_as_float(h & 0xFFFF0000u);
+  float r0 = v0 - h0, r1 = v1 - h1;
+  uint32_t l;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(r1), "f"(r0));
+  *hi = h;
+  *lo = l;
+}
+
+// store 8 consecutive columns [c0, c0+8) of row r (c0 % 8 == 0) into hi / lo operand images
+__device__ __forceinline__ void store_chunk8(unsigned char* img_hi, unsigned char* img_lo, int rows_in_image, int r,
+                                             int c0, const float* v) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) split2(v[2 * i], v[2 * i + 1], &h[i], &l[i]);
+  const size_t off = (size_t)(c0 >> 3) * ((size_t)rows_in_image * 16) + (size_t)r * 16;
+  *reinterpret_cast<uint4*>(img_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(img_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// bytes of one operand image (hi or lo) holding [rows][cols] bf16, cols % 8 == 0
+__host__ __device__ constexpr size_t image_bytes(int rows, int cols) { return (size_t)rows * cols * 2; }
+
+// One GEMM = 3 passes (hi*hi, hi*lo, lo*hi) x ksteps MMAs.  Addresses are 32-bit shared addresses of
+// the hi images; *_lo_off is the byte distance from the hi image to the lo image.
+// a_step / b_step: byte advance of the descriptor start per K step of 16 elements.
+struct GemmOp {
+  uint32_t a_hi, a_lo_off, a_lbo, a_sbo, a_step;
+  uint32_t b_hi, b_lo_off, b_lbo, b_sbo, b_step;
+  uint32_t idesc;
+  int ksteps;
+};
+
+__device__ __forceinline__ void issue_gemm(const GemmOp& g, uint32_t d_tmem, bool accumulate) {
+#pragma unroll 1
+  for (int pass = 0; pass < 3; ++pass) {
+    const uint32_t a0 = g.a_hi + (pass == 2 ? g.a_lo_off : 0);
+    const uint32_t b0 = g.b_hi + (pass == 1 ? g.b_lo_off : 0);
+#pragma unroll 1
+    for (int ks = 0; ks < g.ksteps; ++ks) {
+      const uint64_t ad = make_sdesc(a0 + ks * g.a_step, g.a_lbo, g.a_sbo);
+      const uint64_t bd = make_sdesc(b0 + ks * g.b_step, g.b_lbo, g.b_sbo);
+      umma_bf16(d_tmem, ad, bd, g.idesc, (accumulate || pass > 0 || ks > 0) ? 1u : 0u);
+    }
+  }
+}
+
+// K-major use of an image [rows][cols]: reduction over cols, 16 per step
+__device__ __forceinline__ void operand_kmajor(uint32_t img, uint32_t lo_off, int rows, uint32_t* base,
+                                               uint32_t* lo, uint32_t* lbo, uint32_t* sbo, uint32_t* step) {
+  *base = img; *lo = lo_off; *lbo = rows * 16; *sbo = 128; *step = 2 * rows * 16;
+}
+// MN-major use of the same image: reduction over rows, 16 per step
+__device__ __forceinline__ void operand_mnmajor(uint32_t img, uint32_t lo_off, int rows, uint32_t* base,
+                                                uint32_t* lo, uint32_t* lbo, uint32_t* sbo, uint32_t* step) {
+  *base = img; *lo = lo_off; *lbo = 128; *sbo = rows * 16; *step = 256;
+}
+
+}  // namespace tc
+}  // namespace nl
