@@ -644,6 +644,20 @@ cudaError_t launch_fused_simt(const nl_desc* d, bool bwd, const void* p, const v
   return cudaSuccess;
 }
 
+cudaError_t launch_reduce_slabs_f32(const float* slab, long long slab_len, int nslabs, void* const* grads,
+                                    const nl_desc* d, cudaStream_t st) {
+  const int64_t ldw1 = 2 * d->n + d->K;
+  const int64_t nW1 = (int64_t)d->H * ldw1, nb1 = d->H, nW2 = (int64_t)d->H * d->H, nb2 = d->H,
+                nW3 = (int64_t)2 * d->D * d->n * d->H, nb3 = (int64_t)2 * d->D * d->n;
+  int threads = 256;
+  int64_t blocks = (slab_len + threads - 1) / threads;
+  reduce_slabs_kernel<float><<<(unsigned)blocks, threads, 0, st>>>(slab, slab_len, nslabs, (float*)grads[0],
+                                                                 (float*)grads[1], (float*)grads[2],
+                                                                 (float*)grads[3], (float*)grads[4],
+                                                                 (float*)grads[5], nW1, nb1, nW2, nb2, nW3, nb3);
+  return cudaGetLastError();
+}
+
 template cudaError_t launch_fused_simt<float>(const nl_desc*, bool, const void*, const void*, const void* const*,
                                               const void*, const void*, void*, const void*, void* const*, void*,
                                               cudaStream_t, int*);

@@ -1,10 +1,662 @@
-// tcgen05 / TMEM fused path (placeholder until the tensor-core kernels land).
+// Fused laplace_reconstruct forward / backward on the 5th-gen tensor cores (tcgen05 + TMEM).
+// float32 path of the canonical laplace_rep_func (H = 64) with a shared time grid and the
+// weighted-sum ILT families (Fourier, and every Abate-Whitt table: CME / Euler / Gaver /
+// FixedTablot / Stehfest).  Everything else runs on the SIMT kernels (nl_fused_simt.cu).
+//
+// Work decomposition.  A tile = 128 batch rows at ONE time point, so the s points, their sphere
+// coordinates, the s-part of layer 1 (S1 = W1s.u_t + b1) and the reduction coefficients are
+// CTA-uniform and are regenerated only when the time index changes (every B/128 tiles).  One
+// persistent CTA per SM walks a contiguous range of tiles.  Thread <-> row (TMEM lane); the two
+// warpgroups split the columns.
+//
+// Per tile (forward):  h1 = tanh(S1 + W1p.p)  -> smem (bf16 hi/lo)      [CUDA cores]
+//                      Z2 = h1 . W2^T          -> TMEM                   [tcgen05, bf16x3]
+//                      h2 = tanh(Z2 + b2)      -> smem                   [CUDA cores]
+//      per chunk:      O  = h2 . W3c^T         -> TMEM                   [tcgen05]
+//                      tanh heads, sphere->complex, x += Re(coef * F)    [CUDA cores, registers]
+// Backward recomputes the above and adds, all on the tensor cores with the SAME smem images viewed
+// K-major or MN-major (nl_tc_common.cuh):
+//      dO (registers -> smem);  dH2 += dO . W3c;  dW3c += dO^T . [h2 | 1]   (TMEM-resident across tiles)
+//      Z2g = dH2 (1-h2^2);      dH1  = Z2g . W2;  dW2  += Z2g^T . [h1 | 1 p]
+//      Z1g = dH1 (1-h1^2);      D1  += Z1g^T . [1 p]   (db1 / dW1p / the rank-1 factor of dW1s)
+// Weight-gradient accumulators stay in TMEM for the CTA's whole tile range and are written once to
+// a CTA-private slab; a tiny second kernel reduces the slabs deterministically.  dp uses atomics.
+// The (batch x time x terms x d_obs) complex intermediate only ever exists in registers.
+#include <algorithm>
+
+#include "nl_common.cuh"
 #include "nl_kernels.h"
+#include "nl_tc_common.cuh"
 
 namespace nl {
-TcPlan tc_plan(const nl_desc*, int) { return TcPlan{}; }
-cudaError_t launch_fused_tc(const nl_desc*, bool, const void*, const void*, const void* const*, const void*,
-                            const void*, void*, const void*, void* const*, void*, cudaStream_t, int*) {
-  return cudaErrorNotSupported;
+namespace tc {
+
+constexpr int kH = 64;
+constexpr int kRows = 128;
+constexpr int kEWG = 2;                 // warpgroups splitting the columns of a tile
+constexpr int kThreadsTc = 128 * kEWG;
+constexpr int kColsPerWg = kH / kEWG;   // 32 hidden columns per warpgroup
+constexpr int kH1Cols = 72;             // h1 image: 64 + [1, p_0..p_6]
+constexpr int kH2Cols = 80;             // h2 image: 64 + [1, 0 x 15]
+constexpr int kMaxK = 7;                // latent dim that fits the extra chunk of the h1 image
+
+struct TcArgs {
+  IltParams<float> P;
+  int B, T, K, D, n;
+  int nbt;
+  long long ntiles;
+  int nkc, kc, NP, nch;
+  const float *p, *t, *W1, *b1, *W2, *b2, *W3, *b3;
+  float* x;
+  const float* gx;
+  float* slab;
+  long long slab_len;
+  float* dp;
+};
+
+struct TcSmem {
+  // byte offsets
+  size_t dO, H1, H2, W2, W3, small, total;
+  size_t dO_img, H1_img, H2_img, W2_img, W3_img;  // bytes of ONE (hi or lo) image
+  // float offsets inside `small`
+  int S1b, W1p, b2, b3, coef, u, G1, xacc, misc, nfloats;
+};
+
+__host__ __device__ inline TcSmem tc_smem(bool bwd, int NP, int nch, int n) {
+  TcSmem L;
+  L.dO_img = bwd ? image_bytes(kRows, NP > kH ? NP : kH) : 0;  // also hosts Z2g / Z1g (64 columns)
+  L.H1_img = image_bytes(kRows, bwd ? kH1Cols : kH);
+  L.H2_img = bwd ? image_bytes(kRows, kH2Cols) : 0;
+  L.W2_img = image_bytes(kH, kH);
+  L.W3_img = image_bytes(NP, kH);
+  size_t o = 0;
+  L.dO = o; o += 2 * L.dO_img;
+  L.H1 = o; o += 2 * L.H1_img;
+  L.H2 = o; o += 2 * L.H2_img;
+  L.W2 = o; o += 2 * L.W2_img;
+  L.W3 = o; o += 2 * L.W3_img * nch;
+  L.small = o;
+  int f = 0;
+  L.S1b = f; f += kH;
+  L.W1p = f; f += kH * 8;
+  L.b2 = f; f += kH;
+  L.b3 = f; f += nch * NP;
+  L.coef = f; f += nch * NP;
+  L.u = f; f += 2 * n + 8;
+  L.G1 = f; f += kH * 8;
+  L.xacc = f; f += kEWG * kRows;
+  L.misc = f; f += 16;
+  L.nfloats = f;
+  L.total = o + (size_t)f * 4 + 64;
+  return L;
 }
+
+struct TcTmem {
+  int S, O, dW2, D1, dW3, total;
+};
+__host__ __device__ inline TcTmem tc_tmem(bool bwd, int NP, int nch) {
+  TcTmem t;
+  t.S = 0;
+  t.O = 64;
+  t.dW2 = 64 + NP;
+  t.D1 = t.dW2 + (bwd ? 80 : 0);
+  t.dW3 = t.D1 + (bwd ? 16 : 0);
+  t.total = t.dW3 + (bwd ? 80 * nch : 0);
+  return t;
+}
+
+__device__ __forceinline__ GemmOp make_gemm(uint32_t a_img, uint32_t a_lo_off, int a_rows, int a_mn, uint32_t b_img,
+                                            uint32_t b_lo_off, int b_rows, int b_mn, int M, int N, int Kdim) {
+  GemmOp g;
+  if (a_mn) operand_mnmajor(a_img, a_lo_off, a_rows, &g.a_hi, &g.a_lo_off, &g.a_lbo, &g.a_sbo, &g.a_step);
+  else      operand_kmajor(a_img, a_lo_off, a_rows, &g.a_hi, &g.a_lo_off, &g.a_lbo, &g.a_sbo, &g.a_step);
+  if (b_mn) operand_mnmajor(b_img, b_lo_off, b_rows, &g.b_hi, &g.b_lo_off, &g.b_lbo, &g.b_sbo, &g.b_step);
+  else      operand_kmajor(b_img, b_lo_off, b_rows, &g.b_hi, &g.b_lo_off, &g.b_lbo, &g.b_sbo, &g.b_step);
+  g.idesc = make_idesc_bf16(M, N, a_mn, b_mn);
+  g.ksteps = Kdim / 16;
+  return g;
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(kThreadsTc, 1) fused_tc_kernel(TcArgs A) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar_main;
+  __shared__ __align__(8) uint64_t bar_d1;
+  __shared__ uint32_t tmem_slot;
+
+  const IltParams<float> P = A.P;
+  const int n = A.n, K = A.K, D = A.D, NP = A.NP, nch = A.nch;
+  const TcSmem L = tc_smem(BWD, NP, nch, n);
+  const TcTmem TM = tc_tmem(BWD, NP, nch);
+  unsigned char* dO_hi = smem + L.dO;
+  unsigned char* dO_lo = dO_hi + L.dO_img;
+  unsigned char* H1_hi = smem + L.H1;
+  unsigned char* H1_lo = H1_hi + L.H1_img;
+  unsigned char* H2_hi = BWD ? smem + L.H2 : H1_hi;
+  unsigned char* H2_lo = BWD ? H2_hi + L.H2_img : H1_lo;
+  unsigned char* W2_hi = smem + L.W2;
+  unsigned char* W2_lo = W2_hi + L.W2_img;
+  unsigned char* W3_base = smem + L.W3;
+  float* sf = reinterpret_cast<float*>(smem + L.small);
+  float* sS1b = sf + L.S1b;
+  float* sW1p = sf + L.W1p;
+  float* sb2 = sf + L.b2;
+  float* sb3 = sf + L.b3;
+  float* sCoef = sf + L.coef;
+  float* su = sf + L.u;
+  float* sG1 = sf + L.G1;
+  float* sxacc = sf + L.xacc;
+  float* smisc = sf + L.misc;  // [0] = pref of the current slot
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wg = tid >> 7;        // warpgroup
+  const int r = tid & 127;        // row of the tile == TMEM lane
+  const int ldw1 = 2 * n + K;
+  const int h_rows1 = kRows;      // rows of every activation image
+
+  // ---- prologue: zero smem, weights -> bf16 hi/lo images, TMEM, barriers
+  for (size_t i = tid; i < L.total / 16; i += kThreadsTc) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  if (tid < kH) {
+    for (int c0 = 0; c0 < kH; c0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = __ldg(A.W2 + tid * kH + c0 + i);
+      store_chunk8(W2_hi, W2_lo, kH, tid, c0, v);
+    }
+    sb2[tid] = __ldg(A.b2 + tid);
+    for (int j = 0; j < K; ++j) sW1p[tid * 8 + j] = __ldg(A.W1 + (size_t)tid * ldw1 + 2 * n + j);
+  }
+  for (int idx = tid; idx < nch * NP; idx += kThreadsTc) {
+    const int ch = idx / NP, jj = idx - ch * NP;
+    const int d = ch / A.nkc, k = (ch % A.nkc) * A.kc + (jj >> 1);
+    const bool valid = (jj >> 1) < A.kc && k < n;
+    const int row = ((jj & 1) ? (D + d) : d) * n + k;
+    unsigned char* w_hi = W3_base + (size_t)ch * 2 * L.W3_img;
+    unsigned char* w_lo = w_hi + L.W3_img;
+    for (int c0 = 0; c0 < kH; c0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = valid ? __ldg(A.W3 + (size_t)row * kH + c0 + i) : 0.f;
+      store_chunk8(w_hi, w_lo, NP, jj, c0, v);
+    }
+    sb3[idx] = valid ? __ldg(A.b3 + row) : 0.f;
+  }
+  if (BWD) {
+    // constant "ones" columns: h1 image col 64, h2 image col 64 (bf16 1.0 = 0x3F80 in the hi image)
+    if (tid < kRows) {
+      *reinterpret_cast<uint32_t*>(H2_hi + (size_t)8 * (kRows * 16) + (size_t)tid * 16) = 0x00003F80u;
+    }
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  if (tid == 0) {
+    mbar_init(&bar_main, 1);
+    mbar_init(&bar_d1, 1);
+    fence_mbar_init();
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  uint32_t ph_main = 0, ph_d1 = 0;
+  bool d1_pending = false;
+
+  // ---- GEMM descriptors (shared addresses are CTA constants)
+  const uint32_t aH1 = smem_u32(H1_hi), aH2 = smem_u32(H2_hi), aW2 = smem_u32(W2_hi), adO = smem_u32(dO_hi);
+  const GemmOp gL2 = make_gemm(aH1, (uint32_t)L.H1_img, kRows, 0, aW2, (uint32_t)L.W2_img, kH, 0, 128, kH, kH);
+
+  // ---- tile range of this CTA (contiguous => the time index changes rarely)
+  const long long per = A.ntiles / gridDim.x, rem = A.ntiles % gridDim.x;
+  const long long tile_lo = blockIdx.x * per + min((long long)blockIdx.x, rem);
+  const long long tile_hi = tile_lo + per + (blockIdx.x < rem ? 1 : 0);
+
+  float* slab = BWD ? A.slab + (long long)blockIdx.x * A.slab_len : nullptr;
+  float* gW1 = slab;
+  float* gb1 = gW1 + (long long)kH * ldw1;
+  float* gW2 = gb1 + kH;
+  float* gb2 = gW2 + kH * kH;
+  float* gW3 = gb2 + kH;
+  float* gb3 = gW3 + (long long)2 * D * n * kH;
+
+  int cur_t = -1;
+  bool first_tile = true, first_in_slot = true;
+
+  // flush of the per-slot accumulator D1 = Z1g^T.[1 p]: db1, dW1p and the rank-1 update dW1s += G1 (x) u
+  auto flush_slot = [&]() {
+    if (!BWD || cur_t < 0) return;
+    if (d1_pending) {
+      mbar_wait(&bar_d1, ph_d1);
+      ph_d1 ^= 1;
+      d1_pending = false;
+    }
+    tc_fence_after();
+    if (wg == 0) {
+      float v[8];
+      tmem_ld8(lane_addr + TM.D1, v);
+      tmem_ld_wait();
+      if (lane < 16) {
+        const int c = (warp & 3) * 16 + lane;  // M=64 accumulator: rows 16w..16w+15 in lanes 32w..32w+15
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sG1[c * 8 + i] = v[i];
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+    for (int idx = tid; idx < kH * 2 * n; idx += kThreadsTc) {
+      const int c = idx / (2 * n), k = idx - c * 2 * n;
+      gW1[(long long)c * ldw1 + k] += sG1[c * 8] * su[k];
+    }
+    for (int idx = tid; idx < kH * (1 + K); idx += kThreadsTc) {
+      const int c = idx / (1 + K), j = idx - c * (1 + K);
+      if (j == 0) gb1[c] += sG1[c * 8];
+      else        gW1[(long long)c * ldw1 + 2 * n + (j - 1)] += sG1[c * 8 + j];
+    }
+    __syncthreads();
+  };
+
+  for (long long tile = tile_lo; tile < tile_hi; ++tile) {
+    const int t_idx = (int)(tile / A.nbt);
+    const int b = (int)(tile % A.nbt) * kRows + r;
+    const bool valid = b < A.B;
+
+    // ---- slot context: s points, sphere features, S1 + b1, reduction coefficients
+    if (t_idx != cur_t) {
+      flush_slot();
+      cur_t = t_idx;
+      first_in_slot = true;
+      const TimeCtx<float> c = make_time_ctx<float>(P, __ldg(A.t + t_idx), nullptr, 0);
+      if (tid == 0) smisc[0] = c.pref;
+      for (int k = tid; k < n; k += kThreadsTc) {
+        float f0, f1;
+        s_features(P, s_point(P, c, k), &f0, &f1);
+        su[k] = f0;
+        su[n + k] = f1;
+      }
+      for (int idx = tid; idx < nch * (NP / 2); idx += kThreadsTc) {
+        const int ch = idx / (NP / 2), q = idx - ch * (NP / 2);
+        const int k = (ch % A.nkc) * A.kc + q;
+        Cx<float> w{0.f, 0.f};
+        if (q < A.kc && k < n) w = reduce_coef(P, c, k);
+        sCoef[ch * NP + 2 * q] = w.re;
+        sCoef[ch * NP + 2 * q + 1] = w.im;
+      }
+      __syncthreads();
+      if (tid < kH) {
+        float acc = __ldg(A.b1 + tid);
+        const float* w = A.W1 + (size_t)tid * ldw1;
+        for (int k = 0; k < 2 * n; ++k) acc = fmaf(__ldg(w + k), su[k], acc);
+        sS1b[tid] = acc;
+      }
+      __syncthreads();
+    }
+    const float pref = smisc[0];
+
+    // ---- 1. h1 = tanh(S1b + W1p.p) -> smem
+    float pv[kMaxK];
+#pragma unroll
+    for (int j = 0; j < kMaxK; ++j) pv[j] = (valid && j < K) ? __ldg(A.p + (size_t)b * K + j) : 0.f;
+    float h1[kColsPerWg];
+#pragma unroll
+    for (int i = 0; i < kColsPerWg; ++i) {
+      const int c = wg * kColsPerWg + i;
+      float z = sS1b[c];
+#pragma unroll
+      for (int j = 0; j < kMaxK; ++j)
+        if (j < K) z = fmaf(sW1p[c * 8 + j], pv[j], z);
+      h1[i] = m_tanh(z);
+    }
+    if (BWD && d1_pending) {  // the previous tile's D1 GEMM reads the [1 p] chunk of the h1 image
+      mbar_wait(&bar_d1, ph_d1);
+      ph_d1 ^= 1;
+      d1_pending = false;
+    }
+#pragma unroll
+    for (int i = 0; i < kColsPerWg; i += 8) store_chunk8(H1_hi, H1_lo, h_rows1, r, wg * kColsPerWg + i, &h1[i]);
+    if (BWD && wg == 0) {
+      float q[8];
+      q[0] = valid ? 1.f : 0.f;
+#pragma unroll
+      for (int j = 0; j < kMaxK; ++j) q[1 + j] = pv[j];
+      store_chunk8(H1_hi, H1_lo, h_rows1, r, kH, q);
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+
+    // ---- 2. Z2 = h1 . W2^T
+    if (tid == 0) {
+      tc_fence_after();
+      issue_gemm(gL2, tmem + TM.S, false);
+      umma_commit(&bar_main);
+    }
+    mbar_wait(&bar_main, ph_main);
+    ph_main ^= 1;
+    tc_fence_after();
+
+    // ---- 3. h2 = tanh(Z2 + b2) -> smem
+    float h2[kColsPerWg];
+#pragma unroll
+    for (int i = 0; i < kColsPerWg; i += 16) {
+      float v[16];
+      tmem_ld16(lane_addr + TM.S + wg * kColsPerWg + i, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) h2[i + j] = m_tanh(v[j] + sb2[wg * kColsPerWg + i + j]);
+    }
+#pragma unroll
+    for (int i = 0; i < kColsPerWg; i += 8) store_chunk8(H2_hi, H2_lo, kRows, r, wg * kColsPerWg + i, &h2[i]);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+
+    // ---- 4. chunks of layer 3 + heads + reduction
+    auto issue_L3 = [&](int ch) {
+      const uint32_t w3 = smem_u32(W3_base + (size_t)ch * 2 * L.W3_img);
+      const GemmOp g = make_gemm(aH2, (uint32_t)(BWD ? L.H2_img : L.H1_img), kRows, 0, w3, (uint32_t)L.W3_img, NP, 0,
+                                 128, NP, kH);
+      issue_gemm(g, tmem + TM.O, false);
+    };
+    if (tid == 0) {
+      tc_fence_after();
+      issue_L3(0);
+      umma_commit(&bar_main);
+    }
+    const int cw = NP / kEWG;  // O columns per warpgroup (multiple of 8)
+    float xsum = 0.f;
+    for (int ch = 0; ch < nch; ++ch) {
+      const int d = ch / A.nkc;
+      const bool d_first = (ch % A.nkc) == 0, d_last = (ch % A.nkc) == A.nkc - 1;
+      mbar_wait(&bar_main, ph_main);
+      ph_main ^= 1;
+      tc_fence_after();
+      float g = 0.f;
+      if (BWD) g = valid ? __ldg(A.gx + ((size_t)b * A.T + t_idx) * D + d) * pref : 0.f;
+      if (d_first) xsum = 0.f;
+      const float* cf = sCoef + ch * NP;
+      const float* bb3 = sb3 + ch * NP;
+      for (int c0 = wg * cw; c0 < (wg + 1) * cw; c0 += 8) {
+        float v[8], dv[8];
+        tmem_ld8(lane_addr + TM.O + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c = c0 + 2 * i;
+          HeadOut<float> h = head_forward<float>(P.head, v[2 * i] + bb3[c], v[2 * i + 1] + bb3[c + 1]);
+          const float cr = cf[c], ci = cf[c + 1];
+          if (!BWD) {
+            xsum = fmaf(h.fre, cr, xsum);
+            xsum = fmaf(-h.fim, ci, xsum);
+          } else {
+            head_backward<float>(P.head, h, g * cr, -g * ci, &dv[2 * i], &dv[2 * i + 1]);
+          }
+        }
+        if (BWD) store_chunk8(dO_hi, dO_lo, kRows, r, c0, dv);
+      }
+      if (!BWD) {
+        if (d_last) {
+          sxacc[wg * kRows + r] = xsum;
+        }
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0 && ch + 1 < nch) {
+          tc_fence_after();
+          issue_L3(ch + 1);
+          umma_commit(&bar_main);
+        }
+        if (d_last) {
+          if (wg == 0 && valid) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < kEWG; ++w) s += sxacc[w * kRows + r];
+            A.x[((size_t)b * A.T + t_idx) * D + d] = pref * s;
+          }
+          __syncthreads();
+        }
+      } else {
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+          tc_fence_after();
+          const uint32_t w3 = smem_u32(W3_base + (size_t)ch * 2 * L.W3_img);
+          // dH2 (+)= dO . W3c       (A K-major over the NP columns, B = W3c viewed MN-major)
+          const GemmOp gdh = make_gemm(adO, (uint32_t)L.dO_img, kRows, 0, w3, (uint32_t)L.W3_img, NP, 1, 128, kH, NP);
+          issue_gemm(gdh, tmem + TM.S, ch > 0);
+          // dW3c += dO^T . [h2 | 1] (both MN-major, reduction over the 128 rows; lanes >= NP are scratch)
+          const GemmOp gdw = make_gemm(adO, (uint32_t)L.dO_img, kRows, 1, aH2, (uint32_t)L.H2_img, kRows, 1, 128,
+                                       kH2Cols, kRows);
+          issue_gemm(gdw, tmem + TM.dW3 + 80 * ch, !first_tile);
+          if (ch + 1 < nch) issue_L3(ch + 1);
+          umma_commit(&bar_main);
+        }
+      }
+    }
+
+    if (BWD) {
+      // ---- 5. Z2g = dH2 (1 - h2^2) -> smem (aliases the dO image)
+      mbar_wait(&bar_main, ph_main);
+      ph_main ^= 1;
+      tc_fence_after();
+      float z[kColsPerWg];
+#pragma unroll
+      for (int i = 0; i < kColsPerWg; i += 16) {
+        float v[16];
+        tmem_ld16(lane_addr + TM.S + wg * kColsPerWg + i, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) z[i + j] = v[j] * (1.f - h2[i + j] * h2[i + j]);
+      }
+#pragma unroll
+      for (int i = 0; i < kColsPerWg; i += 8) store_chunk8(dO_hi, dO_lo, kRows, r, wg * kColsPerWg + i, &z[i]);
+      fence_async_smem();
+      tc_fence_before();
+      __syncthreads();
+      // ---- 6. dH1 = Z2g . W2 ;  dW2 += Z2g^T . [h1 | 1 p]
+      if (tid == 0) {
+        tc_fence_after();
+        const GemmOp gdh1 = make_gemm(adO, (uint32_t)L.dO_img, kRows, 0, aW2, (uint32_t)L.W2_img, kH, 1, 128, kH, kH);
+        issue_gemm(gdh1, tmem + TM.S, false);
+        const GemmOp gdw2 = make_gemm(adO, (uint32_t)L.dO_img, kRows, 1, aH1, (uint32_t)L.H1_img, kRows, 1, 64,
+                                      kH1Cols, kRows);
+        issue_gemm(gdw2, tmem + TM.dW2, !first_tile);
+        umma_commit(&bar_main);
+      }
+      mbar_wait(&bar_main, ph_main);
+      ph_main ^= 1;
+      tc_fence_after();
+      // ---- 7. Z1g = dH1 (1 - h1^2) -> smem ; dp
+      float dpv[kMaxK];
+#pragma unroll
+      for (int j = 0; j < kMaxK; ++j) dpv[j] = 0.f;
+#pragma unroll
+      for (int i = 0; i < kColsPerWg; i += 16) {
+        float v[16];
+        tmem_ld16(lane_addr + TM.S + wg * kColsPerWg + i, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float zz = v[j] * (1.f - h1[i + j] * h1[i + j]);
+          z[i + j] = zz;
+          const int c = wg * kColsPerWg + i + j;
+#pragma unroll
+          for (int q = 0; q < kMaxK; ++q)
+            if (q < K) dpv[q] = fmaf(zz, sW1p[c * 8 + q], dpv[q]);
+        }
+      }
+      if (valid) {
+#pragma unroll
+        for (int q = 0; q < kMaxK; ++q)
+          if (q < K) atomicAdd(A.dp + (size_t)b * K + q, dpv[q]);
+      }
+#pragma unroll
+      for (int i = 0; i < kColsPerWg; i += 8) store_chunk8(dO_hi, dO_lo, kRows, r, wg * kColsPerWg + i, &z[i]);
+      fence_async_smem();
+      tc_fence_before();
+      __syncthreads();
+      // ---- 8. D1 (+)= Z1g^T . [1 p]   (M=64, N=8; B = chunk 8 of the h1 image)
+      if (tid == 0) {
+        tc_fence_after();
+        const GemmOp gd1 = make_gemm(adO, (uint32_t)L.dO_img, kRows, 1, aH1 + 8 * (kRows * 16), (uint32_t)L.H1_img,
+                                     kRows, 1, 64, 8, kRows);
+        issue_gemm(gd1, tmem + TM.D1, !first_in_slot);
+        umma_commit(&bar_d1);
+      }
+      d1_pending = true;
+    }
+    first_tile = false;
+    first_in_slot = false;
+  }
+
+  // ---- epilogue: flush the TMEM-resident weight gradients to this CTA's slab
+  if (BWD) {
+    flush_slot();
+    if (tile_hi > tile_lo) {
+      tc_fence_after();
+      // dW3 chunks: lane jj <-> W3 row; columns 0..63 = dW3, column 64 = db3
+      for (int ch = 0; ch < nch; ++ch) {
+        const int d = ch / A.nkc, k = (ch % A.nkc) * A.kc + (r >> 1);
+        const bool ok = (r >> 1) < A.kc && k < n && r < NP;
+        const int row = ((r & 1) ? (D + d) : d) * n + k;
+        for (int i = 0; i < kColsPerWg; i += 16) {
+          float v[16];
+          tmem_ld16(lane_addr + TM.dW3 + 80 * ch + wg * kColsPerWg + i, v);
+          tmem_ld_wait();
+          if (ok)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) gW3[(long long)row * kH + wg * kColsPerWg + i + j] = v[j];
+        }
+        if (wg == 0) {
+          float v[8];
+          tmem_ld8(lane_addr + TM.dW3 + 80 * ch + kH, v);
+          tmem_ld_wait();
+          if (ok) gb3[row] = v[0];
+        }
+      }
+      // dW2: M=64 accumulator
+      {
+        const int j = (warp & 3) * 16 + lane;
+        const bool ok = lane < 16;
+        for (int i = 0; i < kColsPerWg; i += 16) {
+          float v[16];
+          tmem_ld16(lane_addr + TM.dW2 + wg * kColsPerWg + i, v);
+          tmem_ld_wait();
+          if (ok)
+#pragma unroll
+            for (int q = 0; q < 16; ++q) gW2[j * kH + wg * kColsPerWg + i + q] = v[q];
+        }
+        if (wg == 0) {
+          float v[8];
+          tmem_ld8(lane_addr + TM.dW2 + kH, v);
+          tmem_ld_wait();
+          if (ok) gb2[j] = v[0];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace tc
+
+// ---------------------------------------------------------------------------------------------
+static size_t tc_align(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct TcGeom {
+  int nkc, kc, NP, nch;
+};
+static TcGeom tc_geom(const nl_desc* d) {
+  TcGeom g;
+  g.nkc = (2 * d->n + 127) / 128;
+  g.kc = (d->n + g.nkc - 1) / g.nkc;
+  g.NP = (2 * g.kc + 15) / 16 * 16;
+  g.nch = g.nkc * d->D;
+  return g;
+}
+
+TcPlan tc_plan(const nl_desc* d, int pass) {
+  TcPlan pl{};
+  const bool bwd = pass != 0;
+  if (d->dtype != NL_F32 || d->H != tc::kH || d->t_mode != NL_T_SHARED) return pl;
+  if (d->family != NL_FOURIER && d->family != NL_AW) return pl;
+  if (d->K < 1 || d->K > tc::kMaxK || d->n < 1 || d->D < 1) return pl;
+  if ((long long)d->B * d->T <= 0) return pl;
+  // auto mode: tiles are 128 batch rows at one time point; tiny batches waste the tile -> SIMT kernels
+  if (d->impl == 0 && d->B < 64) return pl;
+  const TcGeom g = tc_geom(d);
+  const tc::TcTmem tm = tc::tc_tmem(bwd, g.NP, g.nch);
+  if (tm.total > 512) return pl;
+  const tc::TcSmem L = tc::tc_smem(bwd, g.NP, g.nch, d->n);
+  if (L.total + 1024 > 227 * 1024) return pl;
+  const long long nbt = (d->B + tc::kRows - 1) / tc::kRows;
+  const long long ntiles = nbt * d->T;
+  pl.grid = (int)std::min<long long>(ntiles, device_sm_count());
+  pl.smem = L.total;
+  const long long ldw1 = 2 * d->n + d->K;
+  const size_t slab_len = (size_t)d->H * ldw1 + d->H + (size_t)d->H * d->H + d->H + (size_t)2 * d->D * d->n * d->H +
+                          (size_t)2 * d->D * d->n;
+  pl.ws_bytes = bwd ? tc_align(slab_len * 4 * pl.grid, 256) + 256 : 256;
+  pl.ok = 1;
+  return pl;
+}
+
+cudaError_t launch_reduce_slabs_f32(const float* slab, long long slab_len, int nslabs, void* const* grads,
+                                    const nl_desc* d, cudaStream_t st);
+
+cudaError_t launch_fused_tc(const nl_desc* d, bool bwd, const void* p, const void* t, const void* const* weights,
+                            const void* beta, const void* eta, void* x, const void* gx, void* const* grads, void* ws,
+                            cudaStream_t st, int* launches) {
+  TcPlan pl = tc_plan(d, bwd ? 1 : 0);
+  if (!pl.ok) return cudaErrorInvalidValue;
+  const TcGeom g = tc_geom(d);
+  tc::TcArgs A{};
+  A.P.family = d->family;
+  A.P.n = d->n;
+  A.P.head = d->head;
+  A.P.alpha = (float)d->alpha;
+  A.P.log_tol = (float)d->log_tol;
+  A.P.scale = (float)d->scale;
+  A.P.beta = (const float*)beta;
+  A.P.eta = (const float*)eta;
+  A.B = d->B; A.T = d->T; A.K = d->K; A.D = d->D; A.n = d->n;
+  A.nbt = (d->B + tc::kRows - 1) / tc::kRows;
+  A.ntiles = (long long)A.nbt * d->T;
+  A.nkc = g.nkc; A.kc = g.kc; A.NP = g.NP; A.nch = g.nch;
+  A.p = (const float*)p; A.t = (const float*)t;
+  A.W1 = (const float*)weights[0]; A.b1 = (const float*)weights[1]; A.W2 = (const float*)weights[2];
+  A.b2 = (const float*)weights[3]; A.W3 = (const float*)weights[4]; A.b3 = (const float*)weights[5];
+  A.x = (float*)x; A.gx = (const float*)gx;
+  cudaError_t e;
+  if (bwd) {
+    const long long ldw1 = 2 * d->n + d->K;
+    A.slab_len = (long long)d->H * ldw1 + d->H + (long long)d->H * d->H + d->H + (long long)2 * d->D * d->n * d->H +
+                 (long long)2 * d->D * d->n;
+    A.slab = (float*)tc_align((size_t)ws, 256);
+    e = cudaMemsetAsync(A.slab, 0, (size_t)A.slab_len * 4 * pl.grid, st);
+    if (e != cudaSuccess) return e;
+    A.dp = (float*)grads[6];
+    e = cudaMemsetAsync(A.dp, 0, (size_t)d->B * d->K * 4, st);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(tc::fused_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+    if (e != cudaSuccess) return e;
+    tc::fused_tc_kernel<true><<<pl.grid, tc::kThreadsTc, pl.smem, st>>>(A);
+  } else {
+    e = cudaFuncSetAttribute(tc::fused_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+    if (e != cudaSuccess) return e;
+    tc::fused_tc_kernel<false><<<pl.grid, tc::kThreadsTc, pl.smem, st>>>(A);
+  }
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (launches) *launches += 1;
+  if (bwd) {
+    e = launch_reduce_slabs_f32(A.slab, A.slab_len, pl.grid, grads, d, st);
+    if (e != cudaSuccess) return e;
+    if (launches) *launches += 1;
+  }
+  return cudaSuccess;
+}
+
 }  // namespace nl
