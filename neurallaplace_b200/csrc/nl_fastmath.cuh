@@ -1,0 +1,110 @@
+// MUFU / FMA-pipe evaluation of the laplace_rep_func heads for the tensor-core path.
+//
+// The epilogue (tanh, tanh heads, sphere -> complex, weighted reduction) is the binding unit of the
+// fused kernels (~300 transcendentals against ~17 kFLOP of GEMM per point at d_obs=1,
+// 33 terms), so it is written for instruction count while staying ~1e-6 accurate:
+//   tanh(x)    = 1 - 2/(1 + e^{2x})            ex2.approx + rcp.approx    (abs err ~1e-7)
+//   1 -/+ tanh = 2/(1+E), 2E/(1+E)             relatively accurate near the poles of the sphere
+//   sin, cos   of theta = pi*tanh in (-pi, pi)  sin/cos.approx            (abs err 2^-21)
+//   r = tan(phi/2 + pi/4) = cot(w) or tan(w),  w = (pi/4) * min(1 - tau, 1 + tau) in (0, pi/4]
+//                                               degree-9/8 Taylor on the FMA pipe + one rcp.approx:
+//                                               RELATIVE accuracy ~2e-7 for every r (a MUFU tan
+//                                               would lose it near the pole, where r ~ 1/(1-tau)).
+#pragma once
+#include "nl_common.cuh"
+
+namespace nl {
+namespace fast {
+
+__device__ __forceinline__ float ex2a(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcpa(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sina(float x) {
+  float y;
+  asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float cosa(float x) {
+  float y;
+  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+constexpr float kTwoLog2e = 2.885390081777927f;  // 2 / ln 2
+
+// E = e^{2x} (clamped so that E, 1/(1+E) and E/(1+E) stay normal), D = 1/(1+E)
+__device__ __forceinline__ void exp_pair(float x, float* E, float* Dn) {
+  float t = fminf(fmaxf(x * kTwoLog2e, -100.f), 100.f);
+  *E = ex2a(t);
+  *Dn = rcpa(1.f + *E);
+}
+
+__device__ __forceinline__ float tanh_fast(float x) {
+  float E, Dn;
+  exp_pair(x, &E, &Dn);
+  return fmaf(-2.f, Dn, 1.f);
+}
+
+struct Head {
+  float fre, fim;  // F = r (cos theta + i sin theta)
+  float sn, cs, r;
+  float da, db;    // d theta / d o_a = pi (1 - tau_a^2),  d phi / d o_b = (pi/2)(1 - tau_b^2)
+};
+
+__device__ __forceinline__ Head head_forward(int head, float oa, float ob) {
+  Head h;
+  if (head == NL_HEAD_RAW) {
+    h.fre = oa; h.fim = ob; h.sn = 0.f; h.cs = 0.f; h.r = 0.f; h.da = 1.f; h.db = 1.f;
+    return h;
+  }
+  float Ea, Da, Eb, Db;
+  exp_pair(oa, &Ea, &Da);
+  exp_pair(ob, &Eb, &Db);
+  const float ta = fmaf(-2.f, Da, 1.f);
+  h.da = (float)(4.0 * kPi) * Ea * Da * Da;
+  const float theta = (float)kPi * ta;
+  h.sn = sina(theta);
+  h.cs = cosa(theta);
+  // 1 - tau_b and 1 + tau_b, each relatively accurate; clamp = one float ulp of 1 (tanh saturates there)
+  const float a1 = fmaxf(2.f * Db, 6e-8f);
+  const float b1 = fmaxf(2.f * Eb * Db, 6e-8f);
+  h.db = (float)(0.5 * kPi) * a1 * b1;
+  const float w = (float)(0.25 * kPi) * fminf(a1, b1);
+  const float w2 = w * w;
+  float sw = fmaf(w2, 2.7557319e-6f, -1.9841270e-4f);
+  sw = fmaf(w2, sw, 8.3333333e-3f);
+  sw = fmaf(w2, sw, -1.6666667e-1f);
+  sw = fmaf(w2 * w, sw, w);
+  float cw = fmaf(w2, 2.4801587e-5f, -1.3888889e-3f);
+  cw = fmaf(w2, cw, 4.1666667e-2f);
+  cw = fmaf(w2, cw, -0.5f);
+  cw = fmaf(w2, cw, 1.f);
+  const bool upper = a1 < b1;  // tau_b > 0: r = cot(w) > 1
+  h.r = (upper ? cw : sw) * rcpa(upper ? sw : cw);
+  h.fre = h.r * h.cs;
+  h.fim = h.r * h.sn;
+  return h;
+}
+
+// dL/dF -> dL/d(o_a), dL/d(o_b)
+__device__ __forceinline__ void head_backward(int head, const Head& h, float gre, float gim, float* goa, float* gob) {
+  if (head == NL_HEAD_RAW) {
+    *goa = gre;
+    *gob = gim;
+    return;
+  }
+  const float gtheta = h.r * (gim * h.cs - gre * h.sn);
+  const float gr = gre * h.cs + gim * h.sn;
+  *goa = gtheta * h.da;
+  *gob = gr * fmaf(h.r, h.r, 1.f) * 0.5f * h.db;
+}
+
+}  // namespace fast
+}  // namespace nl

@@ -25,6 +25,7 @@
 #include <algorithm>
 
 #include "nl_common.cuh"
+#include "nl_fastmath.cuh"
 #include "nl_kernels.h"
 #include "nl_tc_common.cuh"
 
@@ -33,9 +34,8 @@ namespace tc {
 
 constexpr int kH = 64;
 constexpr int kRows = 128;
-constexpr int kEWG = 2;                 // warpgroups splitting the columns of a tile
-constexpr int kThreadsTc = 128 * kEWG;
-constexpr int kColsPerWg = kH / kEWG;   // 32 hidden columns per warpgroup
+constexpr int kEwgFwd = 2;  // warpgroups splitting the columns of a tile: forward runs 2 CTAs / SM x 256 threads,
+constexpr int kEwgBwd = 4;  // backward 1 CTA / SM x 512 threads (its shared-memory footprint forbids 2 CTAs)
 constexpr int kH1Cols = 72;             // h1 image: 64 + [1, p_0..p_6]
 constexpr int kH2Cols = 80;             // h2 image: 64 + [1, 0 x 15]
 constexpr int kMaxK = 7;                // latent dim that fits the extra chunk of the h1 image
@@ -84,7 +84,7 @@ __host__ __device__ inline TcSmem tc_smem(bool bwd, int NP, int nch, int n) {
   L.coef = f; f += nch * NP;
   L.u = f; f += 2 * n + 8;
   L.G1 = f; f += kH * 8;
-  L.xacc = f; f += kEWG * kRows;
+  L.xacc = f; f += 4 * kRows;
   L.misc = f; f += 16;
   L.nfloats = f;
   L.total = o + (size_t)f * 4 + 64;
@@ -118,7 +118,11 @@ __device__ __forceinline__ GemmOp make_gemm(uint32_t a_img, uint32_t a_lo_off, i
 }
 
 template <bool BWD>
-__global__ void __launch_bounds__(kThreadsTc, 1) fused_tc_kernel(TcArgs A) {
+__global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 : 2) fused_tc_kernel(TcArgs A) {
+  constexpr int kEWG = BWD ? kEwgBwd : kEwgFwd;
+  constexpr int kThreadsTc = 128 * kEWG;
+  constexpr int kColsPerWg = kH / kEWG;
+  constexpr uint32_t kTmemCols = BWD ? 512 : 256;
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar_main;
   __shared__ __align__(8) uint64_t bar_d1;
@@ -188,7 +192,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) fused_tc_kernel(TcArgs A) {
       *reinterpret_cast<uint32_t*>(H2_hi + (size_t)8 * (kRows * 16) + (size_t)tid * 16) = 0x00003F80u;
     }
   }
-  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  if (warp == 0) tmem_alloc(&tmem_slot, kTmemCols);
   if (tid == 0) {
     mbar_init(&bar_main, 1);
     mbar_init(&bar_d1, 1);
@@ -256,10 +260,33 @@ __global__ void __launch_bounds__(kThreadsTc, 1) fused_tc_kernel(TcArgs A) {
     __syncthreads();
   };
 
+  // software prefetch of the next tile's per-row inputs (p row, upstream gradient) hides their latency
+  constexpr int kGPre = 4;
+  float pv_n[kMaxK], g_n[kGPre];
+  auto prefetch = [&](long long tl) {
+    const int ti = (int)(tl / A.nbt);
+    const int bn = (int)(tl % A.nbt) * kRows + r;
+    const bool ok = bn < A.B;
+#pragma unroll
+    for (int j = 0; j < kMaxK; ++j) pv_n[j] = (ok && j < K) ? __ldg(A.p + (size_t)bn * K + j) : 0.f;
+    if (BWD) {
+#pragma unroll
+      for (int dd = 0; dd < kGPre; ++dd)
+        g_n[dd] = (ok && dd < D) ? __ldg(A.gx + ((size_t)bn * A.T + ti) * D + dd) : 0.f;
+    }
+  };
+  if (tile_lo < tile_hi) prefetch(tile_lo);
+
   for (long long tile = tile_lo; tile < tile_hi; ++tile) {
     const int t_idx = (int)(tile / A.nbt);
     const int b = (int)(tile % A.nbt) * kRows + r;
     const bool valid = b < A.B;
+    float pv[kMaxK], graw[kGPre];
+#pragma unroll
+    for (int j = 0; j < kMaxK; ++j) pv[j] = pv_n[j];
+#pragma unroll
+    for (int dd = 0; dd < kGPre; ++dd) graw[dd] = BWD ? g_n[dd] : 0.f;
+    if (tile + 1 < tile_hi) prefetch(tile + 1);
 
     // ---- slot context: s points, sphere features, S1 + b1, reduction coefficients
     if (t_idx != cur_t) {
@@ -294,9 +321,6 @@ __global__ void __launch_bounds__(kThreadsTc, 1) fused_tc_kernel(TcArgs A) {
     const float pref = smisc[0];
 
     // ---- 1. h1 = tanh(S1b + W1p.p) -> smem
-    float pv[kMaxK];
-#pragma unroll
-    for (int j = 0; j < kMaxK; ++j) pv[j] = (valid && j < K) ? __ldg(A.p + (size_t)b * K + j) : 0.f;
     float h1[kColsPerWg];
 #pragma unroll
     for (int i = 0; i < kColsPerWg; ++i) {
@@ -305,7 +329,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) fused_tc_kernel(TcArgs A) {
 #pragma unroll
       for (int j = 0; j < kMaxK; ++j)
         if (j < K) z = fmaf(sW1p[c * 8 + j], pv[j], z);
-      h1[i] = m_tanh(z);
+      h1[i] = fast::tanh_fast(z);
     }
     if (BWD && d1_pending) {  // the previous tile's D1 GEMM reads the [1 p] chunk of the h1 image
       mbar_wait(&bar_d1, ph_d1);
@@ -343,7 +367,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) fused_tc_kernel(TcArgs A) {
       tmem_ld16(lane_addr + TM.S + wg * kColsPerWg + i, v);
       tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 16; ++j) h2[i + j] = m_tanh(v[j] + sb2[wg * kColsPerWg + i + j]);
+      for (int j = 0; j < 16; ++j) h2[i + j] = fast::tanh_fast(v[j] + sb2[wg * kColsPerWg + i + j]);
     }
 #pragma unroll
     for (int i = 0; i < kColsPerWg; i += 8) store_chunk8(H2_hi, H2_lo, kRows, r, wg * kColsPerWg + i, &h2[i]);
@@ -363,7 +387,10 @@ __global__ void __launch_bounds__(kThreadsTc, 1) fused_tc_kernel(TcArgs A) {
       issue_L3(0);
       umma_commit(&bar_main);
     }
-    const int cw = NP / kEWG;  // O columns per warpgroup (multiple of 8)
+    // O columns per warpgroup: only the real 2*kc columns (rounded to the 4-column group) are evaluated;
+    // the zero padding up to NP exists for the UMMA shape only
+    const int ncols_real = min(NP, (2 * A.kc + 3) & ~3);
+    const int cw = (((ncols_real + kEWG - 1) / kEWG) + 3) & ~3;
     float xsum = 0.f;
     for (int ch = 0; ch < nch; ++ch) {
       const int d = ch / A.nkc;
@@ -372,27 +399,37 @@ __global__ void __launch_bounds__(kThreadsTc, 1) fused_tc_kernel(TcArgs A) {
       ph_main ^= 1;
       tc_fence_after();
       float g = 0.f;
-      if (BWD) g = valid ? __ldg(A.gx + ((size_t)b * A.T + t_idx) * D + d) * pref : 0.f;
+      if (BWD) {
+        float gr = 0.f;
+        if (d < kGPre) {
+#pragma unroll
+          for (int dd = 0; dd < kGPre; ++dd)
+            if (dd == d) gr = graw[dd];
+        } else if (valid) {
+          gr = __ldg(A.gx + ((size_t)b * A.T + t_idx) * D + d);
+        }
+        g = gr * pref;
+      }
       if (d_first) xsum = 0.f;
       const float* cf = sCoef + ch * NP;
       const float* bb3 = sb3 + ch * NP;
-      for (int c0 = wg * cw; c0 < (wg + 1) * cw; c0 += 8) {
-        float v[8], dv[8];
-        tmem_ld8(lane_addr + TM.O + c0, v);
+      for (int c0 = wg * cw; c0 < min((wg + 1) * cw, ncols_real); c0 += 4) {
+        float v[4], dv[4];
+        tmem_ld4(lane_addr + TM.O + c0, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 2; ++i) {
           const int c = c0 + 2 * i;
-          HeadOut<float> h = head_forward<float>(P.head, v[2 * i] + bb3[c], v[2 * i + 1] + bb3[c + 1]);
+          const fast::Head h = fast::head_forward(P.head, v[2 * i] + bb3[c], v[2 * i + 1] + bb3[c + 1]);
           const float cr = cf[c], ci = cf[c + 1];
           if (!BWD) {
             xsum = fmaf(h.fre, cr, xsum);
             xsum = fmaf(-h.fim, ci, xsum);
           } else {
-            head_backward<float>(P.head, h, g * cr, -g * ci, &dv[2 * i], &dv[2 * i + 1]);
+            fast::head_backward(P.head, h, g * cr, -g * ci, &dv[2 * i], &dv[2 * i + 1]);
           }
         }
-        if (BWD) store_chunk8(dO_hi, dO_lo, kRows, r, c0, dv);
+        if (BWD) store_chunk4(dO_hi, dO_lo, kRows, r, c0, dv);
       }
       if (!BWD) {
         if (d_last) {
@@ -557,7 +594,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) fused_tc_kernel(TcArgs A) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 512);
+  if (warp == 0) tmem_dealloc(tmem, kTmemCols);
 }
 
 }  // namespace tc
@@ -588,12 +625,12 @@ TcPlan tc_plan(const nl_desc* d, int pass) {
   if (d->impl == 0 && d->B < 64) return pl;
   const TcGeom g = tc_geom(d);
   const tc::TcTmem tm = tc::tc_tmem(bwd, g.NP, g.nch);
-  if (tm.total > 512) return pl;
+  if (tm.total > (bwd ? 512 : 256)) return pl;
   const tc::TcSmem L = tc::tc_smem(bwd, g.NP, g.nch, d->n);
   if (L.total + 1024 > 227 * 1024) return pl;
   const long long nbt = (d->B + tc::kRows - 1) / tc::kRows;
   const long long ntiles = nbt * d->T;
-  pl.grid = (int)std::min<long long>(ntiles, device_sm_count());
+  pl.grid = (int)std::min<long long>(ntiles, (long long)device_sm_count() * (bwd ? 1 : 2));
   pl.smem = L.total;
   const long long ldw1 = 2 * d->n + d->K;
   const size_t slab_len = (size_t)d->H * ldw1 + d->H + (size_t)d->H * d->H + d->H + (size_t)2 * d->D * d->n * d->H +
@@ -642,11 +679,11 @@ cudaError_t launch_fused_tc(const nl_desc* d, bool bwd, const void* p, const voi
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(tc::fused_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
     if (e != cudaSuccess) return e;
-    tc::fused_tc_kernel<true><<<pl.grid, tc::kThreadsTc, pl.smem, st>>>(A);
+    tc::fused_tc_kernel<true><<<pl.grid, 128 * tc::kEwgBwd, pl.smem, st>>>(A);
   } else {
     e = cudaFuncSetAttribute(tc::fused_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
     if (e != cudaSuccess) return e;
-    tc::fused_tc_kernel<false><<<pl.grid, tc::kThreadsTc, pl.smem, st>>>(A);
+    tc::fused_tc_kernel<false><<<pl.grid, 128 * tc::kEwgFwd, pl.smem, st>>>(A);
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;

@@ -101,6 +101,14 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 }
 
 // ---- TMEM loads: lane = 32*(warp%4) + thread-in-warp, N consecutive 32-bit columns ---------------
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
   uint32_t r[8];
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -143,6 +151,17 @@ __device__ __forceinline__ void store_chunk8(unsigned char* img_hi, unsigned cha
   const size_t off = (size_t)(c0 >> 3) * ((size_t)rows_in_image * 16) + (size_t)r * 16;
   *reinterpret_cast<uint4*>(img_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
   *reinterpret_cast<uint4*>(img_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// store 4 consecutive columns [c0, c0+4) of row r (c0 % 4 == 0): half of a 16-byte piece
+__device__ __forceinline__ void store_chunk4(unsigned char* img_hi, unsigned char* img_lo, int rows_in_image, int r,
+                                             int c0, const float* v) {
+  uint32_t h[2], l[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) split2(v[2 * i], v[2 * i + 1], &h[i], &l[i]);
+  const size_t off = (size_t)(c0 >> 3) * ((size_t)rows_in_image * 16) + (size_t)r * 16 + (size_t)(c0 & 7) * 2;
+  *reinterpret_cast<uint2*>(img_hi + off) = make_uint2(h[0], h[1]);
+  *reinterpret_cast<uint2*>(img_lo + off) = make_uint2(l[0], l[1]);
 }
 
 // bytes of one operand image (hi or lo) holding [rows][cols] bf16, cols % 8 == 0

@@ -1,5 +1,14 @@
 #!/usr/bin/env bash
 set -uo pipefail
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_tc_fused.py -q -m gpu -x -s --timeout=120 > gpurun_out/pytest_tc.log 2>&1; echo "pytest tc rc=$?"
+timeout 600 python -m pytest tests/test_gpu_tc_fused.py tests/test_gpu_tc.py -q -m gpu -x -s --timeout=120 > gpurun_out/pytest_tc.log 2>&1; echo "pytest tc rc=$?"
 grep -E "^\[tc\]|passed|failed|Error|error|assert" gpurun_out/pytest_tc.log | head -40
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_tc.json 2> gpurun_out/bench_tc.err; echo "bench rc=$?"
+python - <<'PY'
+import json
+try:
+    d=json.load(open('gpurun_out/bench_tc.json'))
+    print("value %.1f Mpts/s  ms/step %.3f  fwd %.3f bwd %.3f  e2e %.1f Mpts/s  frac %.4f clocks %s" % (d['value']/1e6, d['ms_per_step'], d['config']['fwd_ms'], d['config']['bwd_ms'], d['e2e']['value']/1e6, d['roofline']['frac'], d['clocks']))
+except Exception as e:
+    print("bench parse failed", e); print(open('gpurun_out/bench_tc.err').read()[-2000:])
+PY
