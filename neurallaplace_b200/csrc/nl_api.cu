@@ -1,6 +1,7 @@
 // C ABI of the library (see include/nl_b200.h for the contract and the reference lines each
 // entry point replaces).  Thin: validate, pick the kernel family, launch on the caller's stream.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "nl_kernels.h"
@@ -32,10 +33,12 @@ int check_fused(const nl_desc* d) {
 }
 
 // 1 = SIMT, 2 = tcgen05, 0 = neither covers the shape
+bool tc_any(const nl_desc* d, int pass) { return nl::tc2_plan(d, pass).ok || nl::tc_plan(d, pass).ok; }
+
 int pick_impl(const nl_desc* d, int pass) {
   if (d->impl == 1) return nl::simt_plan(d, pass).ok ? 1 : 0;
-  if (d->impl == 2) return nl::tc_plan(d, pass).ok ? 2 : 0;
-  if (nl::tc_plan(d, pass).ok) return 2;
+  if (d->impl == 2) return tc_any(d, pass) ? 2 : 0;
+  if (tc_any(d, pass)) return 2;
   if (nl::simt_plan(d, pass).ok) return 1;
   return 0;
 }
@@ -68,6 +71,8 @@ size_t nl_workspace_bytes(const nl_desc* d, int pass) {
   if (sp.ok) a = sp.ws_bytes;
   nl::TcPlan tp = nl::tc_plan(d, pass);
   if (tp.ok) b = tp.ws_bytes;
+  nl::TcPlan tp2 = nl::tc2_plan(d, pass);
+  if (tp2.ok && tp2.ws_bytes > b) b = tp2.ws_bytes;
   return (a > b ? a : b) + 256;
 }
 
@@ -104,7 +109,20 @@ static int reconstruct(const nl_desc* d, bool bwd, const void* p, const void* t,
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
   if (impl == 2) {
-    e = nl::launch_fused_tc(d, bwd, p, t, weights, beta, eta, x, gx, grads, ws, st, &g_launches);
+    // Two tensor-core variants exist (nl_fused_tc.cu: one stream per CTA, nl_fused_tc2.cu: two streams + a
+    // dedicated MMA-issuer warp).  Measured on B200 the two-stream kernel wins for the forward pass and the
+    // one-stream kernel for the backward pass; NL_B200_TC_STREAMS=1|2 forces one of them (profiling).
+    static const int force = [] { const char* v = getenv("NL_B200_TC_STREAMS"); return v ? atoi(v) : 0; }();
+    const bool ok1 = nl::tc_plan(d, pass).ok, ok2 = nl::tc2_plan(d, pass).ok;
+    bool use2 = bwd ? false : true;
+    if (force == 1) use2 = false;
+    if (force == 2) use2 = true;
+    if (use2 && !ok2) use2 = false;
+    if (!use2 && !ok1) use2 = true;
+    if (use2)
+      e = nl::launch_fused_tc2(d, bwd, p, t, weights, beta, eta, x, gx, grads, ws, st, &g_launches);
+    else
+      e = nl::launch_fused_tc(d, bwd, p, t, weights, beta, eta, x, gx, grads, ws, st, &g_launches);
   } else if (d->dtype == NL_F64) {
     e = nl::launch_fused_simt<double>(d, bwd, p, t, weights, beta, eta, x, gx, grads, ws, st, &g_launches);
   } else {

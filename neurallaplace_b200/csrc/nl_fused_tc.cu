@@ -204,8 +204,18 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
   const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  // bar_main: results the epilogue needs next (Z2, O, dH2, dH1).  bar_d1 ("aux"): weight-gradient GEMMs
+  // (dW3, dW2, D1), committed separately so they run behind the epilogue math; it is only waited for
+  // right before the shared-memory images they read are overwritten.
   uint32_t ph_main = 0, ph_d1 = 0;
   bool d1_pending = false;
+  auto wait_aux = [&]() {
+    if (d1_pending) {
+      mbar_wait(&bar_d1, ph_d1);
+      ph_d1 ^= 1;
+      d1_pending = false;
+    }
+  };
 
   // ---- GEMM descriptors (shared addresses are CTA constants)
   const uint32_t aH1 = smem_u32(H1_hi), aH2 = smem_u32(H2_hi), aW2 = smem_u32(W2_hi), adO = smem_u32(dO_hi);
@@ -230,11 +240,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
   // flush of the per-slot accumulator D1 = Z1g^T.[1 p]: db1, dW1p and the rank-1 update dW1s += G1 (x) u
   auto flush_slot = [&]() {
     if (!BWD || cur_t < 0) return;
-    if (d1_pending) {
-      mbar_wait(&bar_d1, ph_d1);
-      ph_d1 ^= 1;
-      d1_pending = false;
-    }
+    wait_aux();
     tc_fence_after();
     if (wg == 0) {
       float v[8];
@@ -331,11 +337,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
         if (j < K) z = fmaf(sW1p[c * 8 + j], pv[j], z);
       h1[i] = fast::tanh_fast(z);
     }
-    if (BWD && d1_pending) {  // the previous tile's D1 GEMM reads the [1 p] chunk of the h1 image
-      mbar_wait(&bar_d1, ph_d1);
-      ph_d1 ^= 1;
-      d1_pending = false;
-    }
+    if (BWD) wait_aux();  // the previous tile's D1 GEMM reads the [1 p] chunk of the h1 image
 #pragma unroll
     for (int i = 0; i < kColsPerWg; i += 8) store_chunk8(H1_hi, H1_lo, h_rows1, r, wg * kColsPerWg + i, &h1[i]);
     if (BWD && wg == 0) {
@@ -397,6 +399,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
       const bool d_first = (ch % A.nkc) == 0, d_last = (ch % A.nkc) == A.nkc - 1;
       mbar_wait(&bar_main, ph_main);
       ph_main ^= 1;
+      if (BWD && ch > 0) wait_aux();  // dW3(ch-1) still reads the dO image
       tc_fence_after();
       float g = 0.f;
       if (BWD) {
@@ -461,13 +464,15 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
           // dH2 (+)= dO . W3c       (A K-major over the NP columns, B = W3c viewed MN-major)
           const GemmOp gdh = make_gemm(adO, (uint32_t)L.dO_img, kRows, 0, w3, (uint32_t)L.W3_img, NP, 1, 128, kH, NP);
           issue_gemm(gdh, tmem + TM.S, ch > 0);
+          if (ch + 1 < nch) issue_L3(ch + 1);
+          umma_commit(&bar_main);
           // dW3c += dO^T . [h2 | 1] (both MN-major, reduction over the 128 rows; lanes >= NP are scratch)
           const GemmOp gdw = make_gemm(adO, (uint32_t)L.dO_img, kRows, 1, aH2, (uint32_t)L.H2_img, kRows, 1, 128,
                                        kH2Cols, kRows);
           issue_gemm(gdw, tmem + TM.dW3 + 80 * ch, !first_tile);
-          if (ch + 1 < nch) issue_L3(ch + 1);
-          umma_commit(&bar_main);
+          umma_commit(&bar_d1);
         }
+        d1_pending = true;
       }
     }
 
@@ -485,6 +490,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
 #pragma unroll
         for (int j = 0; j < 16; ++j) z[i + j] = v[j] * (1.f - h2[i + j] * h2[i + j]);
       }
+      wait_aux();  // dW3 of the last chunk reads the dO image
 #pragma unroll
       for (int i = 0; i < kColsPerWg; i += 8) store_chunk8(dO_hi, dO_lo, kRows, r, wg * kColsPerWg + i, &z[i]);
       fence_async_smem();
@@ -495,11 +501,13 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
         tc_fence_after();
         const GemmOp gdh1 = make_gemm(adO, (uint32_t)L.dO_img, kRows, 0, aW2, (uint32_t)L.W2_img, kH, 1, 128, kH, kH);
         issue_gemm(gdh1, tmem + TM.S, false);
+        umma_commit(&bar_main);
         const GemmOp gdw2 = make_gemm(adO, (uint32_t)L.dO_img, kRows, 1, aH1, (uint32_t)L.H1_img, kRows, 1, 64,
                                       kH1Cols, kRows);
         issue_gemm(gdw2, tmem + TM.dW2, !first_tile);
-        umma_commit(&bar_main);
+        umma_commit(&bar_d1);
       }
+      d1_pending = true;
       mbar_wait(&bar_main, ph_main);
       ph_main ^= 1;
       tc_fence_after();
@@ -527,6 +535,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
         for (int q = 0; q < kMaxK; ++q)
           if (q < K) atomicAdd(A.dp + (size_t)b * K + q, dpv[q]);
       }
+      wait_aux();  // dW2 reads Z2g in the dO image
 #pragma unroll
       for (int i = 0; i < kColsPerWg; i += 8) store_chunk8(dO_hi, dO_lo, kRows, r, wg * kColsPerWg + i, &z[i]);
       fence_async_smem();

@@ -1,0 +1,726 @@
+// Two-stream, warp-specialised variant of the tcgen05 fused kernels (see nl_fused_tc.cu for the math
+// and the operand layouts).  Profiling the single-stream kernel showed its phases are serialised:
+// every warp is in the same phase, so a MUFU-bound phase (tanh), an issue-bound phase (operand
+// split/stores) and the tensor-core phases (a third of the samples sat in mbarrier waits) add up
+// instead of overlapping.  Here one CTA per SM runs
+//     warps 0-7   stream 0  (256 threads: thread <-> row, two warpgroups split the columns)
+//     warps 8-15  stream 1
+//     warp  16    MMA issuer (one elected lane issues every tcgen05.mma of both streams, in order)
+// Each stream walks its own contiguous range of tiles with its own shared-memory images, TMEM
+// accumulators and a ready/done mbarrier pair, so while one stream waits for the tensor core the
+// other one keeps the MUFU / FMA pipes busy.  The weight-gradient accumulators dW2 / dW3 are SHARED
+// by both streams in TMEM (single issuer => accumulation order is well defined) and are written out
+// once per CTA.  h1 and h2 alias one shared-memory image (h1 is re-stored from registers before the
+// layer-2 weight-gradient GEMM), which is what lets two streams fit in 227 KB.
+#include <algorithm>
+
+#include "nl_common.cuh"
+#include "nl_fastmath.cuh"
+#include "nl_kernels.h"
+#include "nl_tc_common.cuh"
+
+namespace nl {
+namespace tc2 {
+
+using namespace nl::tc;
+
+constexpr int kH = 64;
+constexpr int kRows = 128;
+constexpr int kStreams = 2;
+constexpr int kStreamThreads = 256;
+constexpr int kThreads = kStreams * kStreamThreads + 32;
+constexpr int kCols = 32;    // hidden columns per thread (two warpgroups per stream)
+constexpr int kHCols = 80;   // h image: 64 + chunk 8 ([1 p] for h1, [1 0] for h2) + zero chunk 9
+constexpr int kGPre = 4;
+
+struct Args {
+  IltParams<float> P;
+  int B, T, K, D, n;
+  int nbt;
+  long long ntiles;
+  int nkc, kc, NP, nch;
+  const float *p, *t, *W1, *b1, *W2, *b2, *W3, *b3;
+  float* x;
+  const float* gx;
+  float* slab;
+  long long slab_len;
+  float* dp;
+};
+
+struct Smem {
+  size_t dO[kStreams], Hm[kStreams], W2, W3, small, total;
+  size_t dO_img, H_img, W2_img, W3_img;
+  int W1p, b2, b3, per_stream, S1b, coef, u, G1, xacc, misc, nfloats;  // float offsets
+};
+
+__host__ __device__ inline Smem smem_plan(bool bwd, int NP, int nch, int n) {
+  Smem L;
+  L.dO_img = bwd ? image_bytes(kRows, NP > kH ? NP : kH) : 0;
+  L.H_img = image_bytes(kRows, bwd ? kHCols : kH);
+  L.W2_img = image_bytes(kH, kH);
+  L.W3_img = image_bytes(NP, kH);
+  size_t o = 0;
+  for (int s = 0; s < kStreams; ++s) { L.dO[s] = o; o += 2 * L.dO_img; }
+  for (int s = 0; s < kStreams; ++s) { L.Hm[s] = o; o += 2 * L.H_img; }
+  L.W2 = o; o += 2 * L.W2_img;
+  L.W3 = o; o += 2 * L.W3_img * nch;
+  L.small = o;
+  int f = 0;
+  L.W1p = f; f += kH * 8;
+  L.b2 = f; f += kH;
+  L.b3 = f; f += nch * NP;
+  L.per_stream = f;
+  int g = 0;
+  L.S1b = g; g += kH;
+  L.coef = g; g += nch * NP;
+  L.u = g; g += 2 * n + 8;
+  L.G1 = g; g += kH * 8;
+  L.xacc = g; g += 2 * kRows;
+  L.misc = g; g += 8;
+  L.nfloats = g;
+  L.total = o + (size_t)(f + kStreams * g) * 4 + 64;
+  return L;
+}
+
+struct Tmem {
+  int S[kStreams], O[kStreams], D1[kStreams], dW2, dW3, total;
+};
+__host__ __device__ inline Tmem tmem_plan(bool bwd, int NP, int nch) {
+  Tmem t;
+  int c = 0;
+  for (int s = 0; s < kStreams; ++s) { t.S[s] = c; c += 64; }
+  for (int s = 0; s < kStreams; ++s) { t.O[s] = c; c += NP; }
+  for (int s = 0; s < kStreams; ++s) { t.D1[s] = c; c += bwd ? 8 : 0; }
+  t.dW2 = c; c += bwd ? 80 : 0;
+  t.dW3 = c; c += bwd ? 80 * nch : 0;
+  t.total = c;
+  return t;
+}
+
+__device__ __forceinline__ void named_bar(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"  // non-blocking: the issuer polls two streams
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+
+__device__ __forceinline__ GemmOp mk(uint32_t a_img, uint32_t a_lo_off, int a_rows, int a_mn, uint32_t b_img,
+                                     uint32_t b_lo_off, int b_rows, int b_mn, int M, int N, int Kdim) {
+  GemmOp g;
+  if (a_mn) operand_mnmajor(a_img, a_lo_off, a_rows, &g.a_hi, &g.a_lo_off, &g.a_lbo, &g.a_sbo, &g.a_step);
+  else      operand_kmajor(a_img, a_lo_off, a_rows, &g.a_hi, &g.a_lo_off, &g.a_lbo, &g.a_sbo, &g.a_step);
+  if (b_mn) operand_mnmajor(b_img, b_lo_off, b_rows, &g.b_hi, &g.b_lo_off, &g.b_lbo, &g.b_sbo, &g.b_step);
+  else      operand_kmajor(b_img, b_lo_off, b_rows, &g.b_hi, &g.b_lo_off, &g.b_lbo, &g.b_sbo, &g.b_step);
+  g.idesc = make_idesc_bf16(M, N, a_mn, b_mn);
+  g.ksteps = Kdim / 16;
+  return g;
+}
+
+// reload 8 consecutive columns of this thread's row from a hi/lo image pair (v = hi + lo)
+__device__ __forceinline__ void load_chunk8(const unsigned char* img_hi, const unsigned char* img_lo, int rows, int r,
+                                            int c0, float* v) {
+  const size_t off = (size_t)(c0 >> 3) * ((size_t)rows * 16) + (size_t)r * 16;
+  const uint4 h = *reinterpret_cast<const uint4*>(img_hi + off);
+  const uint4 l = *reinterpret_cast<const uint4*>(img_lo + off);
+  const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(hh[i] << 16) + __uint_as_float(ll[i] << 16);
+    v[2 * i + 1] = __uint_as_float(hh[i] & 0xFFFF0000u) + __uint_as_float(ll[i] & 0xFFFF0000u);
+  }
+}
+
+template <bool BWD, int KP>
+__global__ void __launch_bounds__(kThreads, 1) fused_tc2_kernel(Args A) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar_ready[kStreams];
+  __shared__ __align__(8) uint64_t bar_done[kStreams];
+  __shared__ uint32_t tmem_slot;
+
+  const IltParams<float> P = A.P;
+  const int n = A.n, K = A.K, D = A.D, NP = A.NP, nch = A.nch;
+  const Smem L = smem_plan(BWD, NP, nch, n);
+  const Tmem TM = tmem_plan(BWD, NP, nch);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ldw1 = 2 * n + K;
+  float* sf = reinterpret_cast<float*>(smem + L.small);
+  float* sW1p = sf + L.W1p;
+  float* sb2 = sf + L.b2;
+  float* sb3 = sf + L.b3;
+  unsigned char* W2_hi = smem + L.W2;
+  unsigned char* W2_lo = W2_hi + L.W2_img;
+  unsigned char* W3_base = smem + L.W3;
+
+  // ---- prologue (all threads): zero smem, weight images, TMEM, barriers
+  for (size_t i = tid; i < L.total / 16; i += kThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  if (tid < kH) {
+    for (int c0 = 0; c0 < kH; c0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = __ldg(A.W2 + tid * kH + c0 + i);
+      store_chunk8(W2_hi, W2_lo, kH, tid, c0, v);
+    }
+    sb2[tid] = __ldg(A.b2 + tid);
+    for (int j = 0; j < K; ++j) sW1p[tid * 8 + j] = __ldg(A.W1 + (size_t)tid * ldw1 + 2 * n + j);
+  }
+  for (int idx = tid; idx < nch * NP; idx += kThreads) {
+    const int ch = idx / NP, jj = idx - ch * NP;
+    const int d = ch / A.nkc, k = (ch % A.nkc) * A.kc + (jj >> 1);
+    const bool valid = (jj >> 1) < A.kc && k < n;
+    const int row = ((jj & 1) ? (D + d) : d) * n + k;
+    unsigned char* w_hi = W3_base + (size_t)ch * 2 * L.W3_img;
+    unsigned char* w_lo = w_hi + L.W3_img;
+    for (int c0 = 0; c0 < kH; c0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = valid ? __ldg(A.W3 + (size_t)row * kH + c0 + i) : 0.f;
+      store_chunk8(w_hi, w_lo, NP, jj, c0, v);
+    }
+    sb3[idx] = valid ? __ldg(A.b3 + row) : 0.f;
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  if (tid == 0) {
+    for (int s = 0; s < kStreams; ++s) {
+      mbar_init(&bar_ready[s], 1);
+      mbar_init(&bar_done[s], 1);
+    }
+    fence_mbar_init();
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  // ---- tile ranges: CTA range split in two contiguous halves, one per stream
+  const long long per = A.ntiles / gridDim.x, rem = A.ntiles % gridDim.x;
+  const long long cta_lo = blockIdx.x * per + min((long long)blockIdx.x, rem);
+  const long long cta_n = per + (blockIdx.x < rem ? 1 : 0);
+  const long long n0 = (cta_n + 1) / 2;
+  const long long s_lo[kStreams] = {cta_lo, cta_lo + n0};
+  const long long s_n[kStreams] = {n0, cta_n - n0};
+  const int nph = BWD ? 4 + nch : 1 + nch;  // handshakes per tile
+
+  float* slab = BWD ? A.slab + (long long)blockIdx.x * A.slab_len : nullptr;
+  float* gW1 = slab;
+  float* gb1 = gW1 + (long long)kH * ldw1;
+  float* gW2 = gb1 + kH;
+  float* gb2 = gW2 + kH * kH;
+  float* gW3 = gb2 + kH;
+  float* gb3 = gW3 + (long long)2 * D * n * kH;
+
+  if (warp == 2 * kStreamThreads / 32) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      const uint32_t aW2 = smem_u32(W2_hi);
+      uint32_t aH[kStreams], adO[kStreams];
+      for (int s = 0; s < kStreams; ++s) {
+        aH[s] = smem_u32(smem + L.Hm[s]);
+        adO[s] = smem_u32(smem + L.dO[s]);
+      }
+      long long tile_i[kStreams] = {0, 0};
+      int phase[kStreams] = {0, 0};
+      uint32_t par[kStreams] = {0, 0};
+      bool dw2_started = false;
+      uint32_t dw3_started = 0;  // bit per chunk
+      int live = (s_n[0] > 0) + (s_n[1] > 0);
+      int s = 0;
+      uint32_t idle = 0;
+      while (live > 0) {
+        if (tile_i[s] < s_n[s] && mbar_try(&bar_ready[s], par[s])) {
+          idle = 0;
+          par[s] ^= 1;
+          tc_fence_after();
+          const int ph = phase[s];
+          const uint32_t Himg = (uint32_t)L.H_img, dOimg = (uint32_t)L.dO_img, W3img = (uint32_t)L.W3_img;
+          auto issue_L3 = [&](int ch) {
+            const uint32_t w3 = smem_u32(W3_base + (size_t)ch * 2 * L.W3_img);
+            issue_gemm(mk(aH[s], Himg, kRows, 0, w3, W3img, NP, 0, 128, NP, kH), tmem + TM.O[s], false);
+          };
+          if (ph == 0) {
+            issue_gemm(mk(aH[s], Himg, kRows, 0, aW2, (uint32_t)L.W2_img, kH, 0, 128, kH, kH), tmem + TM.S[s], false);
+          } else if (ph == 1) {
+            issue_L3(0);
+          } else if (!BWD) {
+            issue_L3(ph - 1);
+          } else if (ph < 2 + nch) {
+            const int ch = ph - 2;
+            const uint32_t w3 = smem_u32(W3_base + (size_t)ch * 2 * L.W3_img);
+            issue_gemm(mk(adO[s], dOimg, kRows, 0, w3, W3img, NP, 1, 128, kH, NP), tmem + TM.S[s], ch > 0);
+            issue_gemm(mk(adO[s], dOimg, kRows, 1, aH[s], Himg, kRows, 1, 128, kHCols, kRows), tmem + TM.dW3 + 80 * ch,
+                       (dw3_started >> ch) & 1u);
+            dw3_started |= 1u << ch;
+            if (ch + 1 < nch) issue_L3(ch + 1);
+          } else if (ph == 2 + nch) {
+            issue_gemm(mk(adO[s], dOimg, kRows, 0, aW2, (uint32_t)L.W2_img, kH, 1, 128, kH, kH), tmem + TM.S[s], false);
+            issue_gemm(mk(adO[s], dOimg, kRows, 1, aH[s], Himg, kRows, 1, 64, 72, kRows), tmem + TM.dW2, dw2_started);
+            dw2_started = true;
+          } else {
+            // D1 (+)= Z1g^T . [1 p] : accumulate within a time slot
+            const long long tl = s_lo[s] + tile_i[s];
+            const bool first_in_slot = tile_i[s] == 0 || (tl / A.nbt) != ((tl - 1) / A.nbt);
+            issue_gemm(mk(adO[s], dOimg, kRows, 1, aH[s] + 8 * (kRows * 16), Himg, kRows, 1, 64, 8, kRows),
+                       tmem + TM.D1[s], !first_in_slot);
+          }
+          umma_commit(&bar_done[s]);
+          if (++phase[s] == nph) {
+            phase[s] = 0;
+            if (++tile_i[s] == s_n[s]) --live;
+          }
+        } else if (++idle > (1u << 26)) {
+          __trap();  // protocol bug: abort instead of hanging the GPU
+        }
+        s ^= 1;
+      }
+    }
+  } else {
+    // =========================== epilogue streams ===========================
+    const int s = warp / (kStreamThreads / 32);
+    const int stid = tid - s * kStreamThreads;
+    const int wg = stid >> 7;
+    const int r = stid & 127;
+    const int bar_id = 1 + s;
+    unsigned char* dO_hi = smem + L.dO[s];
+    unsigned char* dO_lo = dO_hi + L.dO_img;
+    unsigned char* H_hi = smem + L.Hm[s];
+    unsigned char* H_lo = H_hi + L.H_img;
+    float* ss = sf + L.per_stream + s * L.nfloats;
+    float* sS1b = ss + L.S1b;
+    float* sCoef = ss + L.coef;
+    float* su = ss + L.u;
+    float* sG1 = ss + L.G1;
+    float* sxacc = ss + L.xacc;
+    float* smisc = ss + L.misc;
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    uint32_t pd = 0;        // parity of bar_done[s]
+    bool pending = false;   // a commit we have not waited for yet
+    auto signal_ready = [&]() {
+      fence_async_smem();
+      tc_fence_before();
+      named_bar(bar_id, kStreamThreads);
+      if (stid == 0) mbar_arrive(&bar_ready[s]);
+      pending = true;
+    };
+    auto wait_done = [&]() {
+      mbar_wait(&bar_done[s], pd);
+      pd ^= 1;
+      pending = false;
+      tc_fence_after();
+    };
+
+    int cur_t = -1;
+    auto flush_slot = [&]() {
+      if (!BWD || cur_t < 0) return;
+      if (pending) wait_done();
+      if (wg == 0) {
+        float v[8];
+        tmem_ld8(lane_addr + TM.D1[s], v);
+        tmem_ld_wait();
+        if (lane < 16) {
+          const int c = (warp & 3) * 16 + lane;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) sG1[c * 8 + i] = v[i];
+        }
+      }
+      tc_fence_before();
+      named_bar(bar_id, kStreamThreads);
+      // both streams update the same CTA slab -> atomics (once per time slot, negligible)
+      for (int idx = stid; idx < kH * 2 * n; idx += kStreamThreads) {
+        const int c = idx / (2 * n), k = idx - c * 2 * n;
+        atomicAdd(gW1 + (long long)c * ldw1 + k, sG1[c * 8] * su[k]);
+      }
+      for (int idx = stid; idx < kH * (1 + K); idx += kStreamThreads) {
+        const int c = idx / (1 + K), j = idx - c * (1 + K);
+        if (j == 0) atomicAdd(gb1 + c, sG1[c * 8]);
+        else        atomicAdd(gW1 + (long long)c * ldw1 + 2 * n + (j - 1), sG1[c * 8 + j]);
+      }
+      named_bar(bar_id, kStreamThreads);
+    };
+
+    float pv_n[KP], g_n[kGPre];
+    auto prefetch = [&](long long tl) {
+      const int ti = (int)(tl / A.nbt);
+      const int bn = (int)(tl % A.nbt) * kRows + r;
+      const bool ok = bn < A.B;
+#pragma unroll
+      for (int j = 0; j < KP; ++j) pv_n[j] = (ok && j < K) ? __ldg(A.p + (size_t)bn * K + j) : 0.f;
+      if (BWD) {
+#pragma unroll
+        for (int dd = 0; dd < kGPre; ++dd)
+          g_n[dd] = (ok && dd < D) ? __ldg(A.gx + ((size_t)bn * A.T + ti) * D + dd) : 0.f;
+      }
+    };
+    const long long tile_lo = s_lo[s], tile_hi = s_lo[s] + s_n[s];
+    if (tile_lo < tile_hi) prefetch(tile_lo);
+    const int ncols_real = min(NP, (2 * A.kc + 3) & ~3);
+    const int cw = (((ncols_real + 1) / 2) + 3) & ~3;
+
+    for (long long tile = tile_lo; tile < tile_hi; ++tile) {
+      const int t_idx = (int)(tile / A.nbt);
+      const int b = (int)(tile % A.nbt) * kRows + r;
+      const bool valid = b < A.B;
+      float pv[KP], graw[kGPre];
+#pragma unroll
+      for (int j = 0; j < KP; ++j) pv[j] = pv_n[j];
+#pragma unroll
+      for (int dd = 0; dd < kGPre; ++dd) graw[dd] = BWD ? g_n[dd] : 0.f;
+      if (tile + 1 < tile_hi) prefetch(tile + 1);
+
+      if (t_idx != cur_t) {
+        flush_slot();
+        cur_t = t_idx;
+        const TimeCtx<float> c = make_time_ctx<float>(P, __ldg(A.t + t_idx), nullptr, 0);
+        if (stid == 0) smisc[0] = c.pref;
+        for (int k = stid; k < n; k += kStreamThreads) {
+          float f0, f1;
+          s_features(P, s_point(P, c, k), &f0, &f1);
+          su[k] = f0;
+          su[n + k] = f1;
+        }
+        for (int idx = stid; idx < nch * (NP / 2); idx += kStreamThreads) {
+          const int ch = idx / (NP / 2), q = idx - ch * (NP / 2);
+          const int k = (ch % A.nkc) * A.kc + q;
+          Cx<float> w{0.f, 0.f};
+          if (q < A.kc && k < n) w = reduce_coef(P, c, k);
+          sCoef[ch * NP + 2 * q] = w.re;
+          sCoef[ch * NP + 2 * q + 1] = w.im;
+        }
+        named_bar(bar_id, kStreamThreads);
+        if (stid < kH) {
+          float acc0 = __ldg(A.b1 + stid), acc1 = 0.f;
+          const float* w = A.W1 + (size_t)stid * ldw1;
+          int k = 0;
+          for (; k + 1 < 2 * n; k += 2) {
+            acc0 = fmaf(__ldg(w + k), su[k], acc0);
+            acc1 = fmaf(__ldg(w + k + 1), su[k + 1], acc1);
+          }
+          if (k < 2 * n) acc0 = fmaf(__ldg(w + k), su[k], acc0);
+          sS1b[stid] = acc0 + acc1;
+        }
+        named_bar(bar_id, kStreamThreads);
+      }
+      const float pref = smisc[0];
+
+      // ---- 1. h1 = tanh(S1b + W1p.p)
+      float h1[kCols];
+#pragma unroll
+      for (int i = 0; i < kCols; ++i) {
+        const int c = wg * kCols + i;
+        float z = sS1b[c];
+#pragma unroll
+        for (int j = 0; j < KP; ++j) z = fmaf(sW1p[c * 8 + j], pv[j], z);
+        h1[i] = fast::tanh_fast(z);
+      }
+      if (pending) wait_done();  // previous tile's D1 GEMM still reads this stream's images
+#pragma unroll
+      for (int i = 0; i < kCols; i += 8) store_chunk8(H_hi, H_lo, kRows, r, wg * kCols + i, &h1[i]);
+      signal_ready();  // -> L2
+      wait_done();
+
+      // ---- 3. h2 = tanh(Z2 + b2)
+      {
+        float h2[kCols];
+#pragma unroll
+        for (int i = 0; i < kCols; i += 16) {
+          float v[16];
+          tmem_ld16(lane_addr + TM.S[s] + wg * kCols + i, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) h2[i + j] = fast::tanh_fast(v[j] + sb2[wg * kCols + i + j]);
+        }
+#pragma unroll
+        for (int i = 0; i < kCols; i += 8) store_chunk8(H_hi, H_lo, kRows, r, wg * kCols + i, &h2[i]);
+        if (BWD && wg == 0) {  // chunk 8 of the h2 image = [1 0 0 ...] (column of ones -> db3)
+          const size_t off = (size_t)8 * (kRows * 16) + (size_t)r * 16;
+          *reinterpret_cast<uint4*>(H_hi + off) = make_uint4(0x00003F80u, 0, 0, 0);
+          *reinterpret_cast<uint4*>(H_lo + off) = make_uint4(0, 0, 0, 0);
+        }
+      }
+      signal_ready();  // -> L3(0)
+
+      // ---- 4. chunks
+      float xsum = 0.f;
+      for (int ch = 0; ch < nch; ++ch) {
+        const int d = ch / A.nkc;
+        const bool d_first = (ch % A.nkc) == 0, d_last = (ch % A.nkc) == A.nkc - 1;
+        wait_done();
+        float g = 0.f;
+        if (BWD) {
+          float gr = 0.f;
+          if (d < kGPre) {
+#pragma unroll
+            for (int dd = 0; dd < kGPre; ++dd)
+              if (dd == d) gr = graw[dd];
+          } else if (valid) {
+            gr = __ldg(A.gx + ((size_t)b * A.T + t_idx) * D + d);
+          }
+          g = gr * pref;
+        }
+        if (d_first) xsum = 0.f;
+        const float* cf = sCoef + ch * NP;
+        const float* bb3 = sb3 + ch * NP;
+        for (int c0 = wg * cw; c0 < min((wg + 1) * cw, ncols_real); c0 += 4) {
+          float v[4], dv[4];
+          tmem_ld4(lane_addr + TM.O[s] + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int c = c0 + 2 * i;
+            const fast::Head h = fast::head_forward(P.head, v[2 * i] + bb3[c], v[2 * i + 1] + bb3[c + 1]);
+            const float cr = cf[c], ci = cf[c + 1];
+            if (!BWD) {
+              xsum = fmaf(h.fre, cr, xsum);
+              xsum = fmaf(-h.fim, ci, xsum);
+            } else {
+              fast::head_backward(P.head, h, g * cr, -g * ci, &dv[2 * i], &dv[2 * i + 1]);
+            }
+          }
+          if (BWD) store_chunk4(dO_hi, dO_lo, kRows, r, c0, dv);
+        }
+        if (!BWD) {
+          if (d_last) sxacc[wg * kRows + r] = xsum;
+          if (ch + 1 < nch) {
+            signal_ready();  // O consumed -> L3(ch+1)
+          } else {
+            tc_fence_before();
+            named_bar(bar_id, kStreamThreads);
+          }
+          if (d_last) {
+            if (wg == 0 && valid) A.x[((size_t)b * A.T + t_idx) * D + d] = pref * (sxacc[r] + sxacc[kRows + r]);
+            if (ch + 1 < nch) named_bar(bar_id, kStreamThreads);
+          }
+        } else {
+          signal_ready();  // -> dH2(ch), dW3(ch), L3(ch+1)
+        }
+      }
+
+      if (BWD) {
+        // ---- 5. Z2g = dH2 (1 - h2^2); h1 goes back into the shared h image for the dW2 GEMM
+        wait_done();
+        float z[kCols];
+#pragma unroll
+        for (int i = 0; i < kCols; i += 16) {
+          float v[16];
+          tmem_ld16(lane_addr + TM.S[s] + wg * kCols + i, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 16; q += 8) {
+            float h2v[8];
+            load_chunk8(H_hi, H_lo, kRows, r, wg * kCols + i + q, h2v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) z[i + q + j] = v[q + j] * (1.f - h2v[j] * h2v[j]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < kCols; i += 8) {
+          store_chunk8(dO_hi, dO_lo, kRows, r, wg * kCols + i, &z[i]);
+          store_chunk8(H_hi, H_lo, kRows, r, wg * kCols + i, &h1[i]);
+        }
+        if (wg == 0) {
+          float q[8];
+          q[0] = valid ? 1.f : 0.f;
+#pragma unroll
+          for (int j = 0; j < 7; ++j) q[1 + j] = (j < KP) ? pv[j < KP ? j : 0] : 0.f;
+          store_chunk8(H_hi, H_lo, kRows, r, kH, q);
+        }
+        signal_ready();  // -> dH1, dW2
+        wait_done();
+        // ---- 7. Z1g = dH1 (1 - h1^2) ; dp
+        float dpv[KP];
+#pragma unroll
+        for (int j = 0; j < KP; ++j) dpv[j] = 0.f;
+#pragma unroll
+        for (int i = 0; i < kCols; i += 16) {
+          float v[16];
+          tmem_ld16(lane_addr + TM.S[s] + wg * kCols + i, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float zz = v[j] * (1.f - h1[i + j] * h1[i + j]);
+            z[i + j] = zz;
+            const int c = wg * kCols + i + j;
+#pragma unroll
+            for (int q = 0; q < KP; ++q) dpv[q] = fmaf(zz, sW1p[c * 8 + q], dpv[q]);
+          }
+        }
+        if (valid) {
+#pragma unroll
+          for (int q = 0; q < KP; ++q)
+            if (q < K) atomicAdd(A.dp + (size_t)b * K + q, dpv[q]);
+        }
+#pragma unroll
+        for (int i = 0; i < kCols; i += 8) store_chunk8(dO_hi, dO_lo, kRows, r, wg * kCols + i, &z[i]);
+        signal_ready();  // -> D1 ; waited for at the next tile / slot flush
+      }
+    }
+    flush_slot();
+    if (pending) wait_done();
+  }
+
+  // ---- CTA epilogue: shared weight-gradient accumulators -> slab
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (BWD && cta_n > 0 && warp < 2 * kStreamThreads / 32) {
+    const int s = warp / (kStreamThreads / 32);
+    const int stid = tid - s * kStreamThreads;
+    const int wg = stid >> 7, r = stid & 127;
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    // stream s writes columns [32*(2s+wg), +32) of every accumulator
+    const int cb = (2 * s + wg) * 16;
+    for (int ch = 0; ch < nch; ++ch) {
+      const int d = ch / A.nkc, k = (ch % A.nkc) * A.kc + (r >> 1);
+      const bool ok = (r >> 1) < A.kc && k < n && r < NP;
+      const int row = ((r & 1) ? (D + d) : d) * n + k;
+      float v[16];
+      tmem_ld16(lane_addr + TM.dW3 + 80 * ch + cb, v);
+      tmem_ld_wait();
+      if (ok)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) gW3[(long long)row * kH + cb + j] = v[j];
+      if (s == 0 && wg == 0) {
+        float e[8];
+        tmem_ld8(lane_addr + TM.dW3 + 80 * ch + kH, e);
+        tmem_ld_wait();
+        if (ok) gb3[row] = e[0];
+      }
+    }
+    {
+      const int j = (warp & 3) * 16 + lane;
+      const bool ok = lane < 16;
+      float v[16];
+      tmem_ld16(lane_addr + TM.dW2 + cb, v);
+      tmem_ld_wait();
+      if (ok)
+#pragma unroll
+        for (int q = 0; q < 16; ++q) gW2[j * kH + cb + q] = v[q];
+      if (s == 0 && wg == 0) {
+        float e[8];
+        tmem_ld8(lane_addr + TM.dW2 + kH, e);
+        tmem_ld_wait();
+        if (ok) gb2[j] = e[0];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace tc2
+
+// ---------------------------------------------------------------------------------------------
+struct Tc2Geom {
+  int nkc, kc, NP, nch;
+};
+static Tc2Geom tc2_geom(const nl_desc* d) {
+  Tc2Geom g;
+  g.nkc = (2 * d->n + 127) / 128;
+  g.kc = (d->n + g.nkc - 1) / g.nkc;
+  g.NP = (2 * g.kc + 15) / 16 * 16;
+  g.nch = g.nkc * d->D;
+  return g;
+}
+
+TcPlan tc2_plan(const nl_desc* d, int pass) {
+  TcPlan pl{};
+  const bool bwd = pass != 0;
+  if (d->dtype != NL_F32 || d->H != tc2::kH || d->t_mode != NL_T_SHARED) return pl;
+  if (d->family != NL_FOURIER && d->family != NL_AW) return pl;
+  if (d->K < 1 || d->K > 7 || d->n < 1 || d->D < 1) return pl;
+  if ((long long)d->B * d->T <= 0) return pl;
+  if (d->impl == 0 && d->B < 64) return pl;
+  const Tc2Geom g = tc2_geom(d);
+  if (g.nch > 32) return pl;
+  const tc2::Tmem tm = tc2::tmem_plan(bwd, g.NP, g.nch);
+  if (tm.total > 512) return pl;
+  const tc2::Smem L = tc2::smem_plan(bwd, g.NP, g.nch, d->n);
+  if (L.total + 1024 > 227 * 1024) return pl;
+  const long long nbt = (d->B + tc2::kRows - 1) / tc2::kRows;
+  const long long ntiles = nbt * d->T;
+  pl.grid = (int)std::min<long long>((ntiles + 1) / 2, device_sm_count());
+  if (pl.grid < 1) pl.grid = 1;
+  pl.smem = L.total;
+  const long long ldw1 = 2 * d->n + d->K;
+  const size_t slab_len = (size_t)d->H * ldw1 + d->H + (size_t)d->H * d->H + d->H + (size_t)2 * d->D * d->n * d->H +
+                          (size_t)2 * d->D * d->n;
+  pl.ws_bytes = bwd ? (slab_len * 4 * pl.grid + 255) / 256 * 256 + 256 : 256;
+  pl.ok = 1;
+  return pl;
+}
+
+cudaError_t launch_reduce_slabs_f32(const float* slab, long long slab_len, int nslabs, void* const* grads,
+                                    const nl_desc* d, cudaStream_t st);
+
+template <bool BWD, int KP>
+static cudaError_t launch_tc2_inst(const tc2::Args& A, int grid, size_t smem, cudaStream_t st) {
+  cudaError_t e =
+      cudaFuncSetAttribute(tc2::fused_tc2_kernel<BWD, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  tc2::fused_tc2_kernel<BWD, KP><<<grid, tc2::kThreads, smem, st>>>(A);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fused_tc2(const nl_desc* d, bool bwd, const void* p, const void* t, const void* const* weights,
+                             const void* beta, const void* eta, void* x, const void* gx, void* const* grads, void* ws,
+                             cudaStream_t st, int* launches) {
+  TcPlan pl = tc2_plan(d, bwd ? 1 : 0);
+  if (!pl.ok) return cudaErrorInvalidValue;
+  const Tc2Geom g = tc2_geom(d);
+  tc2::Args A{};
+  A.P.family = d->family;
+  A.P.n = d->n;
+  A.P.head = d->head;
+  A.P.alpha = (float)d->alpha;
+  A.P.log_tol = (float)d->log_tol;
+  A.P.scale = (float)d->scale;
+  A.P.beta = (const float*)beta;
+  A.P.eta = (const float*)eta;
+  A.B = d->B; A.T = d->T; A.K = d->K; A.D = d->D; A.n = d->n;
+  A.nbt = (d->B + tc2::kRows - 1) / tc2::kRows;
+  A.ntiles = (long long)A.nbt * d->T;
+  A.nkc = g.nkc; A.kc = g.kc; A.NP = g.NP; A.nch = g.nch;
+  A.p = (const float*)p; A.t = (const float*)t;
+  A.W1 = (const float*)weights[0]; A.b1 = (const float*)weights[1]; A.W2 = (const float*)weights[2];
+  A.b2 = (const float*)weights[3]; A.W3 = (const float*)weights[4]; A.b3 = (const float*)weights[5];
+  A.x = (float*)x; A.gx = (const float*)gx;
+  cudaError_t e;
+  if (bwd) {
+    const long long ldw1 = 2 * d->n + d->K;
+    A.slab_len = (long long)d->H * ldw1 + d->H + (long long)d->H * d->H + d->H + (long long)2 * d->D * d->n * d->H +
+                 (long long)2 * d->D * d->n;
+    A.slab = (float*)(((size_t)ws + 255) / 256 * 256);
+    e = cudaMemsetAsync(A.slab, 0, (size_t)A.slab_len * 4 * pl.grid, st);
+    if (e != cudaSuccess) return e;
+    A.dp = (float*)grads[6];
+    e = cudaMemsetAsync(A.dp, 0, (size_t)d->B * d->K * 4, st);
+    if (e != cudaSuccess) return e;
+  }
+  const bool small_k = d->K <= 2;
+  if (bwd) e = small_k ? launch_tc2_inst<true, 2>(A, pl.grid, pl.smem, st) : launch_tc2_inst<true, 7>(A, pl.grid, pl.smem, st);
+  else     e = small_k ? launch_tc2_inst<false, 2>(A, pl.grid, pl.smem, st) : launch_tc2_inst<false, 7>(A, pl.grid, pl.smem, st);
+  if (e != cudaSuccess) return e;
+  if (launches) *launches += 1;
+  if (bwd) {
+    e = launch_reduce_slabs_f32(A.slab, A.slab_len, pl.grid, grads, d, st);
+    if (e != cudaSuccess) return e;
+    if (launches) *launches += 1;
+  }
+  return cudaSuccess;
+}
+
+}  // namespace nl

@@ -46,6 +46,12 @@ cudaError_t launch_fused_tc(const nl_desc* d, bool bwd, const void* p, const voi
                             const void* beta, const void* eta, void* x, const void* gx, void* const* grads, void* ws,
                             cudaStream_t st, int* launches);
 
+// two-stream warp-specialised variant (nl_fused_tc2.cu); preferred when its smem / TMEM plan fits
+TcPlan tc2_plan(const nl_desc* d, int pass);
+cudaError_t launch_fused_tc2(const nl_desc* d, bool bwd, const void* p, const void* t, const void* const* weights,
+                             const void* beta, const void* eta, void* x, const void* gx, void* const* grads, void* ws,
+                             cudaStream_t st, int* launches);
+
 int device_sm_count();
 
 }  // namespace nl

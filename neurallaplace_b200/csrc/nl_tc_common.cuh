@@ -178,15 +178,19 @@ struct GemmOp {
 };
 
 __device__ __forceinline__ void issue_gemm(const GemmOp& g, uint32_t d_tmem, bool accumulate) {
+  // descriptors are built once per pass; a K step only bumps the 14-bit start-address field
+  const uint64_t a_inc = (uint64_t)(g.a_step >> 4), b_inc = (uint64_t)(g.b_step >> 4);
+  uint32_t acc = accumulate ? 1u : 0u;
 #pragma unroll 1
   for (int pass = 0; pass < 3; ++pass) {
-    const uint32_t a0 = g.a_hi + (pass == 2 ? g.a_lo_off : 0);
-    const uint32_t b0 = g.b_hi + (pass == 1 ? g.b_lo_off : 0);
-#pragma unroll 1
+    uint64_t ad = make_sdesc(g.a_hi + (pass == 2 ? g.a_lo_off : 0), g.a_lbo, g.a_sbo);
+    uint64_t bd = make_sdesc(g.b_hi + (pass == 1 ? g.b_lo_off : 0), g.b_lbo, g.b_sbo);
+#pragma unroll 4
     for (int ks = 0; ks < g.ksteps; ++ks) {
-      const uint64_t ad = make_sdesc(a0 + ks * g.a_step, g.a_lbo, g.a_sbo);
-      const uint64_t bd = make_sdesc(b0 + ks * g.b_step, g.b_lbo, g.b_sbo);
-      umma_bf16(d_tmem, ad, bd, g.idesc, (accumulate || pass > 0 || ks > 0) ? 1u : 0u);
+      umma_bf16(d_tmem, ad, bd, g.idesc, acc);
+      acc = 1u;
+      ad += a_inc;
+      bd += b_inc;
     }
   }
 }
