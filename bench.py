@@ -130,41 +130,49 @@ def run_reference(a):
 # GPU arm
 # ------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-  """Samples nvidia-smi clocks / throttle reasons for one GPU while the timed region runs."""
-  Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-       "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-       "clocks_event_reasons.sw_power_cap")
+  """Samples SM clock / throttle reasons of one GPU (NVML, ~2 ms period) while the timed region runs."""
+  REASONS = (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("hw_thermal_slowdown", 0x40),
+             ("sw_thermal_slowdown", 0x20))
 
   def __init__(self, index):
     super().__init__(daemon=True)
-    self.index, self.samples, self.stop_flag = index, [], False
+    self.index, self.samples, self.stop_flag, self.active = index, [], False, False
+    self.h = None
+    try:
+      import pynvml
+      pynvml.nvmlInit()
+      self.nv = pynvml
+      self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+      self.max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+    except Exception:  # pylint: disable=broad-except
+      self.h = None
 
   def run(self):
+    if self.h is None:
+      return
+    nv = self.nv
     while not self.stop_flag:
-      try:
-        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                              str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-        if out:
-          self.samples.append([v.strip() for v in out.split(",")])
-      except Exception:  # pylint: disable=broad-except
-        pass
-      time.sleep(0.1)
+      if self.active:
+        try:
+          clk = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+          try:
+            rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+          except Exception:  # pylint: disable=broad-except
+            rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+          self.samples.append((clk, rs))
+        except Exception:  # pylint: disable=broad-except
+          pass
+      time.sleep(0.002)
 
   def summary(self):
-    sm, mx, reasons = [], 0.0, set()
-    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-    for s in self.samples:
-      try:
-        sm.append(float(s[0]))
-        mx = max(mx, float(s[1]))
-        for nm, v in zip(names, s[3:7]):
-          if v.lower().startswith("active"):
-            reasons.add(nm)
-      except (ValueError, IndexError):
-        continue
-    sm.sort()
-    return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-            "samples": len(sm)}
+    sm = sorted(c for c, _ in self.samples)
+    reasons = set()
+    for _, rs in self.samples:
+      for name, bit in self.REASONS:
+        if rs & bit:
+          reasons.add(name)
+    return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": getattr(self, "max", None) if sm else None,
+            "reasons": sorted(reasons), "samples": len(sm)}
 
 
 def run_b200(a):
@@ -223,6 +231,7 @@ def run_b200(a):
   # ---- device-resident timing (value): per-step CUDA events, L2 flushed between steps
   sampler = ClockSampler(local)
   sampler.start()
+  sampler.active = True
   ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
   l0 = _ops.launches()
   barrier()
@@ -233,6 +242,7 @@ def run_b200(a):
     s1.record()
   barrier()
   launches = _ops.launches() - l0
+  sampler.active = False
   sampler.stop_flag = True
   ms_total = sum(s0.elapsed_time(s1) for s0, s1 in ev)
 
@@ -304,6 +314,13 @@ def run_b200(a):
     achieved = dom_fl * pts_rank / (dom_ms * 1e-3) / 1e12
     impl_f = _ops.selected_impl(_consts.get(a.alg, a.terms, dtype), dtype, a.batch, a.time, 2, 64, a.dobs,
                                 1 if a.tmode == "per_row" else 0, 0, 1)
+    traffic = None
+    try:
+      tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+      key = f"{a.alg}_B{a.batch}_T{a.time}_terms{a.terms}_D{a.dobs}_{a.dtype}_{a.tmode}"
+      traffic = tr.get(key, {}).get(dom)
+    except Exception:  # pylint: disable=broad-except
+      pass
     line = {
         "metric": "ILT reconstructed batch*time points/sec fwd+bwd", "value": value, "unit": "points/s",
         "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_total / a.steps,
@@ -318,12 +335,12 @@ def run_b200(a):
         "gpu_launches": launches,
         "clocks": sampler.summary(),
         "roofline": {"bound": "tensor", "kernel": f"fused {dom}", "achieved": achieved, "peak": peak_tf,
-                     "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+                     "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
                      "peak_source": peak_src,
                      "algorithmic_flop_per_point": dom_fl,
                      "hbm_gbs_algorithmic": (8 * a.dobs) * pts_rank / ((fwd_ms + bwd_ms) * 1e-3) / 1e9},
     }
-    if not a.no_cpu_baseline:
+    if not a.no_cpu_baseline and world == 1:  # reported on rank 0 at N=1 only
       rate, ms, cores, sample = cpu_step_rate(a, 2, 1, a.cpu_sample_batch)
       line["cpu_baseline"] = {"value": rate, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample}
     print(json.dumps(line), flush=True)
