@@ -39,17 +39,16 @@ __device__ __forceinline__ float cosa(float x) {
 
 constexpr float kTwoLog2e = 2.885390081777927f;  // 2 / ln 2
 
-// E = e^{2x} (clamped so that E, 1/(1+E) and E/(1+E) stay normal), D = 1/(1+E)
+// E = e^{2x}, D = 1/(1+E).  Only the upper clamp is needed: it keeps E finite so that E*D (= 1 - D) never
+// evaluates inf*0; for x -> -inf, E = 0 and D = 1 are exact.
 __device__ __forceinline__ void exp_pair(float x, float* E, float* Dn) {
-  float t = fminf(fmaxf(x * kTwoLog2e, -100.f), 100.f);
-  *E = ex2a(t);
+  *E = ex2a(fminf(x * kTwoLog2e, 100.f));
   *Dn = rcpa(1.f + *E);
 }
 
+// tanh(x) = 1 - 2/(1+e^{2x}); no clamp at all: E = inf gives D = 0 -> 1, E = 0 gives D = 1 -> -1.
 __device__ __forceinline__ float tanh_fast(float x) {
-  float E, Dn;
-  exp_pair(x, &E, &Dn);
-  return fmaf(-2.f, Dn, 1.f);
+  return fmaf(-2.f, rcpa(1.f + ex2a(x * kTwoLog2e)), 1.f);
 }
 
 struct Head {

@@ -117,7 +117,7 @@ __device__ __forceinline__ GemmOp make_gemm(uint32_t a_img, uint32_t a_lo_off, i
   return g;
 }
 
-template <bool BWD>
+template <bool BWD, int KP>
 __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 : 2) fused_tc_kernel(TcArgs A) {
   constexpr int kEWG = BWD ? kEwgBwd : kEwgFwd;
   constexpr int kThreadsTc = 128 * kEWG;
@@ -268,13 +268,13 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
 
   // software prefetch of the next tile's per-row inputs (p row, upstream gradient) hides their latency
   constexpr int kGPre = 4;
-  float pv_n[kMaxK], g_n[kGPre];
+  float pv_n[KP], g_n[kGPre];
   auto prefetch = [&](long long tl) {
     const int ti = (int)(tl / A.nbt);
     const int bn = (int)(tl % A.nbt) * kRows + r;
     const bool ok = bn < A.B;
 #pragma unroll
-    for (int j = 0; j < kMaxK; ++j) pv_n[j] = (ok && j < K) ? __ldg(A.p + (size_t)bn * K + j) : 0.f;
+    for (int j = 0; j < KP; ++j) pv_n[j] = (ok && j < K) ? __ldg(A.p + (size_t)bn * K + j) : 0.f;
     if (BWD) {
 #pragma unroll
       for (int dd = 0; dd < kGPre; ++dd)
@@ -287,9 +287,9 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
     const int t_idx = (int)(tile / A.nbt);
     const int b = (int)(tile % A.nbt) * kRows + r;
     const bool valid = b < A.B;
-    float pv[kMaxK], graw[kGPre];
+    float pv[KP], graw[kGPre];
 #pragma unroll
-    for (int j = 0; j < kMaxK; ++j) pv[j] = pv_n[j];
+    for (int j = 0; j < KP; ++j) pv[j] = pv_n[j];
 #pragma unroll
     for (int dd = 0; dd < kGPre; ++dd) graw[dd] = BWD ? g_n[dd] : 0.f;
     if (tile + 1 < tile_hi) prefetch(tile + 1);
@@ -333,8 +333,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
       const int c = wg * kColsPerWg + i;
       float z = sS1b[c];
 #pragma unroll
-      for (int j = 0; j < kMaxK; ++j)
-        if (j < K) z = fmaf(sW1p[c * 8 + j], pv[j], z);
+      for (int j = 0; j < KP; ++j) z = fmaf(sW1p[c * 8 + j], pv[j], z);
       h1[i] = fast::tanh_fast(z);
     }
     if (BWD) wait_aux();  // the previous tile's D1 GEMM reads the [1 p] chunk of the h1 image
@@ -344,7 +343,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
       float q[8];
       q[0] = valid ? 1.f : 0.f;
 #pragma unroll
-      for (int j = 0; j < kMaxK; ++j) q[1 + j] = pv[j];
+      for (int j = 0; j < kMaxK; ++j) q[1 + j] = (j < KP) ? pv[j < KP ? j : 0] : 0.f;
       store_chunk8(H1_hi, H1_lo, h_rows1, r, kH, q);
     }
     fence_async_smem();
@@ -512,9 +511,9 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
       ph_main ^= 1;
       tc_fence_after();
       // ---- 7. Z1g = dH1 (1 - h1^2) -> smem ; dp
-      float dpv[kMaxK];
+      float dpv[KP];
 #pragma unroll
-      for (int j = 0; j < kMaxK; ++j) dpv[j] = 0.f;
+      for (int j = 0; j < KP; ++j) dpv[j] = 0.f;
 #pragma unroll
       for (int i = 0; i < kColsPerWg; i += 16) {
         float v[16];
@@ -526,13 +525,12 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
           z[i + j] = zz;
           const int c = wg * kColsPerWg + i + j;
 #pragma unroll
-          for (int q = 0; q < kMaxK; ++q)
-            if (q < K) dpv[q] = fmaf(zz, sW1p[c * 8 + q], dpv[q]);
+          for (int q = 0; q < KP; ++q) dpv[q] = fmaf(zz, sW1p[c * 8 + q], dpv[q]);
         }
       }
       if (valid) {
 #pragma unroll
-        for (int q = 0; q < kMaxK; ++q)
+        for (int q = 0; q < KP; ++q)
           if (q < K) atomicAdd(A.dp + (size_t)b * K + q, dpv[q]);
       }
       wait_aux();  // dW2 reads Z2g in the dO image
@@ -652,6 +650,15 @@ TcPlan tc_plan(const nl_desc* d, int pass) {
 cudaError_t launch_reduce_slabs_f32(const float* slab, long long slab_len, int nslabs, void* const* grads,
                                     const nl_desc* d, cudaStream_t st);
 
+template <bool BWD, int KP>
+static cudaError_t launch_tc1(const tc::TcArgs& A, int grid, size_t smem, cudaStream_t st) {
+  cudaError_t e =
+      cudaFuncSetAttribute(tc::fused_tc_kernel<BWD, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  tc::fused_tc_kernel<BWD, KP><<<grid, 128 * (BWD ? tc::kEwgBwd : tc::kEwgFwd), smem, st>>>(A);
+  return cudaSuccess;
+}
+
 cudaError_t launch_fused_tc(const nl_desc* d, bool bwd, const void* p, const void* t, const void* const* weights,
                             const void* beta, const void* eta, void* x, const void* gx, void* const* grads, void* ws,
                             cudaStream_t st, int* launches) {
@@ -686,14 +693,11 @@ cudaError_t launch_fused_tc(const nl_desc* d, bool bwd, const void* p, const voi
     A.dp = (float*)grads[6];
     e = cudaMemsetAsync(A.dp, 0, (size_t)d->B * d->K * 4, st);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(tc::fused_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
-    if (e != cudaSuccess) return e;
-    tc::fused_tc_kernel<true><<<pl.grid, 128 * tc::kEwgBwd, pl.smem, st>>>(A);
+    e = d->K <= 2 ? launch_tc1<true, 2>(A, pl.grid, pl.smem, st) : launch_tc1<true, tc::kMaxK>(A, pl.grid, pl.smem, st);
   } else {
-    e = cudaFuncSetAttribute(tc::fused_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
-    if (e != cudaSuccess) return e;
-    tc::fused_tc_kernel<false><<<pl.grid, 128 * tc::kEwgFwd, pl.smem, st>>>(A);
+    e = d->K <= 2 ? launch_tc1<false, 2>(A, pl.grid, pl.smem, st) : launch_tc1<false, tc::kMaxK>(A, pl.grid, pl.smem, st);
   }
+  if (e != cudaSuccess) return e;
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (launches) *launches += 1;
