@@ -190,6 +190,10 @@ def run_b200(a):
   if world > 1:
     dist.init_process_group("nccl", device_id=dev)
   _lib.require_cuda()
+  if a.alg == "cme":  # the reference's CME table is not redistributable: synthetic table of the same schema
+    from neurallaplace_b200 import _iltcme
+    from oracle import nl_oracle as orc
+    _iltcme.set_table(orc.synthetic_cme_table())
   dtype = torch.float64 if a.dtype == "f64" else torch.float32
 
   n, weights, p_h, t_h, g_h = make_inputs(a, dtype, 1000 + rank)

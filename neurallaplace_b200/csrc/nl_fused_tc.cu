@@ -1,12 +1,12 @@
 // Fused laplace_reconstruct forward / backward on the 5th-gen tensor cores (tcgen05 + TMEM).
 // float32 path of the canonical laplace_rep_func (H = 64) with a shared time grid and the
 // weighted-sum ILT families (Fourier, and every Abate-Whitt table: CME / Euler / Gaver /
-// FixedTablot / Stehfest).  Everything else runs on the SIMT kernels (nl_fused_simt.cu).
+// FixedTablot / Stehfest), for ANY d_obs x terms.  Everything else runs on the SIMT kernels.
 //
 // Work decomposition.  A tile = 128 batch rows at ONE time point, so the s points, their sphere
 // coordinates, the s-part of layer 1 (S1 = W1s.u_t + b1) and the reduction coefficients are
 // CTA-uniform and are regenerated only when the time index changes (every B/128 tiles).  One
-// persistent CTA per SM walks a contiguous range of tiles.  Thread <-> row (TMEM lane); the two
+// persistent CTA per SM walks a contiguous range of tiles.  Thread <-> row (TMEM lane); the
 // warpgroups split the columns.
 //
 // Per tile (forward):  h1 = tanh(S1 + W1p.p)  -> smem (bf16 hi/lo)      [CUDA cores]
@@ -16,11 +16,16 @@
 //                      tanh heads, sphere->complex, x += Re(coef * F)    [CUDA cores, registers]
 // Backward recomputes the above and adds, all on the tensor cores with the SAME smem images viewed
 // K-major or MN-major (nl_tc_common.cuh):
-//      dO (registers -> smem);  dH2 += dO . W3c;  dW3c += dO^T . [h2 | 1]   (TMEM-resident across tiles)
+//      dO (registers -> smem);  dH2 += dO . W3c;  dW3c += dO^T . [h2 | 1]
 //      Z2g = dH2 (1-h2^2);      dH1  = Z2g . W2;  dW2  += Z2g^T . [h1 | 1 p]
 //      Z1g = dH1 (1-h1^2);      D1  += Z1g^T . [1 p]   (db1 / dW1p / the rank-1 factor of dW1s)
-// Weight-gradient accumulators stay in TMEM for the CTA's whole tile range and are written once to
-// a CTA-private slab; a tiny second kernel reduces the slabs deterministically.  dp uses atomics.
+// A chunk = up to 64 terms of one d_obs (<= 128 output columns of layer 3).  W3 is pre-packed once
+// per call into bf16 hi/lo operand images (pack_w3_kernel) and, when it does not fit in shared
+// memory, streamed through a 3-stage ring with bulk-async (TMA) copies completing on mbarriers.
+// dW2 and the first chunks' dW3 stay TMEM-resident for the CTA's whole tile range and are written
+// once to a CTA-private slab; when d_obs x terms exceeds the TMEM budget the remaining chunks go
+// through one scratch accumulator that is added to the slab per tile by its owning threads
+// (deterministic).  A tiny second kernel reduces the slabs over CTAs.  dp uses atomics.
 // The (batch x time x terms x d_obs) complex intermediate only ever exists in registers.
 #include <algorithm>
 
@@ -36,9 +41,10 @@ constexpr int kH = 64;
 constexpr int kRows = 128;
 constexpr int kEwgFwd = 2;  // warpgroups splitting the columns of a tile: forward runs 2 CTAs / SM x 256 threads,
 constexpr int kEwgBwd = 4;  // backward 1 CTA / SM x 512 threads (its shared-memory footprint forbids 2 CTAs)
-constexpr int kH1Cols = 72;             // h1 image: 64 + [1, p_0..p_6]
-constexpr int kH2Cols = 80;             // h2 image: 64 + [1, 0 x 15]
-constexpr int kMaxK = 7;                // latent dim that fits the extra chunk of the h1 image
+constexpr int kH1Cols = 72;  // h1 image: 64 + [1, p_0..p_6]
+constexpr int kH2Cols = 80;  // h2 image: 64 + [1, 0 x 15]
+constexpr int kMaxK = 7;     // latent dim that fits the extra chunk of the h1 image
+constexpr int kStages = 3;   // W3 ring depth
 
 struct TcArgs {
   IltParams<float> P;
@@ -46,7 +52,11 @@ struct TcArgs {
   int nbt;
   long long ntiles;
   int nkc, kc, NP, nch;
-  const float *p, *t, *W1, *b1, *W2, *b2, *W3, *b3;
+  int w3_slots;   // chunks of W3 held in shared memory: nch (resident) or kStages (streamed ring)
+  int resident;   // dW3 chunks with a TMEM-resident accumulator (the rest use the scratch accumulator)
+  const float *p, *t, *W1, *b1, *W2, *b2;
+  const unsigned char* w3pack;  // [nch][hi image | lo image], each NP x 64 bf16 in operand layout
+  const float* b3pack;          // [nch][NP]
   float* x;
   const float* gx;
   float* slab;
@@ -55,14 +65,12 @@ struct TcArgs {
 };
 
 struct TcSmem {
-  // byte offsets
   size_t dO, H1, H2, W2, W3, small, total;
   size_t dO_img, H1_img, H2_img, W2_img, W3_img;  // bytes of ONE (hi or lo) image
-  // float offsets inside `small`
-  int S1b, W1p, b2, b3, coef, u, G1, xacc, misc, nfloats;
+  int S1b, W1p, b2, b3, coef, u, G1, xacc, misc, nfloats;  // float offsets inside `small`
 };
 
-__host__ __device__ inline TcSmem tc_smem(bool bwd, int NP, int nch, int n) {
+__host__ __device__ inline TcSmem tc_smem(bool bwd, int NP, int nch, int nkc, int w3_slots, int n) {
   TcSmem L;
   L.dO_img = bwd ? image_bytes(kRows, NP > kH ? NP : kH) : 0;  // also hosts Z2g / Z1g (64 columns)
   L.H1_img = image_bytes(kRows, bwd ? kH1Cols : kH);
@@ -74,14 +82,14 @@ __host__ __device__ inline TcSmem tc_smem(bool bwd, int NP, int nch, int n) {
   L.H1 = o; o += 2 * L.H1_img;
   L.H2 = o; o += 2 * L.H2_img;
   L.W2 = o; o += 2 * L.W2_img;
-  L.W3 = o; o += 2 * L.W3_img * nch;
+  L.W3 = o; o += 2 * L.W3_img * w3_slots;
   L.small = o;
   int f = 0;
   L.S1b = f; f += kH;
   L.W1p = f; f += kH * 8;
   L.b2 = f; f += kH;
   L.b3 = f; f += nch * NP;
-  L.coef = f; f += nch * NP;
+  L.coef = f; f += nkc * NP;
   L.u = f; f += 2 * n + 8;
   L.G1 = f; f += kH * 8;
   L.xacc = f; f += 4 * kRows;
@@ -94,14 +102,14 @@ __host__ __device__ inline TcSmem tc_smem(bool bwd, int NP, int nch, int n) {
 struct TcTmem {
   int S, O, dW2, D1, dW3, total;
 };
-__host__ __device__ inline TcTmem tc_tmem(bool bwd, int NP, int nch) {
+__host__ __device__ inline TcTmem tc_tmem(bool bwd, int NP, int acc_slots) {
   TcTmem t;
   t.S = 0;
   t.O = 64;
   t.dW2 = 64 + NP;
   t.D1 = t.dW2 + (bwd ? 80 : 0);
   t.dW3 = t.D1 + (bwd ? 16 : 0);
-  t.total = t.dW3 + (bwd ? 80 * nch : 0);
+  t.total = t.dW3 + (bwd ? 80 * acc_slots : 0);
   return t;
 }
 
@@ -117,7 +125,40 @@ __device__ __forceinline__ GemmOp make_gemm(uint32_t a_img, uint32_t a_lo_off, i
   return g;
 }
 
-template <bool BWD, int KP>
+// bulk-async (TMA) global -> shared copy completing on an mbarrier
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// W3 / b3 -> per-chunk bf16 hi/lo operand images (row jj of chunk ch <-> W3 row of (d, k, theta|phi))
+__global__ void pack_w3_kernel(const float* __restrict__ W3, const float* __restrict__ b3, int D, int n, int nkc,
+                               int kc, int NP, int nch, unsigned char* __restrict__ w3pack,
+                               float* __restrict__ b3pack) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nch * NP) return;
+  const int ch = idx / NP, jj = idx - ch * NP;
+  const int d = ch / nkc, k = (ch % nkc) * kc + (jj >> 1);
+  const bool valid = (jj >> 1) < kc && k < n;
+  const int row = ((jj & 1) ? (D + d) : d) * n + k;
+  const size_t img = image_bytes(NP, kH);
+  unsigned char* w_hi = w3pack + (size_t)ch * 2 * img;
+  unsigned char* w_lo = w_hi + img;
+  for (int c0 = 0; c0 < kH; c0 += 8) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = valid ? __ldg(W3 + (size_t)row * kH + c0 + i) : 0.f;
+    store_chunk8(w_hi, w_lo, NP, jj, c0, v);
+  }
+  b3pack[idx] = valid ? __ldg(b3 + row) : 0.f;
+}
+
+// GENERAL = false: every W3 chunk is shared-memory resident and every dW3 accumulator TMEM resident (the
+// streaming / scratch-flush code is compiled out of the hot loop); GENERAL = true: any d_obs x terms.
+template <bool BWD, int KP, bool GENERAL>
 __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 : 2) fused_tc_kernel(TcArgs A) {
   constexpr int kEWG = BWD ? kEwgBwd : kEwgFwd;
   constexpr int kThreadsTc = 128 * kEWG;
@@ -126,12 +167,16 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar_main;
   __shared__ __align__(8) uint64_t bar_d1;
+  __shared__ __align__(8) uint64_t bar_w3[kStages];
   __shared__ uint32_t tmem_slot;
 
   const IltParams<float> P = A.P;
   const int n = A.n, K = A.K, D = A.D, NP = A.NP, nch = A.nch;
-  const TcSmem L = tc_smem(BWD, NP, nch, n);
-  const TcTmem TM = tc_tmem(BWD, NP, nch);
+  const bool streamed = GENERAL && A.w3_slots < nch;
+  const int n_resident = GENERAL ? A.resident : nch;
+  const int acc_slots = BWD ? (n_resident < nch ? n_resident + 1 : n_resident) : 0;
+  const TcSmem L = tc_smem(BWD, NP, nch, A.nkc, A.w3_slots, n);
+  const TcTmem TM = tc_tmem(BWD, NP, acc_slots);
   unsigned char* dO_hi = smem + L.dO;
   unsigned char* dO_lo = dO_hi + L.dO_img;
   unsigned char* H1_hi = smem + L.H1;
@@ -156,7 +201,13 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
   const int wg = tid >> 7;        // warpgroup
   const int r = tid & 127;        // row of the tile == TMEM lane
   const int ldw1 = 2 * n + K;
-  const int h_rows1 = kRows;      // rows of every activation image
+  const uint32_t w3_bytes = (uint32_t)(2 * L.W3_img);  // hi + lo image of one chunk
+
+  // ---- tile range of this CTA (contiguous => the time index changes rarely)
+  const long long per = A.ntiles / gridDim.x, rem = A.ntiles % gridDim.x;
+  const long long tile_lo = blockIdx.x * per + min((long long)blockIdx.x, rem);
+  const long long tile_hi = tile_lo + per + (blockIdx.x < rem ? 1 : 0);
+  const long long total_chunks = (tile_hi - tile_lo) * nch;  // chunk uses of this CTA, in order
 
   // ---- prologue: zero smem, weights -> bf16 hi/lo images, TMEM, barriers
   for (size_t i = tid; i < L.total / 16; i += kThreadsTc) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
@@ -171,39 +222,56 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
     sb2[tid] = __ldg(A.b2 + tid);
     for (int j = 0; j < K; ++j) sW1p[tid * 8 + j] = __ldg(A.W1 + (size_t)tid * ldw1 + 2 * n + j);
   }
-  for (int idx = tid; idx < nch * NP; idx += kThreadsTc) {
-    const int ch = idx / NP, jj = idx - ch * NP;
-    const int d = ch / A.nkc, k = (ch % A.nkc) * A.kc + (jj >> 1);
-    const bool valid = (jj >> 1) < A.kc && k < n;
-    const int row = ((jj & 1) ? (D + d) : d) * n + k;
-    unsigned char* w_hi = W3_base + (size_t)ch * 2 * L.W3_img;
-    unsigned char* w_lo = w_hi + L.W3_img;
-    for (int c0 = 0; c0 < kH; c0 += 8) {
-      float v[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = valid ? __ldg(A.W3 + (size_t)row * kH + c0 + i) : 0.f;
-      store_chunk8(w_hi, w_lo, NP, jj, c0, v);
-    }
-    sb3[idx] = valid ? __ldg(A.b3 + row) : 0.f;
-  }
+  for (int idx = tid; idx < nch * NP; idx += kThreadsTc) sb3[idx] = __ldg(A.b3pack + idx);
   if (BWD) {
-    // constant "ones" columns: h1 image col 64, h2 image col 64 (bf16 1.0 = 0x3F80 in the hi image)
-    if (tid < kRows) {
-      *reinterpret_cast<uint32_t*>(H2_hi + (size_t)8 * (kRows * 16) + (size_t)tid * 16) = 0x00003F80u;
-    }
+    // constant "ones" column of the h2 image (bf16 1.0 = 0x3F80 in the hi image) -> db3
+    if (tid < kRows) *reinterpret_cast<uint32_t*>(H2_hi + (size_t)8 * (kRows * 16) + (size_t)tid * 16) = 0x00003F80u;
   }
   if (warp == 0) tmem_alloc(&tmem_slot, kTmemCols);
   if (tid == 0) {
     mbar_init(&bar_main, 1);
     mbar_init(&bar_d1, 1);
+    for (int s = 0; s < kStages; ++s) mbar_init(&bar_w3[s], 1);
     fence_mbar_init();
   }
-  fence_async_smem();
+  fence_async_smem();  // the zero fill / generic stores above precede the async-proxy traffic below
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
   const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+
+  // ---- W3 staging: chunk use `g` (g-th chunk this CTA touches) lives in slot g % w3_slots
+  // (resident mode: w3_slots == nch, every chunk loaded once; streamed: ring of kStages)
+  long long w3_issued = 0;  // thread 0 only
+  auto w3_issue_upto = [&](long long upto) {  // thread 0: start the loads of chunk uses < upto
+    if (!streamed) return;
+    const long long lim = min(upto, total_chunks);
+    for (; w3_issued < lim; ++w3_issued) {
+      const int ch = (int)(w3_issued % nch), slot = (int)(w3_issued % kStages);
+      bulk_load(W3_base + (size_t)slot * w3_bytes, A.w3pack + (size_t)ch * w3_bytes, w3_bytes, &bar_w3[slot]);
+    }
+  };
+  if (!streamed) {
+    if (tid == 0 && total_chunks > 0) {
+      // resident: every chunk loaded once; one barrier phase per load keeps the parity bookkeeping trivial
+      for (int ch = 0; ch < nch; ++ch) {
+        bulk_load(W3_base + (size_t)ch * w3_bytes, A.w3pack + (size_t)ch * w3_bytes, w3_bytes, &bar_w3[0]);
+        mbar_wait(&bar_w3[0], ch & 1);
+      }
+    }
+    __syncthreads();
+  } else if (tid == 0) {
+    w3_issue_upto(kStages);
+  }
+  auto w3_slot_addr = [&](long long g) {
+    const int slot = streamed ? (int)(g % kStages) : (int)(g % nch);
+    return smem_u32(W3_base + (size_t)slot * w3_bytes);
+  };
+  auto w3_wait = [&](long long g) {  // thread 0: chunk use g has landed
+    if (streamed) mbar_wait(&bar_w3[g % kStages], (uint32_t)((g / kStages) & 1));
+  };
+
   // bar_main: results the epilogue needs next (Z2, O, dH2, dH1).  bar_d1 ("aux"): weight-gradient GEMMs
   // (dW3, dW2, D1), committed separately so they run behind the epilogue math; it is only waited for
   // right before the shared-memory images they read are overwritten.
@@ -217,14 +285,8 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
     }
   };
 
-  // ---- GEMM descriptors (shared addresses are CTA constants)
   const uint32_t aH1 = smem_u32(H1_hi), aH2 = smem_u32(H2_hi), aW2 = smem_u32(W2_hi), adO = smem_u32(dO_hi);
   const GemmOp gL2 = make_gemm(aH1, (uint32_t)L.H1_img, kRows, 0, aW2, (uint32_t)L.W2_img, kH, 0, 128, kH, kH);
-
-  // ---- tile range of this CTA (contiguous => the time index changes rarely)
-  const long long per = A.ntiles / gridDim.x, rem = A.ntiles % gridDim.x;
-  const long long tile_lo = blockIdx.x * per + min((long long)blockIdx.x, rem);
-  const long long tile_hi = tile_lo + per + (blockIdx.x < rem ? 1 : 0);
 
   float* slab = BWD ? A.slab + (long long)blockIdx.x * A.slab_len : nullptr;
   float* gW1 = slab;
@@ -236,6 +298,33 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
 
   int cur_t = -1;
   bool first_tile = true, first_in_slot = true;
+
+  // W3 row of accumulator lane r in chunk ch (-1: padding lane)
+  auto w3_row_of = [&](int ch) {
+    const int d = ch / A.nkc, k = (ch % A.nkc) * A.kc + (r >> 1);
+    const bool ok = (r >> 1) < A.kc && k < n && r < NP;
+    return ok ? ((r & 1) ? (D + d) : d) * n + k : -1;
+  };
+  // accumulator of chunk ch (columns 0..63 = dW3 rows, column 64 = db3) -> slab; add: scratch flush per tile
+  auto dw3_to_slab = [&](int ch, int tm_col, bool add) {
+    const int row = w3_row_of(ch);
+    for (int i = 0; i < kColsPerWg; i += 16) {
+      float v[16];
+      tmem_ld16(lane_addr + tm_col + wg * kColsPerWg + i, v);
+      tmem_ld_wait();
+      if (row >= 0) {
+        float* dst = gW3 + (long long)row * kH + wg * kColsPerWg + i;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dst[j] = add ? dst[j] + v[j] : v[j];
+      }
+    }
+    if (wg == 0) {
+      float v[8];
+      tmem_ld8(lane_addr + tm_col + kH, v);
+      tmem_ld_wait();
+      if (row >= 0) gb3[row] = add ? gb3[row] + v[0] : v[0];
+    }
+  };
 
   // flush of the per-slot accumulator D1 = Z1g^T.[1 p]: db1, dW1p and the rank-1 update dW1s += G1 (x) u
   auto flush_slot = [&]() {
@@ -282,11 +371,14 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
     }
   };
   if (tile_lo < tile_hi) prefetch(tile_lo);
+  const int ncols_real = min(NP, (2 * A.kc + 3) & ~3);
+  const int cw = (((ncols_real + kEWG - 1) / kEWG) + 3) & ~3;
 
   for (long long tile = tile_lo; tile < tile_hi; ++tile) {
     const int t_idx = (int)(tile / A.nbt);
     const int b = (int)(tile % A.nbt) * kRows + r;
     const bool valid = b < A.B;
+    const long long g0 = (tile - tile_lo) * nch;  // chunk-use index of this tile's chunk 0
     float pv[KP], graw[kGPre];
 #pragma unroll
     for (int j = 0; j < KP; ++j) pv[j] = pv_n[j];
@@ -307,20 +399,25 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
         su[k] = f0;
         su[n + k] = f1;
       }
-      for (int idx = tid; idx < nch * (NP / 2); idx += kThreadsTc) {
-        const int ch = idx / (NP / 2), q = idx - ch * (NP / 2);
-        const int k = (ch % A.nkc) * A.kc + q;
+      for (int idx = tid; idx < A.nkc * (NP / 2); idx += kThreadsTc) {
+        const int kci = idx / (NP / 2), q = idx - kci * (NP / 2);
+        const int k = kci * A.kc + q;
         Cx<float> w{0.f, 0.f};
         if (q < A.kc && k < n) w = reduce_coef(P, c, k);
-        sCoef[ch * NP + 2 * q] = w.re;
-        sCoef[ch * NP + 2 * q + 1] = w.im;
+        sCoef[kci * NP + 2 * q] = w.re;
+        sCoef[kci * NP + 2 * q + 1] = w.im;
       }
       __syncthreads();
       if (tid < kH) {
-        float acc = __ldg(A.b1 + tid);
+        float acc0 = __ldg(A.b1 + tid), acc1 = 0.f;
         const float* w = A.W1 + (size_t)tid * ldw1;
-        for (int k = 0; k < 2 * n; ++k) acc = fmaf(__ldg(w + k), su[k], acc);
-        sS1b[tid] = acc;
+        int k = 0;
+        for (; k + 1 < 2 * n; k += 2) {
+          acc0 = fmaf(__ldg(w + k), su[k], acc0);
+          acc1 = fmaf(__ldg(w + k + 1), su[k + 1], acc1);
+        }
+        if (k < 2 * n) acc0 = fmaf(__ldg(w + k), su[k], acc0);
+        sS1b[tid] = acc0 + acc1;
       }
       __syncthreads();
     }
@@ -338,13 +435,13 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
     }
     if (BWD) wait_aux();  // the previous tile's D1 GEMM reads the [1 p] chunk of the h1 image
 #pragma unroll
-    for (int i = 0; i < kColsPerWg; i += 8) store_chunk8(H1_hi, H1_lo, h_rows1, r, wg * kColsPerWg + i, &h1[i]);
+    for (int i = 0; i < kColsPerWg; i += 8) store_chunk8(H1_hi, H1_lo, kRows, r, wg * kColsPerWg + i, &h1[i]);
     if (BWD && wg == 0) {
       float q[8];
       q[0] = valid ? 1.f : 0.f;
 #pragma unroll
       for (int j = 0; j < kMaxK; ++j) q[1 + j] = (j < KP) ? pv[j < KP ? j : 0] : 0.f;
-      store_chunk8(H1_hi, H1_lo, h_rows1, r, kH, q);
+      store_chunk8(H1_hi, H1_lo, kRows, r, kH, q);
     }
     fence_async_smem();
     tc_fence_before();
@@ -377,28 +474,31 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
     __syncthreads();
 
     // ---- 4. chunks of layer 3 + heads + reduction
-    auto issue_L3 = [&](int ch) {
-      const uint32_t w3 = smem_u32(W3_base + (size_t)ch * 2 * L.W3_img);
-      const GemmOp g = make_gemm(aH2, (uint32_t)(BWD ? L.H2_img : L.H1_img), kRows, 0, w3, (uint32_t)L.W3_img, NP, 0,
-                                 128, NP, kH);
-      issue_gemm(g, tmem + TM.O, false);
+    auto issue_L3 = [&](long long g) {  // thread 0
+      w3_wait(g);
+      tc_fence_after();
+      const GemmOp gg = make_gemm(aH2, (uint32_t)(BWD ? L.H2_img : L.H1_img), kRows, 0, w3_slot_addr(g),
+                                  (uint32_t)L.W3_img, NP, 0, 128, NP, kH);
+      issue_gemm(gg, tmem + TM.O, false);
     };
     if (tid == 0) {
       tc_fence_after();
-      issue_L3(0);
+      issue_L3(g0);
       umma_commit(&bar_main);
     }
-    // O columns per warpgroup: only the real 2*kc columns (rounded to the 4-column group) are evaluated;
-    // the zero padding up to NP exists for the UMMA shape only
-    const int ncols_real = min(NP, (2 * A.kc + 3) & ~3);
-    const int cw = (((ncols_real + kEWG - 1) / kEWG) + 3) & ~3;
     float xsum = 0.f;
     for (int ch = 0; ch < nch; ++ch) {
-      const int d = ch / A.nkc;
-      const bool d_first = (ch % A.nkc) == 0, d_last = (ch % A.nkc) == A.nkc - 1;
+      const int d = ch / A.nkc, kci = ch % A.nkc;
+      const bool d_first = kci == 0, d_last = kci == A.nkc - 1;
       mbar_wait(&bar_main, ph_main);
       ph_main ^= 1;
-      if (BWD && ch > 0) wait_aux();  // dW3(ch-1) still reads the dO image
+      if (BWD && ch > 0) {
+        wait_aux();  // dW3(ch-1) still reads the dO image
+        tc_fence_after();
+        if (GENERAL && ch - 1 >= n_resident) dw3_to_slab(ch - 1, TM.dW3 + 80 * n_resident, true);
+        if (tid == 0) w3_issue_upto(g0 + ch - 1 + kStages + 1);  // the ring slot of chunk ch-1 is free again
+      }
+      if (!BWD && tid == 0) w3_issue_upto(g0 + ch + kStages + 1);  // L3(ch) done -> its ring slot is free
       tc_fence_after();
       float g = 0.f;
       if (BWD) {
@@ -413,7 +513,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
         g = gr * pref;
       }
       if (d_first) xsum = 0.f;
-      const float* cf = sCoef + ch * NP;
+      const float* cf = sCoef + kci * NP;
       const float* bb3 = sb3 + ch * NP;
       for (int c0 = wg * cw; c0 < min((wg + 1) * cw, ncols_real); c0 += 4) {
         float v[4], dv[4];
@@ -434,14 +534,12 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
         if (BWD) store_chunk4(dO_hi, dO_lo, kRows, r, c0, dv);
       }
       if (!BWD) {
-        if (d_last) {
-          sxacc[wg * kRows + r] = xsum;
-        }
+        if (d_last) sxacc[wg * kRows + r] = xsum;
         tc_fence_before();
         __syncthreads();
         if (tid == 0 && ch + 1 < nch) {
           tc_fence_after();
-          issue_L3(ch + 1);
+          issue_L3(g0 + ch + 1);
           umma_commit(&bar_main);
         }
         if (d_last) {
@@ -459,16 +557,17 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
         __syncthreads();
         if (tid == 0) {
           tc_fence_after();
-          const uint32_t w3 = smem_u32(W3_base + (size_t)ch * 2 * L.W3_img);
+          const uint32_t w3 = w3_slot_addr(g0 + ch);
           // dH2 (+)= dO . W3c       (A K-major over the NP columns, B = W3c viewed MN-major)
           const GemmOp gdh = make_gemm(adO, (uint32_t)L.dO_img, kRows, 0, w3, (uint32_t)L.W3_img, NP, 1, 128, kH, NP);
           issue_gemm(gdh, tmem + TM.S, ch > 0);
-          if (ch + 1 < nch) issue_L3(ch + 1);
+          if (ch + 1 < nch) issue_L3(g0 + ch + 1);
           umma_commit(&bar_main);
-          // dW3c += dO^T . [h2 | 1] (both MN-major, reduction over the 128 rows; lanes >= NP are scratch)
+          // dW3c (+)= dO^T . [h2 | 1] (both MN-major, reduction over the 128 rows; lanes >= NP are scratch)
           const GemmOp gdw = make_gemm(adO, (uint32_t)L.dO_img, kRows, 1, aH2, (uint32_t)L.H2_img, kRows, 1, 128,
                                        kH2Cols, kRows);
-          issue_gemm(gdw, tmem + TM.dW3 + 80 * ch, !first_tile);
+          const bool res = ch < n_resident;
+          issue_gemm(gdw, tmem + TM.dW3 + 80 * (res ? ch : n_resident), res ? !first_tile : false);
           umma_commit(&bar_d1);
         }
         d1_pending = true;
@@ -490,6 +589,9 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
         for (int j = 0; j < 16; ++j) z[i + j] = v[j] * (1.f - h2[i + j] * h2[i + j]);
       }
       wait_aux();  // dW3 of the last chunk reads the dO image
+      tc_fence_after();
+      if (GENERAL && nch - 1 >= n_resident) dw3_to_slab(nch - 1, TM.dW3 + 80 * n_resident, true);
+      if (tid == 0) w3_issue_upto(g0 + nch - 1 + kStages + 1);
 #pragma unroll
       for (int i = 0; i < kColsPerWg; i += 8) store_chunk8(dO_hi, dO_lo, kRows, r, wg * kColsPerWg + i, &z[i]);
       fence_async_smem();
@@ -558,44 +660,23 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
     flush_slot();
     if (tile_hi > tile_lo) {
       tc_fence_after();
-      // dW3 chunks: lane jj <-> W3 row; columns 0..63 = dW3, column 64 = db3
-      for (int ch = 0; ch < nch; ++ch) {
-        const int d = ch / A.nkc, k = (ch % A.nkc) * A.kc + (r >> 1);
-        const bool ok = (r >> 1) < A.kc && k < n && r < NP;
-        const int row = ((r & 1) ? (D + d) : d) * n + k;
-        for (int i = 0; i < kColsPerWg; i += 16) {
-          float v[16];
-          tmem_ld16(lane_addr + TM.dW3 + 80 * ch + wg * kColsPerWg + i, v);
-          tmem_ld_wait();
-          if (ok)
-#pragma unroll
-            for (int j = 0; j < 16; ++j) gW3[(long long)row * kH + wg * kColsPerWg + i + j] = v[j];
-        }
-        if (wg == 0) {
-          float v[8];
-          tmem_ld8(lane_addr + TM.dW3 + 80 * ch + kH, v);
-          tmem_ld_wait();
-          if (ok) gb3[row] = v[0];
-        }
-      }
+      for (int ch = 0; ch < min(nch, n_resident); ++ch) dw3_to_slab(ch, TM.dW3 + 80 * ch, false);
       // dW2: M=64 accumulator
-      {
-        const int j = (warp & 3) * 16 + lane;
-        const bool ok = lane < 16;
-        for (int i = 0; i < kColsPerWg; i += 16) {
-          float v[16];
-          tmem_ld16(lane_addr + TM.dW2 + wg * kColsPerWg + i, v);
-          tmem_ld_wait();
-          if (ok)
+      const int j = (warp & 3) * 16 + lane;
+      const bool ok = lane < 16;
+      for (int i = 0; i < kColsPerWg; i += 16) {
+        float v[16];
+        tmem_ld16(lane_addr + TM.dW2 + wg * kColsPerWg + i, v);
+        tmem_ld_wait();
+        if (ok)
 #pragma unroll
-            for (int q = 0; q < 16; ++q) gW2[j * kH + wg * kColsPerWg + i + q] = v[q];
-        }
-        if (wg == 0) {
-          float v[8];
-          tmem_ld8(lane_addr + TM.dW2 + kH, v);
-          tmem_ld_wait();
-          if (ok) gb2[j] = v[0];
-        }
+          for (int q = 0; q < 16; ++q) gW2[j * kH + wg * kColsPerWg + i + q] = v[q];
+      }
+      if (wg == 0) {
+        float v[8];
+        tmem_ld8(lane_addr + TM.dW2 + kH, v);
+        tmem_ld_wait();
+        if (ok) gb2[j] = v[0];
       }
     }
   }
@@ -610,14 +691,32 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
 static size_t tc_align(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct TcGeom {
-  int nkc, kc, NP, nch;
+  int nkc, kc, NP, nch, w3_slots, resident;
+  size_t smem;
+  bool ok;
 };
-static TcGeom tc_geom(const nl_desc* d) {
-  TcGeom g;
+static TcGeom tc_geom(const nl_desc* d, bool bwd) {
+  TcGeom g{};
   g.nkc = (2 * d->n + 127) / 128;
   g.kc = (d->n + g.nkc - 1) / g.nkc;
   g.NP = (2 * g.kc + 15) / 16 * 16;
   g.nch = g.nkc * d->D;
+  // TMEM: every dW3 chunk resident if it fits, else (room-1) resident + one scratch accumulator
+  const int room = bwd ? (512 - (64 + g.NP + 80 + 16)) / 80 : 0;
+  if (bwd && room < 1) return g;
+  g.resident = bwd ? (g.nch <= room ? g.nch : room - 1) : 0;
+  // shared memory: all chunks resident if they fit (forward: within half an SM so that 2 CTAs co-reside)
+  const size_t limit = 227 * 1024 - 1024, half = limit / 2;
+  const tc::TcSmem Lr = tc::tc_smem(bwd, g.NP, g.nch, g.nkc, g.nch, d->n);
+  const tc::TcSmem Ls = tc::tc_smem(bwd, g.NP, g.nch, g.nkc, tc::kStages, d->n);
+  if (g.nch <= tc::kStages || Lr.total <= (bwd ? limit : half)) {
+    g.w3_slots = g.nch;
+    g.smem = Lr.total;
+  } else {
+    g.w3_slots = tc::kStages;
+    g.smem = Ls.total;
+  }
+  g.ok = g.smem <= limit;
   return g;
 }
 
@@ -630,19 +729,18 @@ TcPlan tc_plan(const nl_desc* d, int pass) {
   if ((long long)d->B * d->T <= 0) return pl;
   // auto mode: tiles are 128 batch rows at one time point; tiny batches waste the tile -> SIMT kernels
   if (d->impl == 0 && d->B < 64) return pl;
-  const TcGeom g = tc_geom(d);
-  const tc::TcTmem tm = tc::tc_tmem(bwd, g.NP, g.nch);
-  if (tm.total > (bwd ? 512 : 256)) return pl;
-  const tc::TcSmem L = tc::tc_smem(bwd, g.NP, g.nch, d->n);
-  if (L.total + 1024 > 227 * 1024) return pl;
+  const TcGeom g = tc_geom(d, bwd);
+  if (!g.ok) return pl;
   const long long nbt = (d->B + tc::kRows - 1) / tc::kRows;
   const long long ntiles = nbt * d->T;
   pl.grid = (int)std::min<long long>(ntiles, (long long)device_sm_count() * (bwd ? 1 : 2));
-  pl.smem = L.total;
+  pl.smem = g.smem;
   const long long ldw1 = 2 * d->n + d->K;
   const size_t slab_len = (size_t)d->H * ldw1 + d->H + (size_t)d->H * d->H + d->H + (size_t)2 * d->D * d->n * d->H +
                           (size_t)2 * d->D * d->n;
-  pl.ws_bytes = bwd ? tc_align(slab_len * 4 * pl.grid, 256) + 256 : 256;
+  const size_t pack = tc_align((size_t)g.nch * 2 * tc::image_bytes(g.NP, tc::kH), 256) +
+                      tc_align((size_t)g.nch * g.NP * 4, 256);
+  pl.ws_bytes = pack + (bwd ? tc_align(slab_len * 4 * pl.grid, 256) : 0) + 512;
   pl.ok = 1;
   return pl;
 }
@@ -650,13 +748,18 @@ TcPlan tc_plan(const nl_desc* d, int pass) {
 cudaError_t launch_reduce_slabs_f32(const float* slab, long long slab_len, int nslabs, void* const* grads,
                                     const nl_desc* d, cudaStream_t st);
 
+template <bool BWD, int KP, bool GENERAL>
+static cudaError_t launch_tc1_g(const tc::TcArgs& A, int grid, size_t smem, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(tc::fused_tc_kernel<BWD, KP, GENERAL>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  tc::fused_tc_kernel<BWD, KP, GENERAL><<<grid, 128 * (BWD ? tc::kEwgBwd : tc::kEwgFwd), smem, st>>>(A);
+  return cudaGetLastError();
+}
 template <bool BWD, int KP>
 static cudaError_t launch_tc1(const tc::TcArgs& A, int grid, size_t smem, cudaStream_t st) {
-  cudaError_t e =
-      cudaFuncSetAttribute(tc::fused_tc_kernel<BWD, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  tc::fused_tc_kernel<BWD, KP><<<grid, 128 * (BWD ? tc::kEwgBwd : tc::kEwgFwd), smem, st>>>(A);
-  return cudaSuccess;
+  const bool general = A.w3_slots < A.nch || (BWD && A.resident < A.nch);
+  return general ? launch_tc1_g<BWD, KP, true>(A, grid, smem, st) : launch_tc1_g<BWD, KP, false>(A, grid, smem, st);
 }
 
 cudaError_t launch_fused_tc(const nl_desc* d, bool bwd, const void* p, const void* t, const void* const* weights,
@@ -664,7 +767,7 @@ cudaError_t launch_fused_tc(const nl_desc* d, bool bwd, const void* p, const voi
                             cudaStream_t st, int* launches) {
   TcPlan pl = tc_plan(d, bwd ? 1 : 0);
   if (!pl.ok) return cudaErrorInvalidValue;
-  const TcGeom g = tc_geom(d);
+  const TcGeom g = tc_geom(d, bwd);
   tc::TcArgs A{};
   A.P.family = d->family;
   A.P.n = d->n;
@@ -678,16 +781,32 @@ cudaError_t launch_fused_tc(const nl_desc* d, bool bwd, const void* p, const voi
   A.nbt = (d->B + tc::kRows - 1) / tc::kRows;
   A.ntiles = (long long)A.nbt * d->T;
   A.nkc = g.nkc; A.kc = g.kc; A.NP = g.NP; A.nch = g.nch;
+  A.w3_slots = g.w3_slots; A.resident = g.resident;
   A.p = (const float*)p; A.t = (const float*)t;
   A.W1 = (const float*)weights[0]; A.b1 = (const float*)weights[1]; A.W2 = (const float*)weights[2];
-  A.b2 = (const float*)weights[3]; A.W3 = (const float*)weights[4]; A.b3 = (const float*)weights[5];
+  A.b2 = (const float*)weights[3];
   A.x = (float*)x; A.gx = (const float*)gx;
+  // workspace: [W3 operand images | b3 pack | slabs]
+  unsigned char* w = (unsigned char*)tc_align((size_t)ws, 256);
+  unsigned char* w3pack = w;
+  w += tc_align((size_t)g.nch * 2 * tc::image_bytes(g.NP, tc::kH), 256);
+  float* b3pack = (float*)w;
+  w += tc_align((size_t)g.nch * g.NP * 4, 256);
+  A.w3pack = w3pack; A.b3pack = b3pack;
+  {
+    const int total = g.nch * g.NP, threads = 128;
+    tc::pack_w3_kernel<<<(total + threads - 1) / threads, threads, 0, st>>>(
+        (const float*)weights[4], (const float*)weights[5], d->D, d->n, g.nkc, g.kc, g.NP, g.nch, w3pack, b3pack);
+    cudaError_t e0 = cudaGetLastError();
+    if (e0 != cudaSuccess) return e0;
+    if (launches) *launches += 1;
+  }
   cudaError_t e;
   if (bwd) {
     const long long ldw1 = 2 * d->n + d->K;
     A.slab_len = (long long)d->H * ldw1 + d->H + (long long)d->H * d->H + d->H + (long long)2 * d->D * d->n * d->H +
                  (long long)2 * d->D * d->n;
-    A.slab = (float*)tc_align((size_t)ws, 256);
+    A.slab = (float*)w;
     e = cudaMemsetAsync(A.slab, 0, (size_t)A.slab_len * 4 * pl.grid, st);
     if (e != cudaSuccess) return e;
     A.dp = (float*)grads[6];
@@ -697,8 +816,6 @@ cudaError_t launch_fused_tc(const nl_desc* d, bool bwd, const void* p, const voi
   } else {
     e = d->K <= 2 ? launch_tc1<false, 2>(A, pl.grid, pl.smem, st) : launch_tc1<false, tc::kMaxK>(A, pl.grid, pl.smem, st);
   }
-  if (e != cudaSuccess) return e;
-  e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (launches) *launches += 1;
   if (bwd) {

@@ -21,6 +21,13 @@ CASES = [
     ("fourier", 33, 160, 5, 1, 2, False),
     ("fourier", 17, 300, 9, 1, 7, True),
     ("fourier", 33, 1500, 40, 1, 2, True),
+    # d_obs x terms beyond the TMEM / shared-memory resident budget: W3 streamed (bulk-async ring), dW3 scratch flush
+    ("fourier", 33, 200, 3, 4, 2, True),
+    ("fourier", 33, 300, 5, 16, 2, True),
+    ("fourier", 65, 150, 3, 5, 3, True),
+    ("fourier", 129, 130, 2, 2, 2, True),
+    ("euler", 33, 260, 4, 6, 2, True),
+    ("fourier", 129, 2000, 12, 3, 2, True),
 ]
 
 
