@@ -110,11 +110,13 @@ static int reconstruct(const nl_desc* d, bool bwd, const void* p, const void* t,
   cudaError_t e;
   if (impl == 2) {
     // Two tensor-core variants exist (nl_fused_tc.cu: one stream per CTA, nl_fused_tc2.cu: two streams + a
-    // dedicated MMA-issuer warp).  Measured on B200 the two-stream kernel wins for the forward pass and the
-    // one-stream kernel for the backward pass; NL_B200_TC_STREAMS=1|2 forces one of them (profiling).
+    // dedicated MMA-issuer warp).  Measured on B200: backward -> one stream; forward -> one stream at 2 CTAs/SM
+    // while W3 is small enough for that, else two streams.  NL_B200_TC_STREAMS=1|2 forces one (profiling).
     static const int force = [] { const char* v = getenv("NL_B200_TC_STREAMS"); return v ? atoi(v) : 0; }();
-    const bool ok1 = nl::tc_plan(d, pass).ok, ok2 = nl::tc2_plan(d, pass).ok;
-    bool use2 = bwd ? false : true;
+    const nl::TcPlan p1 = nl::tc_plan(d, pass);
+    const bool ok1 = p1.ok, ok2 = nl::tc2_plan(d, pass).ok;
+    // forward: one-stream kernel when two of its CTAs co-reside on an SM, else the two-stream kernel
+    bool use2 = bwd ? false : !(ok1 && p1.co_resident);
     if (force == 1) use2 = false;
     if (force == 2) use2 = true;
     if (use2 && !ok2) use2 = false;

@@ -45,6 +45,7 @@ constexpr int kH1Cols = 72;  // h1 image: 64 + [1, p_0..p_6]
 constexpr int kH2Cols = 80;  // h2 image: 64 + [1, 0 x 15]
 constexpr int kMaxK = 7;     // latent dim that fits the extra chunk of the h1 image
 constexpr int kStages = 3;   // W3 ring depth
+constexpr int kMaxB3Smem = 4096;  // floats of packed b3 kept in shared memory
 
 struct TcArgs {
   IltParams<float> P;
@@ -88,7 +89,7 @@ __host__ __device__ inline TcSmem tc_smem(bool bwd, int NP, int nch, int nkc, in
   L.S1b = f; f += kH;
   L.W1p = f; f += kH * 8;
   L.b2 = f; f += kH;
-  L.b3 = f; f += nch * NP;
+  L.b3 = f; f += (nch * NP <= kMaxB3Smem) ? nch * NP : 0;  // else b3 is read from the global pack
   L.coef = f; f += nkc * NP;
   L.u = f; f += 2 * n + 8;
   L.G1 = f; f += kH * 8;
@@ -222,7 +223,9 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
     sb2[tid] = __ldg(A.b2 + tid);
     for (int j = 0; j < K; ++j) sW1p[tid * 8 + j] = __ldg(A.W1 + (size_t)tid * ldw1 + 2 * n + j);
   }
-  for (int idx = tid; idx < nch * NP; idx += kThreadsTc) sb3[idx] = __ldg(A.b3pack + idx);
+  const bool b3_in_smem = nch * NP <= kMaxB3Smem;
+  if (b3_in_smem)
+    for (int idx = tid; idx < nch * NP; idx += kThreadsTc) sb3[idx] = __ldg(A.b3pack + idx);
   if (BWD) {
     // constant "ones" column of the h2 image (bf16 1.0 = 0x3F80 in the hi image) -> db3
     if (tid < kRows) *reinterpret_cast<uint32_t*>(H2_hi + (size_t)8 * (kRows * 16) + (size_t)tid * 16) = 0x00003F80u;
@@ -314,15 +317,25 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
       tmem_ld_wait();
       if (row >= 0) {
         float* dst = gW3 + (long long)row * kH + wg * kColsPerWg + i;
+        // add: fire-and-forget reductions (RED) -- only this thread ever touches these addresses, so the
+        // result is still deterministic, and no load latency is exposed
+        if (add) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) dst[j] = add ? dst[j] + v[j] : v[j];
+          for (int j = 0; j < 16; ++j) atomicAdd(dst + j, v[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) dst[j] = v[j];
+        }
       }
     }
     if (wg == 0) {
       float v[8];
       tmem_ld8(lane_addr + tm_col + kH, v);
       tmem_ld_wait();
-      if (row >= 0) gb3[row] = add ? gb3[row] + v[0] : v[0];
+      if (row >= 0) {
+        if (add) atomicAdd(gb3 + row, v[0]);
+        else     gb3[row] = v[0];
+      }
     }
   };
 
@@ -514,7 +527,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
       }
       if (d_first) xsum = 0.f;
       const float* cf = sCoef + kci * NP;
-      const float* bb3 = sb3 + ch * NP;
+      const float* bb3 = (!GENERAL || b3_in_smem) ? sb3 + ch * NP : A.b3pack + ch * NP;
       for (int c0 = wg * cw; c0 < min((wg + 1) * cw, ncols_real); c0 += 4) {
         float v[4], dv[4];
         tmem_ld4(lane_addr + TM.O + c0, v);
@@ -735,6 +748,7 @@ TcPlan tc_plan(const nl_desc* d, int pass) {
   const long long ntiles = nbt * d->T;
   pl.grid = (int)std::min<long long>(ntiles, (long long)device_sm_count() * (bwd ? 1 : 2));
   pl.smem = g.smem;
+  pl.co_resident = !bwd && g.smem <= (227 * 1024 - 1024) / 2;
   const long long ldw1 = 2 * d->n + d->K;
   const size_t slab_len = (size_t)d->H * ldw1 + d->H + (size_t)d->H * d->H + d->H + (size_t)2 * d->D * d->n * d->H +
                           (size_t)2 * d->D * d->n;

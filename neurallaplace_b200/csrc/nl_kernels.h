@@ -40,6 +40,7 @@ struct TcPlan {
   int grid;
   size_t smem;
   size_t ws_bytes;
+  int co_resident;  // forward: two CTAs fit on one SM (shared memory <= half)
 };
 TcPlan tc_plan(const nl_desc* d, int pass);
 cudaError_t launch_fused_tc(const nl_desc* d, bool bwd, const void* p, const void* t, const void* const* weights,

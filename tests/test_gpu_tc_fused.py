@@ -28,6 +28,7 @@ CASES = [
     ("fourier", 129, 130, 2, 2, 2, True),
     ("euler", 33, 260, 4, 6, 2, True),
     ("fourier", 129, 2000, 12, 3, 2, True),
+    ("fourier", 129, 140, 2, 16, 2, True),
 ]
 
 
