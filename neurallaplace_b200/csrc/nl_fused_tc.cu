@@ -37,6 +37,19 @@
 namespace nl {
 namespace tc {
 
+#ifdef NL_TC_PROFILE
+#define NL_PROF(i)                                   \
+  do {                                               \
+    if (tid == 0) {                                  \
+      const long long c_ = clock64();                \
+      prof_acc[i] += c_ - prof_last;                 \
+      prof_last = c_;                                \
+    }                                                \
+  } while (0)
+#else
+#define NL_PROF(i) do { } while (0)
+#endif
+
 constexpr int kH = 64;
 constexpr int kRows = 128;
 constexpr int kEwgFwd = 2;  // warpgroups splitting the columns of a tile: forward runs 2 CTAs / SM x 256 threads,
@@ -63,6 +76,7 @@ struct TcArgs {
   float* slab;
   long long slab_len;
   float* dp;
+  long long* prof;  // optional: per-phase clock totals of thread 0 (NL_TC_PROFILE builds)
 };
 
 struct TcSmem {
@@ -387,6 +401,9 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
   const int ncols_real = min(NP, (2 * A.kc + 3) & ~3);
   const int cw = (((ncols_real + kEWG - 1) / kEWG) + 3) & ~3;
 
+#ifdef NL_TC_PROFILE
+  long long prof_acc[12] = {0}, prof_last = clock64();
+#endif
   for (long long tile = tile_lo; tile < tile_hi; ++tile) {
     const int t_idx = (int)(tile / A.nbt);
     const int b = (int)(tile % A.nbt) * kRows + r;
@@ -435,6 +452,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
       __syncthreads();
     }
     const float pref = smisc[0];
+    NL_PROF(0);
 
     // ---- 1. h1 = tanh(S1b + W1p.p) -> smem
     float h1[kColsPerWg];
@@ -460,6 +478,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
     tc_fence_before();
     __syncthreads();
 
+    NL_PROF(1);
     // ---- 2. Z2 = h1 . W2^T
     if (tid == 0) {
       tc_fence_after();
@@ -469,6 +488,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
     mbar_wait(&bar_main, ph_main);
     ph_main ^= 1;
     tc_fence_after();
+    NL_PROF(2);
 
     // ---- 3. h2 = tanh(Z2 + b2) -> smem
     float h2[kColsPerWg];
@@ -486,6 +506,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
     tc_fence_before();
     __syncthreads();
 
+    NL_PROF(3);
     // ---- 4. chunks of layer 3 + heads + reduction
     auto issue_L3 = [&](long long g) {  // thread 0
       w3_wait(g);
@@ -513,6 +534,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
       }
       if (!BWD && tid == 0) w3_issue_upto(g0 + ch + kStages + 1);  // L3(ch) done -> its ring slot is free
       tc_fence_after();
+      NL_PROF(4);
       float g = 0.f;
       if (BWD) {
         float gr = 0.f;
@@ -546,6 +568,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
         }
         if (BWD) store_chunk4(dO_hi, dO_lo, kRows, r, c0, dv);
       }
+      NL_PROF(5);
       if (!BWD) {
         if (d_last) sxacc[wg * kRows + r] = xsum;
         tc_fence_before();
@@ -585,6 +608,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
         }
         d1_pending = true;
       }
+      NL_PROF(6);
     }
 
     if (BWD) {
@@ -592,6 +616,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
       mbar_wait(&bar_main, ph_main);
       ph_main ^= 1;
       tc_fence_after();
+      NL_PROF(7);
       float z[kColsPerWg];
 #pragma unroll
       for (int i = 0; i < kColsPerWg; i += 16) {
@@ -610,6 +635,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
       fence_async_smem();
       tc_fence_before();
       __syncthreads();
+      NL_PROF(8);
       // ---- 6. dH1 = Z2g . W2 ;  dW2 += Z2g^T . [h1 | 1 p]
       if (tid == 0) {
         tc_fence_after();
@@ -625,6 +651,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
       mbar_wait(&bar_main, ph_main);
       ph_main ^= 1;
       tc_fence_after();
+      NL_PROF(9);
       // ---- 7. Z1g = dH1 (1 - h1^2) -> smem ; dp
       float dpv[KP];
 #pragma unroll
@@ -654,6 +681,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
       fence_async_smem();
       tc_fence_before();
       __syncthreads();
+      NL_PROF(10);
       // ---- 8. D1 (+)= Z1g^T . [1 p]   (M=64, N=8; B = chunk 8 of the h1 image)
       if (tid == 0) {
         tc_fence_after();
@@ -666,7 +694,12 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
     }
     first_tile = false;
     first_in_slot = false;
+    NL_PROF(11);
   }
+#ifdef NL_TC_PROFILE
+  if (tid == 0 && A.prof)
+    for (int i = 0; i < 12; ++i) atomicAdd((unsigned long long*)A.prof + i, (unsigned long long)prof_acc[i]);
+#endif
 
   // ---- epilogue: flush the TMEM-resident weight gradients to this CTA's slab
   if (BWD) {
@@ -701,6 +734,9 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
 }  // namespace tc
 
 // ---------------------------------------------------------------------------------------------
+#ifdef NL_TC_PROFILE
+static long long* g_prof_buf = nullptr;
+#endif
 static size_t tc_align(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct TcGeom {
@@ -800,6 +836,13 @@ cudaError_t launch_fused_tc(const nl_desc* d, bool bwd, const void* p, const voi
   A.W1 = (const float*)weights[0]; A.b1 = (const float*)weights[1]; A.W2 = (const float*)weights[2];
   A.b2 = (const float*)weights[3];
   A.x = (float*)x; A.gx = (const float*)gx;
+#ifdef NL_TC_PROFILE
+  if (!g_prof_buf) {
+    cudaMalloc(&g_prof_buf, 2 * 12 * sizeof(long long));
+    cudaMemset(g_prof_buf, 0, 2 * 12 * sizeof(long long));
+  }
+  A.prof = g_prof_buf + (bwd ? 12 : 0);
+#endif
   // workspace: [W3 operand images | b3 pack | slabs]
   unsigned char* w = (unsigned char*)tc_align((size_t)ws, 256);
   unsigned char* w3pack = w;
@@ -841,3 +884,14 @@ cudaError_t launch_fused_tc(const nl_desc* d, bool bwd, const void* p, const voi
 }
 
 }  // namespace nl
+
+#ifdef NL_TC_PROFILE
+// profiling build only (scripts/gpu_phase_profile.sh): per-phase clock totals of thread 0, summed over CTAs
+extern "C" int nl_debug_tc_profile(long long* out24, int reset) {
+  if (!nl::g_prof_buf) return -1;
+  cudaDeviceSynchronize();
+  cudaMemcpy(out24, nl::g_prof_buf, 24 * sizeof(long long), cudaMemcpyDeviceToHost);
+  if (reset) cudaMemset(nl::g_prof_buf, 0, 24 * sizeof(long long));
+  return 0;
+}
+#endif

@@ -1,0 +1,38 @@
+#!/usr/bin/env bash
+# Builds a profiling variant of the library (per-phase clock64 counters in the 1-stream tcgen05 kernel) into
+# /tmp and prints where thread 0 of each CTA spends its cycles.  Not part of the product build.
+set -euo pipefail
+cd "$(dirname "$0")/.."
+SRC=neurallaplace_b200/csrc
+mkdir -p /tmp/nlprof
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --extended-lambda -DNL_TC_PROFILE"
+for f in nl_api nl_elementwise nl_fused_simt nl_fused_tc nl_fused_tc2 nl_tc_selftest; do
+  nvcc $FLAGS -c $SRC/$f.cu -o /tmp/nlprof/$f.o 2>/dev/null &
+done; wait
+nvcc -shared -o /tmp/nlprof/libnl_b200.so /tmp/nlprof/*.o -lcudart
+cp neurallaplace_b200/lib/libnl_b200.so /tmp/nlprof/orig.so
+cp /tmp/nlprof/libnl_b200.so neurallaplace_b200/lib/libnl_b200.so
+trap 'cp /tmp/nlprof/orig.so neurallaplace_b200/lib/libnl_b200.so' EXIT
+NL_B200_TC_STREAMS=1 python - <<'PY'
+import ctypes, torch, sys
+sys.path.insert(0, '.')
+from neurallaplace_b200 import laplace_reconstruct, _lib
+from neurallaplace_b200.rep_func import LaplaceRepresentationFunc
+dev = torch.device('cuda', 0)
+B, T, terms, D = 4096, 1024, 33, 1
+f = LaplaceRepresentationFunc(terms, D, 2).to(dev)
+p = torch.randn(B, 2, device=dev, requires_grad=True); t = torch.linspace(20.0/T, 20.0, T, device=dev); g = torch.randn(B, T, D, device=dev)
+lib = _lib.load()
+for _ in range(2):
+    x = laplace_reconstruct(f, p, t, recon_dim=D); x.backward(g)
+out = (ctypes.c_longlong * 24)()
+lib.nl_debug_tc_profile(out, 1)
+x = laplace_reconstruct(f, p, t, recon_dim=D); x.backward(g)
+lib.nl_debug_tc_profile(out, 0)
+names = ["slot-ctx/prefetch", "1 h1 compute+store+sync", "2 issue L2 + wait", "3 h2 tanh+store+sync", "4 issue L3 + wait", "5 element stage", "6 dO fence+sync+issue", "7 wait dH2", "8 Z2g+aux wait+store+sync", "9 issue dH1/dW2 + wait", "10 Z1g+dp+store+sync", "11 issue D1"]
+for k, nm in ((0, "forward"), (12, "backward")):
+    v = [out[k+i] for i in range(12)]; tot = sum(v)
+    print(nm, "total clocks (sum over CTAs) %.3e  per CTA %.0f" % (tot, tot/296 if k == 0 else tot/148))
+    for i in range(12):
+        if v[i]: print("   %-28s %5.1f%%" % (names[i], 100.0*v[i]/tot))
+PY
