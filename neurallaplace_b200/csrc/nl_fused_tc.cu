@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
 
   // ---- W3 staging: chunk use `g` (g-th chunk this CTA touches) lives in slot g % w3_slots
   // (resident mode: w3_slots == nch, every chunk loaded once; streamed: ring of kStages)
-  long long w3_issued = 0;  // thread 0 only
+  long long w3_issued = 0;  // meaningful in the elected lane of warp 0 only (elect.sync is deterministic)
   auto w3_issue_upto = [&](long long upto) {  // thread 0: start the loads of chunk uses < upto
     if (!streamed) return;
     const long long lim = min(upto, total_chunks);
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
     }
   };
   if (!streamed) {
-    if (tid == 0 && total_chunks > 0) {
+    if (total_chunks > 0 && warp == 0 && elect_one()) {
       // resident: every chunk loaded once; one barrier phase per load keeps the parity bookkeeping trivial
       for (int ch = 0; ch < nch; ++ch) {
         bulk_load(W3_base + (size_t)ch * w3_bytes, A.w3pack + (size_t)ch * w3_bytes, w3_bytes, &bar_w3[0]);
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
       }
     }
     __syncthreads();
-  } else if (tid == 0) {
+  } else if (warp == 0 && elect_one()) {
     w3_issue_upto(kStages);
   }
   auto w3_slot_addr = [&](long long g) {
@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
 
     NL_PROF(1);
     // ---- 2. Z2 = h1 . W2^T
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       tc_fence_after();
       issue_gemm(gL2, tmem + TM.S, false);
       umma_commit(&bar_main);
@@ -515,7 +515,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
                                   (uint32_t)L.W3_img, NP, 0, 128, NP, kH);
       issue_gemm(gg, tmem + TM.O, false);
     };
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       tc_fence_after();
       issue_L3(g0);
       umma_commit(&bar_main);
@@ -530,9 +530,9 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
         wait_aux();  // dW3(ch-1) still reads the dO image
         tc_fence_after();
         if (GENERAL && ch - 1 >= n_resident) dw3_to_slab(ch - 1, TM.dW3 + 80 * n_resident, true);
-        if (tid == 0) w3_issue_upto(g0 + ch - 1 + kStages + 1);  // the ring slot of chunk ch-1 is free again
+        if (warp == 0 && elect_one()) w3_issue_upto(g0 + ch - 1 + kStages + 1);  // the ring slot of chunk ch-1 is free again
       }
-      if (!BWD && tid == 0) w3_issue_upto(g0 + ch + kStages + 1);  // L3(ch) done -> its ring slot is free
+      if (!BWD && warp == 0 && elect_one()) w3_issue_upto(g0 + ch + kStages + 1);  // L3(ch) done -> its ring slot is free
       tc_fence_after();
       NL_PROF(4);
       float g = 0.f;
@@ -573,7 +573,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
         if (d_last) sxacc[wg * kRows + r] = xsum;
         tc_fence_before();
         __syncthreads();
-        if (tid == 0 && ch + 1 < nch) {
+        if (ch + 1 < nch && warp == 0 && elect_one()) {
           tc_fence_after();
           issue_L3(g0 + ch + 1);
           umma_commit(&bar_main);
@@ -591,7 +591,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
           tc_fence_after();
           const uint32_t w3 = w3_slot_addr(g0 + ch);
           // dH2 (+)= dO . W3c       (A K-major over the NP columns, B = W3c viewed MN-major)
@@ -629,7 +629,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
       wait_aux();  // dW3 of the last chunk reads the dO image
       tc_fence_after();
       if (GENERAL && nch - 1 >= n_resident) dw3_to_slab(nch - 1, TM.dW3 + 80 * n_resident, true);
-      if (tid == 0) w3_issue_upto(g0 + nch - 1 + kStages + 1);
+      if (warp == 0 && elect_one()) w3_issue_upto(g0 + nch - 1 + kStages + 1);
 #pragma unroll
       for (int i = 0; i < kColsPerWg; i += 8) store_chunk8(dO_hi, dO_lo, kRows, r, wg * kColsPerWg + i, &z[i]);
       fence_async_smem();
@@ -637,7 +637,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
       __syncthreads();
       NL_PROF(8);
       // ---- 6. dH1 = Z2g . W2 ;  dW2 += Z2g^T . [h1 | 1 p]
-      if (tid == 0) {
+      if (warp == 0 && elect_one()) {
         tc_fence_after();
         const GemmOp gdh1 = make_gemm(adO, (uint32_t)L.dO_img, kRows, 0, aW2, (uint32_t)L.W2_img, kH, 1, 128, kH, kH);
         issue_gemm(gdh1, tmem + TM.S, false);
@@ -683,7 +683,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
       __syncthreads();
       NL_PROF(10);
       // ---- 8. D1 (+)= Z1g^T . [1 p]   (M=64, N=8; B = chunk 8 of the h1 image)
-      if (tid == 0) {
+      if (warp == 0 && elect_one()) {
         tc_fence_after();
         const GemmOp gd1 = make_gemm(adO, (uint32_t)L.dO_img, kRows, 1, aH1 + 8 * (kRows * 16), (uint32_t)L.H1_img,
                                      kRows, 1, 64, 8, kRows);

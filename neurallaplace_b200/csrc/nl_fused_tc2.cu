@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_tc2_kernel(Args A) {
 
   if (warp == 2 * kStreamThreads / 32) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t aW2 = smem_u32(W2_hi);
       uint32_t aH[kStreams], adO[kStreams];
       for (int s = 0; s < kStreams; ++s) {

@@ -25,6 +25,22 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a fully converged warp (deterministic for a given member mask).  tcgen05.mma must be issued from a
+// branch on THIS predicate: ptxas then knows the region is single-lane and keeps the descriptors in uniform
+// registers.  Behind a plain `tid == 0` test it wraps every UTCHMMA in a per-lane "waterfall" loop (ELECT +
+// BRA.U.ANY + 4 R2UR), measured at ~90 clk per MMA instead of ~50 (scripts/mb/tc_mb.cu).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- mbarrier ---------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

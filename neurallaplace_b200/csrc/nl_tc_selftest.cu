@@ -51,7 +51,7 @@ umma_selftest_kernel(const float* __restrict__ A, int rowsA, int colsA, int a_mn
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  if (tid == 0) {
+  if (warp == 0 && elect_one()) {
     GemmOp g;
     if (a_mn) operand_mnmajor(smem_u32(a_hi), (uint32_t)a_bytes, rowsA, &g.a_hi, &g.a_lo_off, &g.a_lbo, &g.a_sbo, &g.a_step);
     else      operand_kmajor(smem_u32(a_hi), (uint32_t)a_bytes, rowsA, &g.a_hi, &g.a_lo_off, &g.a_lbo, &g.a_sbo, &g.a_step);
