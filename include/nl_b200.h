@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define NL_B200_ABI_VERSION 1
+#define NL_B200_ABI_VERSION 2
 
 typedef enum nl_status {
   NL_OK = 0,
@@ -106,6 +106,25 @@ int nl_reconstruct_backward(const nl_desc* desc, const void* p, const void* t,
                             const void* const* weights, const void* beta, const void* eta,
                             const void* grad_x, void* const* grads, void* workspace,
                             size_t workspace_bytes, void* cuda_stream);
+
+/* Training variant of the pair above (what autograd's saved-tensor mechanism does for the reference's
+ * op chain -- every intermediate of core.py:104-150 is kept for backward; here only the two hidden
+ * activations are).  nl_reconstruct_forward_save additionally writes the hidden activations h1, h2 of
+ * the laplace_rep_func MLP (as the bf16 hi/lo tensor-core operand images, 512 B per (b,t) point) into
+ * `saved` (nl_saved_bytes(desc) bytes, caller-owned, must stay untouched until the backward call);
+ * nl_reconstruct_backward_saved streams them back instead of recomputing layers 1-2.  Results are
+ * bit-identical to nl_reconstruct_forward / within rounding of nl_reconstruct_backward.
+ * nl_saved_bytes returns 0 when the shape is not covered (use the plain pair).                     */
+size_t nl_saved_bytes(const nl_desc* desc);
+int nl_reconstruct_forward_save(const nl_desc* desc, const void* p, const void* t,
+                                const void* const* weights, const void* beta, const void* eta,
+                                void* x, void* saved, size_t saved_bytes, void* workspace,
+                                size_t workspace_bytes, void* cuda_stream);
+int nl_reconstruct_backward_saved(const nl_desc* desc, const void* p, const void* t,
+                                  const void* const* weights, const void* beta, const void* eta,
+                                  const void* grad_x, const void* saved, size_t saved_bytes,
+                                  void* const* grads, void* workspace, size_t workspace_bytes,
+                                  void* cuda_stream);
 
 /* ---- split path (arbitrary user laplace_rep_func, and the class-level ILT API) -------
  * nl_query_points: <ILT>.compute_s (inverse_laplace.py:316-344, 494-496, 703-735, 1122-1147,

@@ -32,6 +32,9 @@ EXPORTS = (
     "nl_last_launch_count",
     "nl_reconstruct_forward",
     "nl_reconstruct_backward",
+    "nl_saved_bytes",
+    "nl_reconstruct_forward_save",
+    "nl_reconstruct_backward_saved",
     "nl_query_points",
     "nl_line_integrate_forward",
     "nl_line_integrate_backward",
@@ -96,6 +99,12 @@ def load():
     lib.nl_reconstruct_forward.argtypes = [dp, vp, vp, pp, vp, vp, vp, vp, sz, vp]
     lib.nl_reconstruct_backward.restype = i32
     lib.nl_reconstruct_backward.argtypes = [dp, vp, vp, pp, vp, vp, vp, pp, vp, sz, vp]
+    lib.nl_saved_bytes.restype = sz
+    lib.nl_saved_bytes.argtypes = [dp]
+    lib.nl_reconstruct_forward_save.restype = i32
+    lib.nl_reconstruct_forward_save.argtypes = [dp, vp, vp, pp, vp, vp, vp, vp, sz, vp, sz, vp]
+    lib.nl_reconstruct_backward_saved.restype = i32
+    lib.nl_reconstruct_backward_saved.argtypes = [dp, vp, vp, pp, vp, vp, vp, vp, sz, pp, vp, sz, vp]
     lib.nl_query_points.restype = i32
     lib.nl_query_points.argtypes = [dp, i64, vp, vp, vp, vp, vp, vp]
     lib.nl_line_integrate_forward.restype = i32

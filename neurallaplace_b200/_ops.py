@@ -59,13 +59,26 @@ class ReconstructFn(torch.autograd.Function):
     weights = [w.contiguous() for w in (W1, b1, W2, b2, W3, b3)]
     x = torch.empty((B, T, D), dtype=p.dtype, device=dev)
     pc, tc = p.contiguous(), t.contiguous()
-    st = lib.nl_reconstruct_forward(ctypes.byref(d), _lib.ptr(pc), _lib.ptr(tc), _lib.ptr_array(weights),
-                                    _lib.ptr(beta), _lib.ptr(eta), _lib.ptr(x), _lib.ptr(ws), nbytes,
-                                    _lib.stream_ptr())
+    # Training: keep the two hidden activations for backward (the analogue of autograd's saved tensors,
+    # 512 B per (b,t) point) so that backward does not recompute layers 1-2.  NL_B200_STASH=0 disables it.
+    saved, saved_bytes = None, 0
+    if any(ctx.needs_input_grad) and os.environ.get("NL_B200_STASH", "1") != "0":
+      saved_bytes = int(lib.nl_saved_bytes(ctypes.byref(d)))
+      if saved_bytes:
+        saved = torch.empty(saved_bytes, dtype=torch.uint8, device=dev)
+    if saved is not None:
+      st = lib.nl_reconstruct_forward_save(ctypes.byref(d), _lib.ptr(pc), _lib.ptr(tc), _lib.ptr_array(weights),
+                                           _lib.ptr(beta), _lib.ptr(eta), _lib.ptr(x), _lib.ptr(saved), saved_bytes,
+                                           _lib.ptr(ws), nbytes, _lib.stream_ptr())
+    else:
+      st = lib.nl_reconstruct_forward(ctypes.byref(d), _lib.ptr(pc), _lib.ptr(tc), _lib.ptr_array(weights),
+                                      _lib.ptr(beta), _lib.ptr(eta), _lib.ptr(x), _lib.ptr(ws), nbytes,
+                                      _lib.stream_ptr())
     _lib.check(st)
     _stats["launches"] += lib.nl_last_launch_count()
     ctx.save_for_backward(pc, tc, *weights)
     ctx.meta = (consts, D, t_mode, head, impl)
+    ctx.saved_act = saved
     return x
 
   @staticmethod
@@ -82,9 +95,16 @@ class ReconstructFn(torch.autograd.Function):
     beta, eta = consts.tables_on(dev)
     grads = [torch.empty_like(w) for w in weights] + [torch.empty_like(pc)]
     gxc = gx.contiguous()
-    st = lib.nl_reconstruct_backward(ctypes.byref(d), _lib.ptr(pc), _lib.ptr(tc), _lib.ptr_array(weights),
-                                     _lib.ptr(beta), _lib.ptr(eta), _lib.ptr(gxc), _lib.ptr_array(grads),
-                                     _lib.ptr(ws), nbytes, _lib.stream_ptr())
+    saved = ctx.saved_act
+    if saved is not None:
+      st = lib.nl_reconstruct_backward_saved(ctypes.byref(d), _lib.ptr(pc), _lib.ptr(tc), _lib.ptr_array(weights),
+                                             _lib.ptr(beta), _lib.ptr(eta), _lib.ptr(gxc), _lib.ptr(saved),
+                                             saved.numel(), _lib.ptr_array(grads), _lib.ptr(ws), nbytes,
+                                             _lib.stream_ptr())
+    else:
+      st = lib.nl_reconstruct_backward(ctypes.byref(d), _lib.ptr(pc), _lib.ptr(tc), _lib.ptr_array(weights),
+                                       _lib.ptr(beta), _lib.ptr(eta), _lib.ptr(gxc), _lib.ptr_array(grads),
+                                       _lib.ptr(ws), nbytes, _lib.stream_ptr())
     _lib.check(st)
     _stats["launches"] += lib.nl_last_launch_count()
     gW1, gb1, gW2, gb2, gW3, gb3, gp = grads

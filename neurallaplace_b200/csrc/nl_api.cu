@@ -81,9 +81,15 @@ int nl_selected_impl(const nl_desc* d, int pass) {
   return pick_impl(d, pass);
 }
 
+static size_t saved_bytes(const nl_desc* d) {
+  if (check_fused(d)) return 0;
+  if (pick_impl(d, 0) != 2 || pick_impl(d, 1) != 2) return 0;
+  return nl::tc_saved_bytes(d);
+}
+
 static int reconstruct(const nl_desc* d, bool bwd, const void* p, const void* t, const void* const* weights,
                        const void* beta, const void* eta, void* x, const void* gx, void* const* grads, void* ws,
-                       size_t ws_bytes, void* stream) {
+                       size_t ws_bytes, void* stream, void* saved = nullptr, size_t saved_size = 0) {
   g_launches = 0;
   int s = check_fused(d);
   if (s) return s;
@@ -104,6 +110,11 @@ static int reconstruct(const nl_desc* d, bool bwd, const void* p, const void* t,
   const int pass = bwd ? 1 : 0;
   const int impl = pick_impl(d, pass);
   if (impl == 0) return NL_ERR_UNSUPPORTED;
+  if (saved) {
+    const size_t sb = saved_bytes(d);
+    if (sb == 0) return NL_ERR_UNSUPPORTED;
+    if (saved_size < sb) return NL_ERR_WORKSPACE;
+  }
   const size_t need = nl_workspace_bytes(d, pass);
   if (need > 0 && (!ws || ws_bytes < need)) return NL_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
@@ -121,10 +132,11 @@ static int reconstruct(const nl_desc* d, bool bwd, const void* p, const void* t,
     if (force == 2) use2 = true;
     if (use2 && !ok2) use2 = false;
     if (!use2 && !ok1) use2 = true;
+    if (saved) use2 = false;  // the activation stash is written / read by the one-stream kernels
     if (use2)
       e = nl::launch_fused_tc2(d, bwd, p, t, weights, beta, eta, x, gx, grads, ws, st, &g_launches);
     else
-      e = nl::launch_fused_tc(d, bwd, p, t, weights, beta, eta, x, gx, grads, ws, st, &g_launches);
+      e = nl::launch_fused_tc(d, bwd, p, t, weights, beta, eta, x, gx, grads, ws, st, &g_launches, empty ? nullptr : saved);
   } else if (d->dtype == NL_F64) {
     e = nl::launch_fused_simt<double>(d, bwd, p, t, weights, beta, eta, x, gx, grads, ws, st, &g_launches);
   } else {
@@ -143,6 +155,23 @@ int nl_reconstruct_backward(const nl_desc* d, const void* p, const void* t, cons
                             const void* beta, const void* eta, const void* grad_x, void* const* grads, void* ws,
                             size_t ws_bytes, void* stream) {
   return reconstruct(d, true, p, t, weights, beta, eta, nullptr, grad_x, grads, ws, ws_bytes, stream);
+}
+
+size_t nl_saved_bytes(const nl_desc* d) { return saved_bytes(d); }
+
+int nl_reconstruct_forward_save(const nl_desc* d, const void* p, const void* t, const void* const* weights,
+                                const void* beta, const void* eta, void* x, void* saved, size_t saved_size, void* ws,
+                                size_t ws_bytes, void* stream) {
+  if (!saved) return NL_ERR_NULL;
+  return reconstruct(d, false, p, t, weights, beta, eta, x, nullptr, nullptr, ws, ws_bytes, stream, saved, saved_size);
+}
+
+int nl_reconstruct_backward_saved(const nl_desc* d, const void* p, const void* t, const void* const* weights,
+                                  const void* beta, const void* eta, const void* grad_x, const void* saved,
+                                  size_t saved_size, void* const* grads, void* ws, size_t ws_bytes, void* stream) {
+  if (!saved) return NL_ERR_NULL;
+  return reconstruct(d, true, p, t, weights, beta, eta, nullptr, grad_x, grads, ws, ws_bytes, stream,
+                     const_cast<void*>(saved), saved_size);
 }
 
 int nl_query_points(const nl_desc* d, int64_t rows, const void* t, const void* Tper, const void* beta, void* s_out,

@@ -59,6 +59,12 @@ constexpr int kH2Cols = 80;  // h2 image: 64 + [1, 0 x 15]
 constexpr int kMaxK = 7;     // latent dim that fits the extra chunk of the h1 image
 constexpr int kStages = 3;   // W3 ring depth
 constexpr int kMaxB3Smem = 4096;  // floats of packed b3 kept in shared memory
+// Activation stash: the forward pass can save the bf16 hi/lo operand images of h1 and h2 (the first 64
+// columns, 128 rows x 64 x 2 B = 16 KB per image) per tile; the "saved" backward kernel streams them back
+// with bulk-async copies instead of recomputing layers 1-2 (512 B per (b,t) point each way through HBM
+// against ~40 % of the backward's CUDA-core work).
+constexpr uint32_t kStashImg = 128 * 64 * 2;
+constexpr size_t kStashTile = 4 * (size_t)kStashImg;
 
 struct TcArgs {
   IltParams<float> P;
@@ -76,6 +82,7 @@ struct TcArgs {
   float* slab;
   long long slab_len;
   float* dp;
+  unsigned char* stash;  // optional [ntiles][h1_hi | h1_lo | h2_hi | h2_lo] operand images (16 KB each), see kStashTile
   long long* prof;  // optional: per-phase clock totals of thread 0 (NL_TC_PROFILE builds)
 };
 
@@ -85,11 +92,11 @@ struct TcSmem {
   int S1b, W1p, b2, b3, coef, u, G1, xacc, misc, nfloats;  // float offsets inside `small`
 };
 
-__host__ __device__ inline TcSmem tc_smem(bool bwd, int NP, int nch, int nkc, int w3_slots, int n) {
+__host__ __device__ inline TcSmem tc_smem(bool bwd, int NP, int nch, int nkc, int w3_slots, int n, bool stash = false) {
   TcSmem L;
   L.dO_img = bwd ? image_bytes(kRows, NP > kH ? NP : kH) : 0;  // also hosts Z2g / Z1g (64 columns)
   L.H1_img = image_bytes(kRows, bwd ? kH1Cols : kH);
-  L.H2_img = bwd ? image_bytes(kRows, kH2Cols) : 0;
+  L.H2_img = bwd ? image_bytes(kRows, kH2Cols) : (stash ? image_bytes(kRows, kH) : 0);  // forward: h2 aliases h1 unless stashing
   L.W2_img = image_bytes(kH, kH);
   L.W3_img = image_bytes(NP, kH);
   size_t o = 0;
@@ -149,6 +156,19 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, 
                : "memory");
 }
 
+// bulk-async shared -> global copy (bulk-group completion)
+__device__ __forceinline__ void bulk_store(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
+
 // W3 / b3 -> per-chunk bf16 hi/lo operand images (row jj of chunk ch <-> W3 row of (d, k, theta|phi))
 __global__ void pack_w3_kernel(const float* __restrict__ W3, const float* __restrict__ b3, int D, int n, int nkc,
                                int kc, int NP, int nch, unsigned char* __restrict__ w3pack,
@@ -181,7 +201,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
   constexpr uint32_t kTmemCols = BWD ? 512 : 256;
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar_main;
-  __shared__ __align__(8) uint64_t bar_d1;
+  __shared__ __align__(8) uint64_t bar_aux[3];  // weight-gradient GEMMs: 0 = dW3, 1 = dW2, 2 = D1
   __shared__ __align__(8) uint64_t bar_w3[kStages];
   __shared__ uint32_t tmem_slot;
 
@@ -190,14 +210,15 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
   const bool streamed = GENERAL && A.w3_slots < nch;
   const int n_resident = GENERAL ? A.resident : nch;
   const int acc_slots = BWD ? (n_resident < nch ? n_resident + 1 : n_resident) : 0;
-  const TcSmem L = tc_smem(BWD, NP, nch, A.nkc, A.w3_slots, n);
+  const bool stash = !BWD && A.stash != nullptr;
+  const TcSmem L = tc_smem(BWD, NP, nch, A.nkc, A.w3_slots, n, stash);
   const TcTmem TM = tc_tmem(BWD, NP, acc_slots);
   unsigned char* dO_hi = smem + L.dO;
   unsigned char* dO_lo = dO_hi + L.dO_img;
   unsigned char* H1_hi = smem + L.H1;
   unsigned char* H1_lo = H1_hi + L.H1_img;
-  unsigned char* H2_hi = BWD ? smem + L.H2 : H1_hi;
-  unsigned char* H2_lo = BWD ? H2_hi + L.H2_img : H1_lo;
+  unsigned char* H2_hi = (BWD || stash) ? smem + L.H2 : H1_hi;
+  unsigned char* H2_lo = (BWD || stash) ? H2_hi + L.H2_img : H1_lo;
   unsigned char* W2_hi = smem + L.W2;
   unsigned char* W2_lo = W2_hi + L.W2_img;
   unsigned char* W3_base = smem + L.W3;
@@ -247,7 +268,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
   if (warp == 0) tmem_alloc(&tmem_slot, kTmemCols);
   if (tid == 0) {
     mbar_init(&bar_main, 1);
-    mbar_init(&bar_d1, 1);
+    for (int j = 0; j < 3; ++j) mbar_init(&bar_aux[j], 1);
     for (int s = 0; s < kStages; ++s) mbar_init(&bar_w3[s], 1);
     fence_mbar_init();
   }
@@ -289,18 +310,26 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
     if (streamed) mbar_wait(&bar_w3[g % kStages], (uint32_t)((g / kStages) & 1));
   };
 
-  // bar_main: results the epilogue needs next (Z2, O, dH2, dH1).  bar_d1 ("aux"): weight-gradient GEMMs
-  // (dW3, dW2, D1), committed separately so they run behind the epilogue math; it is only waited for
-  // right before the shared-memory images they read are overwritten.
-  uint32_t ph_main = 0, ph_d1 = 0;
-  bool d1_pending = false;
-  auto wait_aux = [&]() {
-    if (d1_pending) {
-      mbar_wait(&bar_d1, ph_d1);
-      ph_d1 ^= 1;
-      d1_pending = false;
-    }
+  // bar_main: results the epilogue needs next (Z2, O, dH2, dH1), issued by warp 0.  bar_aux[j]: the
+  // weight-gradient GEMMs (dW3, dW2, D1).  Each of them is issued by the first warp of ANOTHER warpgroup
+  // (a tcgen05.mma dispatch blocks its issuing thread for ~50 clk, 24 of them per GEMM), right after
+  // warp 0 has queued the main-chain GEMM of the same stage, so neither their issue nor their execution
+  // sits on warp 0's critical path; they are only waited for right before the shared-memory images they
+  // read are overwritten.
+  uint32_t ph_main = 0;
+  uint32_t ph_aux0 = 0, ph_aux1 = 0, ph_aux2 = 0;
+  bool pend_aux0 = false, pend_aux1 = false, pend_aux2 = false;
+  auto wait_dw3 = [&]() {
+    if (pend_aux0) { mbar_wait(&bar_aux[0], ph_aux0); ph_aux0 ^= 1; pend_aux0 = false; }
   };
+  auto wait_dw2 = [&]() {
+    if (pend_aux1) { mbar_wait(&bar_aux[1], ph_aux1); ph_aux1 ^= 1; pend_aux1 = false; }
+  };
+  auto wait_d1 = [&]() {
+    if (pend_aux2) { mbar_wait(&bar_aux[2], ph_aux2); ph_aux2 ^= 1; pend_aux2 = false; }
+  };
+  constexpr int kWarpDW3 = 4, kWarpDW2 = 8, kWarpD1 = 12;  // backward only (16 warps)
+  auto pair_bar = [&](int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); };
 
   const uint32_t aH1 = smem_u32(H1_hi), aH2 = smem_u32(H2_hi), aW2 = smem_u32(W2_hi), adO = smem_u32(dO_hi);
   const GemmOp gL2 = make_gemm(aH1, (uint32_t)L.H1_img, kRows, 0, aW2, (uint32_t)L.W2_img, kH, 0, 128, kH, kH);
@@ -356,7 +385,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
   // flush of the per-slot accumulator D1 = Z1g^T.[1 p]: db1, dW1p and the rank-1 update dW1s += G1 (x) u
   auto flush_slot = [&]() {
     if (!BWD || cur_t < 0) return;
-    wait_aux();
+    wait_d1();
     tc_fence_after();
     if (wg == 0) {
       float v[8];
@@ -464,7 +493,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
       for (int j = 0; j < KP; ++j) z = fmaf(sW1p[c * 8 + j], pv[j], z);
       h1[i] = fast::tanh_fast(z);
     }
-    if (BWD) wait_aux();  // the previous tile's D1 GEMM reads the [1 p] chunk of the h1 image
+    if (BWD) wait_d1();  // the previous tile's D1 GEMM reads the [1 p] chunk of the h1 image (and Z1g in the dO image)
 #pragma unroll
     for (int i = 0; i < kColsPerWg; i += 8) store_chunk8(H1_hi, H1_lo, kRows, r, wg * kColsPerWg + i, &h1[i]);
     if (BWD && wg == 0) {
@@ -476,6 +505,8 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
     }
     fence_async_smem();
     tc_fence_before();
+    // stash: the h2 image is rewritten after this barrier -> its previous bulk store must have read it
+    if (!BWD && stash && warp == 0 && elect_one()) bulk_wait_read_all();
     __syncthreads();
 
     NL_PROF(1);
@@ -484,6 +515,12 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
       tc_fence_after();
       issue_gemm(gL2, tmem + TM.S, false);
       umma_commit(&bar_main);
+      if (!BWD && stash) {
+        unsigned char* dst = A.stash + (size_t)tile * kStashTile;
+        bulk_store(dst, H1_hi, kStashImg);
+        bulk_store(dst + kStashImg, H1_lo, kStashImg);
+        bulk_commit();
+      }
     }
     mbar_wait(&bar_main, ph_main);
     ph_main ^= 1;
@@ -504,6 +541,8 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
     for (int i = 0; i < kColsPerWg; i += 8) store_chunk8(H2_hi, H2_lo, kRows, r, wg * kColsPerWg + i, &h2[i]);
     fence_async_smem();
     tc_fence_before();
+    // stash: the h1 image is rewritten by the next tile -> its bulk store must have read it
+    if (!BWD && stash && warp == 0 && elect_one()) bulk_wait_read_all();
     __syncthreads();
 
     NL_PROF(3);
@@ -511,7 +550,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
     auto issue_L3 = [&](long long g) {  // thread 0
       w3_wait(g);
       tc_fence_after();
-      const GemmOp gg = make_gemm(aH2, (uint32_t)(BWD ? L.H2_img : L.H1_img), kRows, 0, w3_slot_addr(g),
+      const GemmOp gg = make_gemm(aH2, (uint32_t)((BWD || stash) ? L.H2_img : L.H1_img), kRows, 0, w3_slot_addr(g),
                                   (uint32_t)L.W3_img, NP, 0, 128, NP, kH);
       issue_gemm(gg, tmem + TM.O, false);
     };
@@ -519,6 +558,12 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
       tc_fence_after();
       issue_L3(g0);
       umma_commit(&bar_main);
+      if (!BWD && stash) {
+        unsigned char* dst = A.stash + (size_t)tile * kStashTile + 2 * kStashImg;
+        bulk_store(dst, H2_hi, kStashImg);
+        bulk_store(dst + kStashImg, H2_lo, kStashImg);
+        bulk_commit();
+      }
     }
     float xsum = 0.f;
     for (int ch = 0; ch < nch; ++ch) {
@@ -527,7 +572,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
       mbar_wait(&bar_main, ph_main);
       ph_main ^= 1;
       if (BWD && ch > 0) {
-        wait_aux();  // dW3(ch-1) still reads the dO image
+        wait_dw3();  // dW3(ch-1) still reads the dO image
         tc_fence_after();
         if (GENERAL && ch - 1 >= n_resident) dw3_to_slab(ch - 1, TM.dW3 + 80 * n_resident, true);
         if (warp == 0 && elect_one()) w3_issue_upto(g0 + ch - 1 + kStages + 1);  // the ring slot of chunk ch-1 is free again
@@ -591,22 +636,32 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
-        if (warp == 0 && elect_one()) {
-          tc_fence_after();
-          const uint32_t w3 = w3_slot_addr(g0 + ch);
-          // dH2 (+)= dO . W3c       (A K-major over the NP columns, B = W3c viewed MN-major)
-          const GemmOp gdh = make_gemm(adO, (uint32_t)L.dO_img, kRows, 0, w3, (uint32_t)L.W3_img, NP, 1, 128, kH, NP);
-          issue_gemm(gdh, tmem + TM.S, ch > 0);
-          if (ch + 1 < nch) issue_L3(g0 + ch + 1);
-          umma_commit(&bar_main);
-          // dW3c (+)= dO^T . [h2 | 1] (both MN-major, reduction over the 128 rows; lanes >= NP are scratch)
-          const GemmOp gdw = make_gemm(adO, (uint32_t)L.dO_img, kRows, 1, aH2, (uint32_t)L.H2_img, kRows, 1, 128,
-                                       kH2Cols, kRows);
-          const bool res = ch < n_resident;
-          issue_gemm(gdw, tmem + TM.dW3 + 80 * (res ? ch : n_resident), res ? !first_tile : false);
-          umma_commit(&bar_d1);
+        if (warp == 0) {
+          if (elect_one()) {
+            tc_fence_after();
+            const uint32_t w3 = w3_slot_addr(g0 + ch);
+            // dH2 (+)= dO . W3c       (A K-major over the NP columns, B = W3c viewed MN-major)
+            const GemmOp gdh = make_gemm(adO, (uint32_t)L.dO_img, kRows, 0, w3, (uint32_t)L.W3_img, NP, 1, 128, kH, NP);
+            issue_gemm(gdh, tmem + TM.S, ch > 0);
+            if (ch + 1 < nch) issue_L3(g0 + ch + 1);
+            umma_commit(&bar_main);
+          }
+          __syncwarp();
+          pair_bar(1);  // the main-chain GEMMs are queued: release the dW3 issuer
+        } else if (warp == kWarpDW3) {
+          pair_bar(1);
+          if (elect_one()) {
+            tc_fence_after();
+            // dW3c (+)= dO^T . [h2 | 1] (both MN-major, reduction over the 128 rows; lanes >= NP are scratch)
+            const GemmOp gdw = make_gemm(adO, (uint32_t)L.dO_img, kRows, 1, aH2, (uint32_t)L.H2_img, kRows, 1, 128,
+                                         kH2Cols, kRows);
+            const bool res = ch < n_resident;
+            issue_gemm(gdw, tmem + TM.dW3 + 80 * (res ? ch : n_resident), res ? !first_tile : false);
+            umma_commit(&bar_aux[0]);
+          }
+          __syncwarp();
         }
-        d1_pending = true;
+        pend_aux0 = true;
       }
       NL_PROF(6);
     }
@@ -626,7 +681,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
 #pragma unroll
         for (int j = 0; j < 16; ++j) z[i + j] = v[j] * (1.f - h2[i + j] * h2[i + j]);
       }
-      wait_aux();  // dW3 of the last chunk reads the dO image
+      wait_dw3();  // dW3 of the last chunk reads the dO image
       tc_fence_after();
       if (GENERAL && nch - 1 >= n_resident) dw3_to_slab(nch - 1, TM.dW3 + 80 * n_resident, true);
       if (warp == 0 && elect_one()) w3_issue_upto(g0 + nch - 1 + kStages + 1);
@@ -637,17 +692,27 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
       __syncthreads();
       NL_PROF(8);
       // ---- 6. dH1 = Z2g . W2 ;  dW2 += Z2g^T . [h1 | 1 p]
-      if (warp == 0 && elect_one()) {
-        tc_fence_after();
-        const GemmOp gdh1 = make_gemm(adO, (uint32_t)L.dO_img, kRows, 0, aW2, (uint32_t)L.W2_img, kH, 1, 128, kH, kH);
-        issue_gemm(gdh1, tmem + TM.S, false);
-        umma_commit(&bar_main);
-        const GemmOp gdw2 = make_gemm(adO, (uint32_t)L.dO_img, kRows, 1, aH1, (uint32_t)L.H1_img, kRows, 1, 64,
-                                      kH1Cols, kRows);
-        issue_gemm(gdw2, tmem + TM.dW2, !first_tile);
-        umma_commit(&bar_d1);
+      if (warp == 0) {
+        if (elect_one()) {
+          tc_fence_after();
+          const GemmOp gdh1 = make_gemm(adO, (uint32_t)L.dO_img, kRows, 0, aW2, (uint32_t)L.W2_img, kH, 1, 128, kH, kH);
+          issue_gemm(gdh1, tmem + TM.S, false);
+          umma_commit(&bar_main);
+        }
+        __syncwarp();
+        pair_bar(2);
+      } else if (warp == kWarpDW2) {
+        pair_bar(2);
+        if (elect_one()) {
+          tc_fence_after();
+          const GemmOp gdw2 = make_gemm(adO, (uint32_t)L.dO_img, kRows, 1, aH1, (uint32_t)L.H1_img, kRows, 1, 64,
+                                        kH1Cols, kRows);
+          issue_gemm(gdw2, tmem + TM.dW2, !first_tile);
+          umma_commit(&bar_aux[1]);
+        }
+        __syncwarp();
       }
-      d1_pending = true;
+      pend_aux1 = true;
       mbar_wait(&bar_main, ph_main);
       ph_main ^= 1;
       tc_fence_after();
@@ -675,7 +740,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
         for (int q = 0; q < KP; ++q)
           if (q < K) atomicAdd(A.dp + (size_t)b * K + q, dpv[q]);
       }
-      wait_aux();  // dW2 reads Z2g in the dO image
+      wait_dw2();  // dW2 reads Z2g in the dO image
 #pragma unroll
       for (int i = 0; i < kColsPerWg; i += 8) store_chunk8(dO_hi, dO_lo, kRows, r, wg * kColsPerWg + i, &z[i]);
       fence_async_smem();
@@ -683,14 +748,14 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
       __syncthreads();
       NL_PROF(10);
       // ---- 8. D1 (+)= Z1g^T . [1 p]   (M=64, N=8; B = chunk 8 of the h1 image)
-      if (warp == 0 && elect_one()) {
+      if (warp == kWarpD1 && elect_one()) {
         tc_fence_after();
         const GemmOp gd1 = make_gemm(adO, (uint32_t)L.dO_img, kRows, 1, aH1 + 8 * (kRows * 16), (uint32_t)L.H1_img,
                                      kRows, 1, 64, 8, kRows);
         issue_gemm(gd1, tmem + TM.D1, !first_in_slot);
-        umma_commit(&bar_d1);
+        umma_commit(&bar_aux[2]);
       }
-      d1_pending = true;
+      pend_aux2 = true;
     }
     first_tile = false;
     first_in_slot = false;
@@ -708,6 +773,608 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
       tc_fence_after();
       for (int ch = 0; ch < min(nch, n_resident); ++ch) dw3_to_slab(ch, TM.dW3 + 80 * ch, false);
       // dW2: M=64 accumulator
+      const int j = (warp & 3) * 16 + lane;
+      const bool ok = lane < 16;
+      for (int i = 0; i < kColsPerWg; i += 16) {
+        float v[16];
+        tmem_ld16(lane_addr + TM.dW2 + wg * kColsPerWg + i, v);
+        tmem_ld_wait();
+        if (ok)
+#pragma unroll
+          for (int q = 0; q < 16; ++q) gW2[j * kH + wg * kColsPerWg + i + q] = v[q];
+      }
+      if (wg == 0) {
+        float v[8];
+        tmem_ld8(lane_addr + TM.dW2 + kH, v);
+        tmem_ld_wait();
+        if (ok) gb2[j] = v[0];
+      }
+    }
+  }
+  if (!BWD && stash && warp == 0 && elect_one()) bulk_wait_all();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, kTmemCols);
+}
+
+
+// =============================================================================================
+// Backward from the activation stash ("saved" backward).  Same math and operand layouts as the BWD
+// instantiation of fused_tc_kernel, but layers 1-2 are NOT recomputed: the h1 / h2 operand images the
+// forward pass stashed are streamed back with bulk-async copies (h2 of tile i+1 while tile i is in its
+// last stage, h1 of tile i at the start of tile i -- it is first needed two stages later), and their
+// values are re-read from shared memory for the tanh derivatives.  Z2g has its own image, so the dW3
+// GEMM no longer blocks the Z2g store.  Requires every W3 chunk resident in shared memory and every
+// dW3 accumulator resident in TMEM (d_obs x terms beyond that uses the recomputing kernel).
+struct BsSmem {
+  size_t dO, Z, H1, H2, W2, W3, small, total;
+  size_t dO_img, Z_img, H1_img, H2_img, W2_img, W3_img;
+  int W1p, b3, coef, u, G1, misc, nfloats;
+  bool zsep;
+};
+__host__ __device__ inline BsSmem bs_smem(int NP, int nch, int nkc, int n, bool zsep) {
+  BsSmem L;
+  L.zsep = zsep;
+  L.dO_img = image_bytes(kRows, NP > kH ? NP : kH);
+  L.Z_img = zsep ? image_bytes(kRows, kH) : 0;
+  L.H1_img = image_bytes(kRows, kH1Cols);
+  L.H2_img = image_bytes(kRows, kH2Cols);
+  L.W2_img = image_bytes(kH, kH);
+  L.W3_img = image_bytes(NP, kH);
+  size_t o = 0;
+  L.dO = o; o += 2 * L.dO_img;
+  L.Z = zsep ? o : L.dO; o += 2 * L.Z_img;
+  L.H1 = o; o += 2 * L.H1_img;
+  L.H2 = o; o += 2 * L.H2_img;
+  L.W2 = o; o += 2 * L.W2_img;
+  L.W3 = o; o += 2 * L.W3_img * nch;
+  L.small = o;
+  int f = 0;
+  L.W1p = f; f += kH * 8;
+  L.b3 = f; f += nch * NP;
+  L.coef = f; f += nkc * NP;
+  L.u = f; f += 2 * n + 8;
+  L.G1 = f; f += kH * 8;
+  L.misc = f; f += 16;
+  L.nfloats = f;
+  L.total = o + (size_t)f * 4 + 64;
+  return L;
+}
+
+// reload 8 consecutive columns of this thread's row from a hi/lo image pair (v = hi + lo)
+__device__ __forceinline__ void load_chunk8(const unsigned char* img_hi, const unsigned char* img_lo, int rows, int r,
+                                            int c0, float* v) {
+  const size_t off = (size_t)(c0 >> 3) * ((size_t)rows * 16) + (size_t)r * 16;
+  const uint4 h = *reinterpret_cast<const uint4*>(img_hi + off);
+  const uint4 l = *reinterpret_cast<const uint4*>(img_lo + off);
+  const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(hh[i] << 16) + __uint_as_float(ll[i] << 16);
+    v[2 * i + 1] = __uint_as_float(hh[i] & 0xFFFF0000u) + __uint_as_float(ll[i] & 0xFFFF0000u);
+  }
+}
+
+constexpr int kBsThreads = 128 * kEwgBwd + 128;  // 4 epilogue warpgroups + 1 issuer warpgroup
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_load_tx(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+// Warp roles: warps 0-15 = epilogue (thread <-> row, warpgroups split the columns), warp 16 issues the
+// main-chain GEMMs (L3, dH2, dH1), warp 17 the weight-gradient GEMMs (dW3, dW2, D1) and the bulk-async loads
+// of the stashed h1 / h2 images.  A tcgen05.mma dispatch blocks its issuing thread for ~50 clk (24 per
+// weight-gradient GEMM), so no epilogue warp ever issues one.  640 threads cap the kernel at 96 registers per
+// thread; the epilogue (16 columns per thread, h1 / h2 re-read from shared memory) needs 86.
+template <int KP>
+__global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArgs A, int zsep_i) {
+  constexpr int kEWG = kEwgBwd;
+  constexpr int kEpi = 128 * kEWG;
+  constexpr int kColsPerWg = kH / kEWG;
+  constexpr uint32_t kTmemCols = 512;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar_main;    // dH2(ch) [+ L3(ch+1)], dH1            issuer 16 -> epilogue
+  __shared__ __align__(8) uint64_t bar_l3;      // L3(0) of a tile                       issuer 16 -> epilogue
+  __shared__ __align__(8) uint64_t bar_aux[3];  // dW3 / dW2 / D1 complete               issuer 17 -> epilogue, 17
+  __shared__ __align__(8) uint64_t bar_h1;      // stashed h1 image landed               TMA -> epilogue, 17
+  __shared__ __align__(8) uint64_t bar_h2;      // stashed h2 image landed               TMA -> epilogue, 16
+  __shared__ __align__(8) uint64_t rdy_dO;      // dO(ch) image stored                   epilogue -> 16, 17
+  __shared__ __align__(8) uint64_t rdy_z2;      // Z2g image stored                      epilogue -> 16, 17
+  __shared__ __align__(8) uint64_t rdy_z1;      // Z1g image stored                      epilogue -> 17
+  __shared__ __align__(8) uint64_t seq_l3, seq_dh2, seq_dh1;  // that main-chain GEMM is queued   16 -> 17
+  __shared__ uint32_t tmem_slot;
+
+  const IltParams<float> P = A.P;
+  const int n = A.n, K = A.K, D = A.D, NP = A.NP, nch = A.nch;
+  const bool zsep = zsep_i != 0;
+  const BsSmem L = bs_smem(NP, nch, A.nkc, n, zsep);
+  const TcTmem TM = tc_tmem(true, NP, nch);
+  unsigned char* dO_hi = smem + L.dO;
+  unsigned char* dO_lo = dO_hi + L.dO_img;
+  unsigned char* Z_hi = smem + L.Z;
+  unsigned char* Z_lo = Z_hi + (zsep ? L.Z_img : L.dO_img);
+  unsigned char* H1_hi = smem + L.H1;
+  unsigned char* H1_lo = H1_hi + L.H1_img;
+  unsigned char* H2_hi = smem + L.H2;
+  unsigned char* H2_lo = H2_hi + L.H2_img;
+  unsigned char* W2_hi = smem + L.W2;
+  unsigned char* W2_lo = W2_hi + L.W2_img;
+  unsigned char* W3_base = smem + L.W3;
+  float* sf = reinterpret_cast<float*>(smem + L.small);
+  float* sW1p = sf + L.W1p;
+  float* sb3 = sf + L.b3;
+  float* sCoef = sf + L.coef;
+  float* su = sf + L.u;
+  float* sG1 = sf + L.G1;
+  float* smisc = sf + L.misc;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wg = tid >> 7;
+  const int r = tid & 127;
+  const int ldw1 = 2 * n + K;
+  const uint32_t w3_bytes = (uint32_t)(2 * L.W3_img);
+
+  const long long per = A.ntiles / gridDim.x, rem = A.ntiles % gridDim.x;
+  const long long tile_lo = blockIdx.x * per + min((long long)blockIdx.x, rem);
+  const long long tile_hi = tile_lo + per + (blockIdx.x < rem ? 1 : 0);
+
+  // ---- prologue (all 640 threads)
+  for (size_t i = tid; i < L.total / 16; i += kBsThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  if (tid < kH) {
+    for (int c0 = 0; c0 < kH; c0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = __ldg(A.W2 + tid * kH + c0 + i);
+      store_chunk8(W2_hi, W2_lo, kH, tid, c0, v);
+    }
+    for (int j = 0; j < K; ++j) sW1p[tid * 8 + j] = __ldg(A.W1 + (size_t)tid * ldw1 + 2 * n + j);
+  }
+  for (int idx = tid; idx < nch * NP; idx += kBsThreads) sb3[idx] = __ldg(A.b3pack + idx);
+  // constant "ones" column of the h2 image (chunk 8; the streamed images only cover chunks 0-7) -> db3
+  if (tid < kRows) *reinterpret_cast<uint32_t*>(H2_hi + (size_t)8 * (kRows * 16) + (size_t)tid * 16) = 0x00003F80u;
+  if (warp == 0) tmem_alloc(&tmem_slot, kTmemCols);
+  if (tid == 0) {
+    mbar_init(&bar_main, 1);
+    mbar_init(&bar_l3, 1);
+    for (int j = 0; j < 3; ++j) mbar_init(&bar_aux[j], 1);
+    mbar_init(&bar_h1, 1);
+    mbar_init(&bar_h2, 1);
+    mbar_init(&rdy_dO, 1);
+    mbar_init(&rdy_z2, 1);
+    mbar_init(&rdy_z1, 1);
+    mbar_init(&seq_l3, 1);
+    mbar_init(&seq_dh2, 1);
+    mbar_init(&seq_dh1, 1);
+    fence_mbar_init();
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  const uint32_t aH1 = smem_u32(H1_hi), aH2 = smem_u32(H2_hi), aW2 = smem_u32(W2_hi), adO = smem_u32(dO_hi),
+                 aZ = smem_u32(Z_hi);
+  const uint32_t z_lo_off = (uint32_t)(zsep ? L.Z_img : L.dO_img);
+
+  if (warp >= kEpi / 32) {
+    // =============================== issuer warpgroup ===============================
+    if (warp == kEpi / 32) {
+      // ---- main-chain GEMMs
+      if (elect_one()) {
+        __shared__ __align__(8) uint64_t bar_w3;
+        mbar_init(&bar_w3, 1);
+        fence_mbar_init();
+        if (tile_lo < tile_hi)
+          for (int ch = 0; ch < nch; ++ch) {
+            bulk_load(W3_base + (size_t)ch * w3_bytes, A.w3pack + (size_t)ch * w3_bytes, w3_bytes, &bar_w3);
+            mbar_wait(&bar_w3, ch & 1);
+          }
+        uint32_t p_h2 = 0, p_dO = 0, p_z2 = 0;
+        for (long long tile = tile_lo; tile < tile_hi; ++tile) {
+          auto issue_L3 = [&](int ch) {
+            const GemmOp gg = make_gemm(aH2, (uint32_t)L.H2_img, kRows, 0, smem_u32(W3_base + (size_t)ch * w3_bytes),
+                                        (uint32_t)L.W3_img, NP, 0, 128, NP, kH);
+            issue_gemm(gg, tmem + TM.O, false);
+          };
+          // O is free: the heads of the previous tile were done before its last rdy_dO (consumed below)
+          mbar_wait(&bar_h2, p_h2);
+          p_h2 ^= 1;
+          tc_fence_after();
+          issue_L3(0);
+          umma_commit(&bar_l3);
+          mbar_arrive(&seq_l3);  // releases dW2 of the previous tile (runs behind this L3, under the head math)
+          for (int ch = 0; ch < nch; ++ch) {
+            mbar_wait(&rdy_dO, p_dO);
+            p_dO ^= 1;
+            tc_fence_after();
+            const uint32_t w3 = smem_u32(W3_base + (size_t)ch * w3_bytes);
+            const GemmOp gdh = make_gemm(adO, (uint32_t)L.dO_img, kRows, 0, w3, (uint32_t)L.W3_img, NP, 1, 128, kH, NP);
+            issue_gemm(gdh, tmem + TM.S, ch > 0);
+            if (ch + 1 < nch) issue_L3(ch + 1);
+            umma_commit(&bar_main);
+            mbar_arrive(&seq_dh2);
+          }
+          mbar_wait(&rdy_z2, p_z2);
+          p_z2 ^= 1;
+          tc_fence_after();
+          const GemmOp gdh1 = make_gemm(aZ, z_lo_off, kRows, 0, aW2, (uint32_t)L.W2_img, kH, 1, 128, kH, kH);
+          issue_gemm(gdh1, tmem + TM.S, false);
+          umma_commit(&bar_main);
+          mbar_arrive(&seq_dh1);
+        }
+      }
+    } else if (warp == kEpi / 32 + 1) {
+      // ---- weight-gradient GEMMs + streamed activation images
+      if (elect_one()) {
+        auto load_h1 = [&](long long tl) {
+          const unsigned char* src = A.stash + (size_t)tl * kStashTile;
+          mbar_expect_tx(&bar_h1, 2 * kStashImg);
+          bulk_load_tx(H1_hi, src, kStashImg, &bar_h1);
+          bulk_load_tx(H1_lo, src + kStashImg, kStashImg, &bar_h1);
+        };
+        auto load_h2 = [&](long long tl) {
+          const unsigned char* src = A.stash + (size_t)tl * kStashTile + 2 * kStashImg;
+          mbar_expect_tx(&bar_h2, 2 * kStashImg);
+          bulk_load_tx(H2_hi, src, kStashImg, &bar_h2);
+          bulk_load_tx(H2_lo, src + kStashImg, kStashImg, &bar_h2);
+        };
+        if (tile_lo < tile_hi) {
+          load_h2(tile_lo);
+          load_h1(tile_lo);
+          if (tile_lo + 1 < tile_hi) bulk_prefetch_l2(A.stash + (size_t)(tile_lo + 1) * kStashTile, (uint32_t)kStashTile);
+        }
+        uint32_t p_dO = 0, p_z2 = 0, p_z1 = 0, p_sl3 = 0, p_sdh2 = 0, p_sdh1 = 0, p_h1 = 0, p_a0 = 0, p_a1 = 0, p_a2 = 0;
+        bool first_tile = true;
+        int cur_t = -1;
+        // dW2(i) = Z2g^T.[h1 | 1 p] only has to finish before tile i+1 rewrites the Z2g image / reloads h1, so it is
+        // issued behind L3 of tile i+1 and streams its operands while the epilogue is in its math-heavy head
+        // stage (an SS-mode MMA saturates the shared-memory port: issued right after dH1 it starved the
+        // epilogue's Z1g stage, measured 3000 clk instead of 900).
+        auto issue_dw2 = [&](bool accumulate) {
+          mbar_wait(&bar_h1, p_h1);
+          p_h1 ^= 1;
+          tc_fence_after();
+          const GemmOp gdw2 = make_gemm(aZ, z_lo_off, kRows, 1, aH1, (uint32_t)L.H1_img, kRows, 1, 64, kH1Cols, kRows);
+          issue_gemm(gdw2, tmem + TM.dW2, accumulate);
+          umma_commit(&bar_aux[1]);
+        };
+        for (long long tile = tile_lo; tile < tile_hi; ++tile) {
+          const int t_idx = (int)(tile / A.nbt);
+          const bool first_in_slot = t_idx != cur_t;
+          cur_t = t_idx;
+          mbar_wait(&seq_l3, p_sl3);  // L3(0) of this tile is queued
+          p_sl3 ^= 1;
+          if (tile > tile_lo) {
+            issue_dw2(tile > tile_lo + 1);
+            // the h1 image is free once D1 and dW2 of the previous tile have executed: request this tile's h1
+            mbar_wait(&bar_aux[2], p_a2);
+            p_a2 ^= 1;
+            mbar_wait(&bar_aux[1], p_a1);
+            p_a1 ^= 1;
+            load_h1(tile);
+          }
+          for (int ch = 0; ch < nch; ++ch) {
+            mbar_wait(&rdy_dO, p_dO);
+            p_dO ^= 1;
+            mbar_wait(&seq_dh2, p_sdh2);  // dH2(ch) is queued first
+            p_sdh2 ^= 1;
+            if (ch > 0) {  // keep the parity of bar_aux[0] in step (the epilogue waited for it before dO(ch))
+              mbar_wait(&bar_aux[0], p_a0);
+              p_a0 ^= 1;
+            }
+            tc_fence_after();
+            const GemmOp gdw = make_gemm(adO, (uint32_t)L.dO_img, kRows, 1, aH2, (uint32_t)L.H2_img, kRows, 1, 128,
+                                         kH2Cols, kRows);
+            issue_gemm(gdw, tmem + TM.dW3 + 80 * ch, !first_tile);
+            umma_commit(&bar_aux[0]);
+          }
+          // the h2 image is free once the last dW3 has executed: request the next tile's h2
+          mbar_wait(&bar_aux[0], p_a0);
+          p_a0 ^= 1;
+          if (tile + 1 < tile_hi) {
+            load_h2(tile + 1);
+            if (tile + 2 < tile_hi) bulk_prefetch_l2(A.stash + (size_t)(tile + 2) * kStashTile, (uint32_t)kStashTile);
+          }
+          mbar_wait(&rdy_z2, p_z2);  // (consumed to stay in step; dW2 is deferred)
+          p_z2 ^= 1;
+          mbar_wait(&seq_dh1, p_sdh1);  // dH1 queued
+          p_sdh1 ^= 1;
+          mbar_wait(&rdy_z1, p_z1);
+          p_z1 ^= 1;
+          tc_fence_after();
+          const GemmOp gd1 = make_gemm(adO, (uint32_t)L.dO_img, kRows, 1, aH1 + 8 * (kRows * 16), (uint32_t)L.H1_img,
+                                       kRows, 1, 64, 8, kRows);
+          issue_gemm(gd1, tmem + TM.D1, !first_in_slot);
+          umma_commit(&bar_aux[2]);
+          first_tile = false;
+        }
+        if (tile_lo < tile_hi) issue_dw2(tile_hi - tile_lo > 1);
+      }
+    }
+  } else {
+    // =============================== epilogue warpgroups ===============================
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    auto ep_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kEpi) : "memory"); };
+    uint32_t ph_main = 0, ph_l3 = 0, ph_h1 = 0, ph_h2 = 0;
+    uint32_t ph_aux0 = 0, ph_aux1 = 0, ph_aux2 = 0;
+    bool pend_aux0 = false, pend_aux1 = false, pend_aux2 = false;
+    auto wait_dw3 = [&]() {
+      if (pend_aux0) { mbar_wait(&bar_aux[0], ph_aux0); ph_aux0 ^= 1; pend_aux0 = false; }
+    };
+    auto wait_dw2 = [&]() {
+      if (pend_aux1) { mbar_wait(&bar_aux[1], ph_aux1); ph_aux1 ^= 1; pend_aux1 = false; }
+    };
+    auto wait_d1 = [&]() {
+      if (pend_aux2) { mbar_wait(&bar_aux[2], ph_aux2); ph_aux2 ^= 1; pend_aux2 = false; }
+    };
+
+    float* slab = A.slab + (long long)blockIdx.x * A.slab_len;
+    float* gW1 = slab;
+    float* gb1 = gW1 + (long long)kH * ldw1;
+    float* gW2 = gb1 + kH;
+    float* gb2 = gW2 + kH * kH;
+    float* gW3 = gb2 + kH;
+    float* gb3 = gW3 + (long long)2 * D * n * kH;
+
+    int cur_t = -1;
+    auto flush_slot = [&]() {
+      if (cur_t < 0) return;
+      wait_d1();
+      tc_fence_after();
+      if (wg == 0) {
+        float v[8];
+        tmem_ld8(lane_addr + TM.D1, v);
+        tmem_ld_wait();
+        if (lane < 16) {
+          const int c = (warp & 3) * 16 + lane;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) sG1[c * 8 + i] = v[i];
+        }
+      }
+      tc_fence_before();
+      ep_sync();
+      for (int idx = tid; idx < kH * 2 * n; idx += kEpi) {
+        const int c = idx / (2 * n), k = idx - c * 2 * n;
+        gW1[(long long)c * ldw1 + k] += sG1[c * 8] * su[k];
+      }
+      for (int idx = tid; idx < kH * (1 + K); idx += kEpi) {
+        const int c = idx / (1 + K), j = idx - c * (1 + K);
+        if (j == 0) gb1[c] += sG1[c * 8];
+        else        gW1[(long long)c * ldw1 + 2 * n + (j - 1)] += sG1[c * 8 + j];
+      }
+      ep_sync();
+    };
+
+    constexpr int kGPre = 4;
+    float pv_n[KP], g_n[kGPre];
+    auto prefetch = [&](long long tl) {
+      const int ti = (int)(tl / A.nbt);
+      const int bn = (int)(tl % A.nbt) * kRows + r;
+      const bool ok = bn < A.B;
+#pragma unroll
+      for (int j = 0; j < KP; ++j) pv_n[j] = (ok && j < K) ? __ldg(A.p + (size_t)bn * K + j) : 0.f;
+#pragma unroll
+      for (int dd = 0; dd < kGPre; ++dd)
+        g_n[dd] = (ok && dd < D) ? __ldg(A.gx + ((size_t)bn * A.T + ti) * D + dd) : 0.f;
+    };
+    if (tile_lo < tile_hi) prefetch(tile_lo);
+    const int ncols_real = min(NP, (2 * A.kc + 3) & ~3);
+    const int cw = (((ncols_real + kEWG - 1) / kEWG) + 3) & ~3;
+
+#ifdef NL_TC_PROFILE
+    long long prof_acc[12] = {0}, prof_last = clock64();
+#endif
+    for (long long tile = tile_lo; tile < tile_hi; ++tile) {
+      const int t_idx = (int)(tile / A.nbt);
+      const int b = (int)(tile % A.nbt) * kRows + r;
+      const bool valid = b < A.B;
+      float pv[KP], graw[kGPre];
+#pragma unroll
+      for (int j = 0; j < KP; ++j) pv[j] = pv_n[j];
+#pragma unroll
+      for (int dd = 0; dd < kGPre; ++dd) graw[dd] = g_n[dd];
+      if (tile + 1 < tile_hi) prefetch(tile + 1);
+
+      // ---- slot context: sphere features (for the rank-1 dW1s update) and reduction coefficients
+      if (t_idx != cur_t) {
+        flush_slot();
+        cur_t = t_idx;
+        const TimeCtx<float> c = make_time_ctx<float>(P, __ldg(A.t + t_idx), nullptr, 0);
+        if (tid == 0) smisc[0] = c.pref;
+        for (int k = tid; k < n; k += kEpi) {
+          float f0, f1;
+          s_features(P, s_point(P, c, k), &f0, &f1);
+          su[k] = f0;
+          su[n + k] = f1;
+        }
+        for (int idx = tid; idx < A.nkc * (NP / 2); idx += kEpi) {
+          const int kci = idx / (NP / 2), q = idx - kci * (NP / 2);
+          const int k = kci * A.kc + q;
+          Cx<float> w{0.f, 0.f};
+          if (q < A.kc && k < n) w = reduce_coef(P, c, k);
+          sCoef[kci * NP + 2 * q] = w.re;
+          sCoef[kci * NP + 2 * q + 1] = w.im;
+        }
+        ep_sync();
+      }
+      const float pref = smisc[0];
+      NL_PROF(0);
+
+      // ---- 1. D1 of the previous tile reads Z1g in the dO image, which the head stage rewrites
+      wait_d1();
+      NL_PROF(1);
+
+      // ---- 2. chunks of layer 3 + heads + dO
+      for (int ch = 0; ch < nch; ++ch) {
+        const int d = ch / A.nkc, kci = ch % A.nkc;
+        if (ch == 0) {
+          mbar_wait(&bar_l3, ph_l3);
+          ph_l3 ^= 1;
+          // landed before L3 could run; waiting here (never blocks) makes the bulk-async writes of the h2 image
+          // visible to this thread's loads in stage 3 and keeps this thread's parity in step with the loads
+          mbar_wait(&bar_h2, ph_h2);
+          ph_h2 ^= 1;
+        } else {
+          mbar_wait(&bar_main, ph_main);
+          ph_main ^= 1;
+          wait_dw3();  // dW3(ch-1) still reads the dO image
+        }
+        tc_fence_after();
+        NL_PROF(4);
+        float gr = 0.f;
+        if (d < kGPre) {
+#pragma unroll
+          for (int dd = 0; dd < kGPre; ++dd)
+            if (dd == d) gr = graw[dd];
+        } else if (valid) {
+          gr = __ldg(A.gx + ((size_t)b * A.T + t_idx) * D + d);
+        }
+        const float g = gr * pref;
+        const float* cf = sCoef + kci * NP;
+        const float* bb3 = sb3 + ch * NP;
+        for (int c0 = wg * cw; c0 < min((wg + 1) * cw, ncols_real); c0 += 4) {
+          float v[4], dv[4];
+          tmem_ld4(lane_addr + TM.O + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int c = c0 + 2 * i;
+            const fast::Head h = fast::head_forward(P.head, v[2 * i] + bb3[c], v[2 * i + 1] + bb3[c + 1]);
+            fast::head_backward(P.head, h, g * cf[c], -g * cf[c + 1], &dv[2 * i], &dv[2 * i + 1]);
+          }
+          store_chunk4(dO_hi, dO_lo, kRows, r, c0, dv);
+        }
+        NL_PROF(5);
+        fence_async_smem();
+        tc_fence_before();
+        ep_sync();
+        if (tid == 0) mbar_arrive(&rdy_dO);
+        pend_aux0 = true;
+        NL_PROF(6);
+      }
+
+      // ---- 3. Z2g = dH2 (1 - h2^2) -> its own image (zsep) or the dO image
+      mbar_wait(&bar_main, ph_main);
+      ph_main ^= 1;
+      tc_fence_after();
+      NL_PROF(7);
+      float z[kColsPerWg];
+#pragma unroll
+      for (int i = 0; i < kColsPerWg; i += 16) {
+        float v[16];
+        tmem_ld16(lane_addr + TM.S + wg * kColsPerWg + i, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 16; q += 8) {
+          float hv[8];
+          load_chunk8(H2_hi, H2_lo, kRows, r, wg * kColsPerWg + i + q, hv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) z[i + q + j] = v[q + j] * (1.f - hv[j] * hv[j]);
+        }
+      }
+      if (!zsep) wait_dw3();  // dW3 of the last chunk reads the dO image
+      wait_dw2();             // dW2 of the PREVIOUS tile (deferred behind this tile's L3) reads the Z2g and h1 images
+      if (wg == 0) {          // this tile's [1 p] chunk of the h1 image (B operand of dW2 and D1)
+        float q[8];
+        q[0] = valid ? 1.f : 0.f;
+#pragma unroll
+        for (int j = 0; j < kMaxK; ++j) q[1 + j] = (j < KP) ? pv[j < KP ? j : 0] : 0.f;
+        store_chunk8(H1_hi, H1_lo, kRows, r, kH, q);
+      }
+#pragma unroll
+      for (int i = 0; i < kColsPerWg; i += 8) store_chunk8(Z_hi, Z_lo, kRows, r, wg * kColsPerWg + i, &z[i]);
+      fence_async_smem();
+      tc_fence_before();
+      ep_sync();
+      if (tid == 0) mbar_arrive(&rdy_z2);
+      NL_PROF(8);
+
+      // ---- 4. Z1g = dH1 (1 - h1^2) -> dO image ; dp
+      mbar_wait(&bar_main, ph_main);
+      ph_main ^= 1;
+      tc_fence_after();
+      NL_PROF(9);
+      mbar_wait(&bar_h1, ph_h1);
+      ph_h1 ^= 1;
+      float dpv[KP];
+#pragma unroll
+      for (int j = 0; j < KP; ++j) dpv[j] = 0.f;
+#pragma unroll
+      for (int i = 0; i < kColsPerWg; i += 16) {
+        float v[16];
+        tmem_ld16(lane_addr + TM.S + wg * kColsPerWg + i, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 16; q += 8) {
+          float hv[8];
+          load_chunk8(H1_hi, H1_lo, kRows, r, wg * kColsPerWg + i + q, hv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float zz = v[q + j] * (1.f - hv[j] * hv[j]);
+            z[i + q + j] = zz;
+            const int c = wg * kColsPerWg + i + q + j;
+#pragma unroll
+            for (int qq = 0; qq < KP; ++qq) dpv[qq] = fmaf(zz, sW1p[c * 8 + qq], dpv[qq]);
+          }
+        }
+      }
+      if (valid) {
+#pragma unroll
+        for (int q = 0; q < KP; ++q)
+          if (q < K) atomicAdd(A.dp + (size_t)b * K + q, dpv[q]);
+      }
+      wait_dw3();  // dW3 of the last chunk reads the dO image
+#pragma unroll
+      for (int i = 0; i < kColsPerWg; i += 8) store_chunk8(dO_hi, dO_lo, kRows, r, wg * kColsPerWg + i, &z[i]);
+      fence_async_smem();
+      tc_fence_before();
+      ep_sync();
+      if (tid == 0) mbar_arrive(&rdy_z1);
+      pend_aux2 = true;  // D1 of this tile
+      pend_aux1 = true;  // dW2 of this tile (issued behind the next tile's L3, or after the loop)
+      NL_PROF(10);
+    }
+#ifdef NL_TC_PROFILE
+    if (tid == 0 && A.prof)
+      for (int i = 0; i < 12; ++i) atomicAdd((unsigned long long*)A.prof + i, (unsigned long long)prof_acc[i]);
+#endif
+
+    // ---- TMEM-resident weight gradients -> this CTA's slab
+    flush_slot();
+    wait_dw2();
+    wait_dw3();
+    if (tile_hi > tile_lo) {
+      tc_fence_after();
+      for (int ch = 0; ch < nch; ++ch) {
+        const int d = ch / A.nkc, k = (ch % A.nkc) * A.kc + (r >> 1);
+        const bool ok = (r >> 1) < A.kc && k < n && r < NP;
+        const int row = ((r & 1) ? (D + d) : d) * n + k;
+        for (int i = 0; i < kColsPerWg; i += 16) {
+          float v[16];
+          tmem_ld16(lane_addr + TM.dW3 + 80 * ch + wg * kColsPerWg + i, v);
+          tmem_ld_wait();
+          if (ok)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) gW3[(long long)row * kH + wg * kColsPerWg + i + j] = v[j];
+        }
+        if (wg == 0) {
+          float v[8];
+          tmem_ld8(lane_addr + TM.dW3 + 80 * ch + kH, v);
+          tmem_ld_wait();
+          if (ok) gb3[row] = v[0];
+        }
+      }
       const int j = (warp & 3) * 16 + lane;
       const bool ok = lane < 16;
       for (int i = 0; i < kColsPerWg; i += 16) {
@@ -744,7 +1411,7 @@ struct TcGeom {
   size_t smem;
   bool ok;
 };
-static TcGeom tc_geom(const nl_desc* d, bool bwd) {
+static TcGeom tc_geom(const nl_desc* d, bool bwd, bool stash = false) {
   TcGeom g{};
   g.nkc = (2 * d->n + 127) / 128;
   g.kc = (d->n + g.nkc - 1) / g.nkc;
@@ -756,8 +1423,8 @@ static TcGeom tc_geom(const nl_desc* d, bool bwd) {
   g.resident = bwd ? (g.nch <= room ? g.nch : room - 1) : 0;
   // shared memory: all chunks resident if they fit (forward: within half an SM so that 2 CTAs co-reside)
   const size_t limit = 227 * 1024 - 1024, half = limit / 2;
-  const tc::TcSmem Lr = tc::tc_smem(bwd, g.NP, g.nch, g.nkc, g.nch, d->n);
-  const tc::TcSmem Ls = tc::tc_smem(bwd, g.NP, g.nch, g.nkc, tc::kStages, d->n);
+  const tc::TcSmem Lr = tc::tc_smem(bwd, g.NP, g.nch, g.nkc, g.nch, d->n, stash);
+  const tc::TcSmem Ls = tc::tc_smem(bwd, g.NP, g.nch, g.nkc, tc::kStages, d->n, stash);
   if (g.nch <= tc::kStages || Lr.total <= (bwd ? limit : half)) {
     g.w3_slots = g.nch;
     g.smem = Lr.total;
@@ -767,6 +1434,35 @@ static TcGeom tc_geom(const nl_desc* d, bool bwd) {
   }
   g.ok = g.smem <= limit;
   return g;
+}
+
+// geometry of the "saved" backward (activation stash): everything resident
+struct BsGeom {
+  bool ok, zsep;
+  size_t smem;
+};
+static BsGeom bs_geom(const nl_desc* d, const TcGeom& g) {
+  BsGeom b{};
+  const int room = (512 - (64 + g.NP + 80 + 16)) / 80;
+  if (g.nch > room) return b;
+  const size_t limit = 227 * 1024 - 1024;
+  for (int zs = 1; zs >= 1; --zs) {  // Z2g must own its image: dW2 is deferred past the Z1g store
+    const tc::BsSmem L = tc::bs_smem(g.NP, g.nch, g.nkc, d->n, zs != 0);
+    if (L.total <= limit) {
+      b.ok = true;
+      b.zsep = zs != 0;
+      b.smem = L.total;
+      return b;
+    }
+  }
+  return b;
+}
+
+size_t tc_saved_bytes(const nl_desc* d) {
+  if (!tc_plan(d, 0).ok || !tc_plan(d, 1).ok) return 0;
+  if (!tc_geom(d, false, true).ok || !bs_geom(d, tc_geom(d, true)).ok) return 0;
+  const long long nbt = (d->B + tc::kRows - 1) / tc::kRows;
+  return (size_t)(nbt * d->T) * tc::kStashTile;
 }
 
 TcPlan tc_plan(const nl_desc* d, int pass) {
@@ -812,12 +1508,29 @@ static cudaError_t launch_tc1(const tc::TcArgs& A, int grid, size_t smem, cudaSt
   return general ? launch_tc1_g<BWD, KP, true>(A, grid, smem, st) : launch_tc1_g<BWD, KP, false>(A, grid, smem, st);
 }
 
+template <int KP>
+static cudaError_t launch_bs(const tc::TcArgs& A, int grid, size_t smem, bool zsep, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(tc::fused_tc_bwd_saved_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem);
+  if (e != cudaSuccess) return e;
+  tc::fused_tc_bwd_saved_kernel<KP><<<grid, tc::kBsThreads, smem, st>>>(A, zsep ? 1 : 0);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_fused_tc(const nl_desc* d, bool bwd, const void* p, const void* t, const void* const* weights,
                             const void* beta, const void* eta, void* x, const void* gx, void* const* grads, void* ws,
-                            cudaStream_t st, int* launches) {
+                            cudaStream_t st, int* launches, void* saved) {
   TcPlan pl = tc_plan(d, bwd ? 1 : 0);
   if (!pl.ok) return cudaErrorInvalidValue;
-  const TcGeom g = tc_geom(d, bwd);
+  TcGeom g = tc_geom(d, bwd, !bwd && saved != nullptr);
+  if (!bwd && saved && !g.ok) {  // no room for the separate h2 image: run without the stash (never happens at H = 64)
+    return cudaErrorInvalidValue;
+  }
+  if (!bwd && saved) {
+    pl.smem = g.smem;
+    pl.co_resident = g.smem <= (227 * 1024 - 1024) / 2;
+  }
+  const BsGeom bg = (bwd && saved) ? bs_geom(d, g) : BsGeom{};
   tc::TcArgs A{};
   A.P.family = d->family;
   A.P.n = d->n;
@@ -836,6 +1549,7 @@ cudaError_t launch_fused_tc(const nl_desc* d, bool bwd, const void* p, const voi
   A.W1 = (const float*)weights[0]; A.b1 = (const float*)weights[1]; A.W2 = (const float*)weights[2];
   A.b2 = (const float*)weights[3];
   A.x = (float*)x; A.gx = (const float*)gx;
+  A.stash = (unsigned char*)saved;
 #ifdef NL_TC_PROFILE
   if (!g_prof_buf) {
     cudaMalloc(&g_prof_buf, 2 * 12 * sizeof(long long));
@@ -869,7 +1583,10 @@ cudaError_t launch_fused_tc(const nl_desc* d, bool bwd, const void* p, const voi
     A.dp = (float*)grads[6];
     e = cudaMemsetAsync(A.dp, 0, (size_t)d->B * d->K * 4, st);
     if (e != cudaSuccess) return e;
-    e = d->K <= 2 ? launch_tc1<true, 2>(A, pl.grid, pl.smem, st) : launch_tc1<true, tc::kMaxK>(A, pl.grid, pl.smem, st);
+    if (bg.ok)
+      e = d->K <= 2 ? launch_bs<2>(A, pl.grid, bg.smem, bg.zsep, st) : launch_bs<tc::kMaxK>(A, pl.grid, bg.smem, bg.zsep, st);
+    else
+      e = d->K <= 2 ? launch_tc1<true, 2>(A, pl.grid, pl.smem, st) : launch_tc1<true, tc::kMaxK>(A, pl.grid, pl.smem, st);
   } else {
     e = d->K <= 2 ? launch_tc1<false, 2>(A, pl.grid, pl.smem, st) : launch_tc1<false, tc::kMaxK>(A, pl.grid, pl.smem, st);
   }

@@ -43,9 +43,12 @@ struct TcPlan {
   int co_resident;  // forward: two CTAs fit on one SM (shared memory <= half)
 };
 TcPlan tc_plan(const nl_desc* d, int pass);
+// `saved`: optional activation stash of tc_saved_bytes(d) bytes -- written by the forward pass, consumed by the
+// backward pass (which then skips the recomputation of layers 1-2); NULL = plain forward / recomputing backward.
 cudaError_t launch_fused_tc(const nl_desc* d, bool bwd, const void* p, const void* t, const void* const* weights,
                             const void* beta, const void* eta, void* x, const void* gx, void* const* grads, void* ws,
-                            cudaStream_t st, int* launches);
+                            cudaStream_t st, int* launches, void* saved = nullptr);
+size_t tc_saved_bytes(const nl_desc* d);
 
 // two-stream warp-specialised variant (nl_fused_tc2.cu); preferred when its smem / TMEM plan fits
 TcPlan tc2_plan(const nl_desc* d, int pass);

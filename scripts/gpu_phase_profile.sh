@@ -29,7 +29,7 @@ out = (ctypes.c_longlong * 24)()
 lib.nl_debug_tc_profile(out, 1)
 x = laplace_reconstruct(f, p, t, recon_dim=D); x.backward(g)
 lib.nl_debug_tc_profile(out, 0)
-names = ["slot-ctx/prefetch", "1 h1 compute+store+sync", "2 issue L2 + wait", "3 h2 tanh+store+sync", "4 issue L3 + wait", "5 element stage", "6 dO fence+sync+issue", "7 wait dH2", "8 Z2g+aux wait+store+sync", "9 issue dH1/dW2 + wait", "10 Z1g+dp+store+sync", "11 issue D1"]
+names = ["slot-ctx/prefetch", "1 h1 compute+store+sync (saved bwd: waits dW2,D1)", "2 issue L2 + wait (saved bwd: wait h2 image)", "3 h2 tanh+store+sync", "4 issue L3 + wait", "5 element stage", "6 dO fence+sync+issue", "7 wait dH2", "8 Z2g+aux wait+store+sync", "9 issue dH1/dW2 + wait", "10 Z1g+dp+store+sync", "11 issue D1"]
 for k, nm in ((0, "forward"), (12, "backward")):
     v = [out[k+i] for i in range(12)]; tot = sum(v)
     print(nm, "total clocks (sum over CTAs) %.3e  per CTA %.0f" % (tot, tot/296 if k == 0 else tot/148))

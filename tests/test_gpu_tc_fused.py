@@ -32,12 +32,15 @@ CASES = [
 ]
 
 
+# the backward either streams the hidden activations the forward stashed (default) or recomputes them
+@pytest.mark.parametrize("stash", ["1", "0"])
 @pytest.mark.parametrize("alg,terms,B,T,D,K,sphere", CASES)
-def test_tc_against_oracle(alg, terms, B, T, D, K, sphere, monkeypatch):
+def test_tc_against_oracle(alg, terms, B, T, D, K, sphere, stash, monkeypatch):
   if not torch.cuda.is_available():
     pytest.skip("no CUDA device")
   dev = torch.device("cuda", 0)
   monkeypatch.setenv("NL_B200_IMPL", "tc")
+  monkeypatch.setenv("NL_B200_STASH", stash)
   from neurallaplace_b200 import _consts, _ops
   from oracle import nl_oracle as orc
   n = orc.IltConsts(alg, terms).n
@@ -53,7 +56,7 @@ def test_tc_against_oracle(alg, terms, B, T, D, K, sphere, monkeypatch):
   x, grads = _run_product(weights, p, t, D, alg, sphere, terms, None, gout, dev)
   ex = hp.rel(x, x_ref)
   eg = [hp.rel(a, b) for a, b in zip(grads, g_ref)]
-  print(f"\n[tc] {alg} terms={terms} B={B} T={T} D={D}: x {ex:.2e} grads " + " ".join(f"{e:.1e}" for e in eg))
+  print(f"\n[tc stash={stash}] {alg} terms={terms} B={B} T={T} D={D}: x {ex:.2e} grads " + " ".join(f"{e:.1e}" for e in eg))
   assert ex <= 1e-4, ex
   for i, e in enumerate(eg):
     assert e <= 1e-4, (i, e)
