@@ -82,6 +82,12 @@ struct TcArgs {
   float* slab;
   long long slab_len;
   float* dp;
+  // per-time-point tables built by time_tables_kernel (forward and saved backward): the s points, their sphere
+  // features, the s part of layer 1 and the reduction coefficients depend on the time index only
+  const float* tabS1;    // [T][64]        S1 + b1
+  const float* tabCoef;  // [T][nkc][NP]   pref * (cr, ci) interleaved, zero in padded columns
+  const float* tabU;     // [T][2n]        (theta_s | phi_s) or (Re s | Im s)
+  float* g1buf;          // [T][64][8]     saved backward: sum over the batch of Z1g (x) [1 p]
   unsigned char* stash;  // optional [ntiles][h1_hi | h1_lo | h2_hi | h2_lo] operand images (16 KB each), see kStashTile
   long long* prof;  // optional: per-phase clock totals of thread 0 (NL_TC_PROFILE builds)
 };
@@ -189,6 +195,73 @@ __global__ void pack_w3_kernel(const float* __restrict__ W3, const float* __rest
     store_chunk8(w_hi, w_lo, NP, jj, c0, v);
   }
   b3pack[idx] = valid ? __ldg(b3 + row) : 0.f;
+}
+
+// One block per time point: s points -> sphere features u_t, S1 = W1s.u_t + b1, pref * reduction coefficients.
+// (with a shared time grid S1[t] is T x H and is computed once, not per (b, t) point.)
+__global__ void __launch_bounds__(128) time_tables_kernel(IltParams<float> P, const float* __restrict__ t,
+                                                           const float* __restrict__ W1, const float* __restrict__ b1,
+                                                           int K, int nkc, int kc, int NP, float* __restrict__ tabS1,
+                                                           float* __restrict__ tabCoef, float* __restrict__ tabU) {
+  extern __shared__ float su[];  // [2n]
+  const int ti = blockIdx.x, tid = threadIdx.x, n = P.n;
+  const TimeCtx<float> c = make_time_ctx<float>(P, __ldg(t + ti), nullptr, 0);
+  for (int k = tid; k < n; k += blockDim.x) {
+    float f0, f1;
+    s_features(P, s_point(P, c, k), &f0, &f1);
+    su[k] = f0;
+    su[n + k] = f1;
+    tabU[(size_t)ti * 2 * n + k] = f0;
+    tabU[(size_t)ti * 2 * n + n + k] = f1;
+  }
+  for (int idx = tid; idx < nkc * (NP / 2); idx += blockDim.x) {
+    const int kci = idx / (NP / 2), q = idx - kci * (NP / 2);
+    const int k = kci * kc + q;
+    Cx<float> w{0.f, 0.f};
+    if (q < kc && k < n) w = reduce_coef(P, c, k);
+    tabCoef[((size_t)ti * nkc + kci) * NP + 2 * q] = c.pref * w.re;
+    tabCoef[((size_t)ti * nkc + kci) * NP + 2 * q + 1] = c.pref * w.im;
+  }
+  __syncthreads();
+  if (tid < kH) {
+    const int ldw1 = 2 * n + K;
+    float acc0 = __ldg(b1 + tid), acc1 = 0.f;
+    const float* w = W1 + (size_t)tid * ldw1;
+    int k = 0;
+    for (; k + 1 < 2 * n; k += 2) {
+      acc0 = fmaf(__ldg(w + k), su[k], acc0);
+      acc1 = fmaf(__ldg(w + k + 1), su[k + 1], acc1);
+    }
+    if (k < 2 * n) acc0 = fmaf(__ldg(w + k), su[k], acc0);
+    tabS1[(size_t)ti * kH + tid] = acc0 + acc1;
+  }
+}
+
+// dW1 / db1 from the per-time-point sums G1[t][c][0..K] = sum_b Z1g[b,t,c] * [1 p_b]:
+//   dW1[c][k<2n] = sum_t G1[t][c][0] u_t[k];  dW1[c][2n+j] = sum_t G1[t][c][1+j];  db1[c] = sum_t G1[t][c][0].
+// grid (64, ceil(T/128)); the outputs were zeroed by the slab reduction and are accumulated with atomics.
+__global__ void __launch_bounds__(128) dw1_from_g1_kernel(const float* __restrict__ g1buf,
+                                                           const float* __restrict__ tabU, int T, int n, int K,
+                                                           float* __restrict__ dW1, float* __restrict__ db1) {
+  __shared__ float sg[128][8];
+  const int c = blockIdx.x, t0 = blockIdx.y * 128, tid = threadIdx.x;
+  const int nt = min(128, T - t0), ldw1 = 2 * n + K;
+  for (int idx = tid; idx < nt * 8; idx += blockDim.x)
+    sg[idx >> 3][idx & 7] = __ldg(g1buf + ((size_t)(t0 + (idx >> 3)) * kH + c) * 8 + (idx & 7));
+  __syncthreads();
+  for (int j = tid; j < ldw1 + 1; j += blockDim.x) {
+    float acc = 0.f;
+    if (j < 2 * n) {
+      for (int tt = 0; tt < nt; ++tt) acc = fmaf(sg[tt][0], __ldg(tabU + (size_t)(t0 + tt) * 2 * n + j), acc);
+      atomicAdd(dW1 + (size_t)c * ldw1 + j, acc);
+    } else if (j < ldw1) {
+      for (int tt = 0; tt < nt; ++tt) acc += sg[tt][1 + (j - 2 * n)];
+      atomicAdd(dW1 + (size_t)c * ldw1 + j, acc);
+    } else {
+      for (int tt = 0; tt < nt; ++tt) acc += sg[tt][0];
+      atomicAdd(db1 + c, acc);
+    }
+  }
 }
 
 // GENERAL = false: every W3 chunk is shared-memory resident and every dW3 accumulator TMEM resident (the
@@ -414,9 +487,8 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
   // software prefetch of the next tile's per-row inputs (p row, upstream gradient) hides their latency
   constexpr int kGPre = 4;
   float pv_n[KP], g_n[kGPre];
-  auto prefetch = [&](long long tl) {
-    const int ti = (int)(tl / A.nbt);
-    const int bn = (int)(tl % A.nbt) * kRows + r;
+  auto prefetch = [&](int ti, int bi) {
+    const int bn = bi * kRows + r;
     const bool ok = bn < A.B;
 #pragma unroll
     for (int j = 0; j < KP; ++j) pv_n[j] = (ok && j < K) ? __ldg(A.p + (size_t)bn * K + j) : 0.f;
@@ -426,7 +498,10 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
         g_n[dd] = (ok && dd < D) ? __ldg(A.gx + ((size_t)bn * A.T + ti) * D + dd) : 0.f;
     }
   };
-  if (tile_lo < tile_hi) prefetch(tile_lo);
+  // (time index, batch block) of the current tile, advanced incrementally: a 64-bit division per thread and
+  // tile cost ~1500 clk of issue slots per tile
+  int t_cur = (int)(tile_lo / A.nbt), b_cur = (int)(tile_lo % A.nbt);
+  if (tile_lo < tile_hi) prefetch(t_cur, b_cur);
   const int ncols_real = min(NP, (2 * A.kc + 3) & ~3);
   const int cw = (((ncols_real + kEWG - 1) / kEWG) + 3) & ~3;
 
@@ -434,8 +509,12 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
   long long prof_acc[12] = {0}, prof_last = clock64();
 #endif
   for (long long tile = tile_lo; tile < tile_hi; ++tile) {
-    const int t_idx = (int)(tile / A.nbt);
-    const int b = (int)(tile % A.nbt) * kRows + r;
+    const int t_idx = t_cur;
+    const int b = b_cur * kRows + r;
+    if (++b_cur == A.nbt) {
+      b_cur = 0;
+      ++t_cur;
+    }
     const bool valid = b < A.B;
     const long long g0 = (tile - tile_lo) * nch;  // chunk-use index of this tile's chunk 0
     float pv[KP], graw[kGPre];
@@ -443,13 +522,21 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
     for (int j = 0; j < KP; ++j) pv[j] = pv_n[j];
 #pragma unroll
     for (int dd = 0; dd < kGPre; ++dd) graw[dd] = BWD ? g_n[dd] : 0.f;
-    if (tile + 1 < tile_hi) prefetch(tile + 1);
+    if (tile + 1 < tile_hi) prefetch(t_cur, b_cur);
 
     // ---- slot context: s points, sphere features, S1 + b1, reduction coefficients
     if (t_idx != cur_t) {
       flush_slot();
       cur_t = t_idx;
       first_in_slot = true;
+      if (!BWD && A.tabCoef) {
+        // forward: everything that depends on the time index only comes from the tables (pref is folded in)
+        for (int idx = tid; idx < A.nkc * NP; idx += kThreadsTc)
+          sCoef[idx] = __ldg(A.tabCoef + (size_t)t_idx * A.nkc * NP + idx);
+        if (tid < kH) sS1b[tid] = __ldg(A.tabS1 + (size_t)t_idx * kH + tid);
+        if (tid == 0) smisc[0] = 1.f;
+        __syncthreads();
+      } else {
       const TimeCtx<float> c = make_time_ctx<float>(P, __ldg(A.t + t_idx), nullptr, 0);
       if (tid == 0) smisc[0] = c.pref;
       for (int k = tid; k < n; k += kThreadsTc) {
@@ -479,6 +566,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
         sS1b[tid] = acc0 + acc1;
       }
       __syncthreads();
+      }
     }
     const float pref = smisc[0];
     NL_PROF(0);
@@ -809,7 +897,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
 struct BsSmem {
   size_t dO, Z, H1, H2, W2, W3, small, total;
   size_t dO_img, Z_img, H1_img, H2_img, W2_img, W3_img;
-  int W1p, b3, coef, u, G1, misc, nfloats;
+  int W1p, b3, coef, nfloats;
   bool zsep;
 };
 __host__ __device__ inline BsSmem bs_smem(int NP, int nch, int nkc, int n, bool zsep) {
@@ -833,9 +921,6 @@ __host__ __device__ inline BsSmem bs_smem(int NP, int nch, int nkc, int n, bool 
   L.W1p = f; f += kH * 8;
   L.b3 = f; f += nch * NP;
   L.coef = f; f += nkc * NP;
-  L.u = f; f += 2 * n + 8;
-  L.G1 = f; f += kH * 8;
-  L.misc = f; f += 16;
   L.nfloats = f;
   L.total = o + (size_t)f * 4 + 64;
   return L;
@@ -913,9 +998,6 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
   float* sW1p = sf + L.W1p;
   float* sb3 = sf + L.b3;
   float* sCoef = sf + L.coef;
-  float* su = sf + L.u;
-  float* sG1 = sf + L.G1;
-  float* smisc = sf + L.misc;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wg = tid >> 7;
@@ -1049,8 +1131,13 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
           issue_gemm(gdw2, tmem + TM.dW2, accumulate);
           umma_commit(&bar_aux[1]);
         };
+        int t_run = (int)(tile_lo / A.nbt), b_run = (int)(tile_lo % A.nbt);
         for (long long tile = tile_lo; tile < tile_hi; ++tile) {
-          const int t_idx = (int)(tile / A.nbt);
+          const int t_idx = t_run;
+          if (++b_run == A.nbt) {
+            b_run = 0;
+            ++t_run;
+          }
           const bool first_in_slot = t_idx != cur_t;
           cur_t = t_idx;
           mbar_wait(&seq_l3, p_sl3);  // L3(0) of this tile is queued
@@ -1120,14 +1207,14 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
     };
 
     float* slab = A.slab + (long long)blockIdx.x * A.slab_len;
-    float* gW1 = slab;
-    float* gb1 = gW1 + (long long)kH * ldw1;
-    float* gW2 = gb1 + kH;
+    float* gW2 = slab + (long long)kH * ldw1 + kH;  // (the dW1 / db1 part of the slab stays zero: see g1buf)
     float* gb2 = gW2 + kH * kH;
     float* gW3 = gb2 + kH;
     float* gb3 = gW3 + (long long)2 * D * n * kH;
 
     int cur_t = -1;
+    // per-slot accumulator D1 = Z1g^T.[1 p] -> G1[t] (a time index can be shared by two CTAs -> atomics);
+    // dw1_from_g1_kernel turns G1 into dW1 / db1 afterwards
     auto flush_slot = [&]() {
       if (cur_t < 0) return;
       wait_d1();
@@ -1136,31 +1223,20 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
         float v[8];
         tmem_ld8(lane_addr + TM.D1, v);
         tmem_ld_wait();
-        if (lane < 16) {
-          const int c = (warp & 3) * 16 + lane;
+        if (lane < 16) {  // M=64 accumulator: rows 16w..16w+15 in lanes 32w..32w+15
+          float* dst = A.g1buf + ((size_t)cur_t * kH + (warp & 3) * 16 + lane) * 8;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) sG1[c * 8 + i] = v[i];
+          for (int i = 0; i < 8; ++i)
+            if (i <= K) atomicAdd(dst + i, v[i]);
         }
       }
       tc_fence_before();
-      ep_sync();
-      for (int idx = tid; idx < kH * 2 * n; idx += kEpi) {
-        const int c = idx / (2 * n), k = idx - c * 2 * n;
-        gW1[(long long)c * ldw1 + k] += sG1[c * 8] * su[k];
-      }
-      for (int idx = tid; idx < kH * (1 + K); idx += kEpi) {
-        const int c = idx / (1 + K), j = idx - c * (1 + K);
-        if (j == 0) gb1[c] += sG1[c * 8];
-        else        gW1[(long long)c * ldw1 + 2 * n + (j - 1)] += sG1[c * 8 + j];
-      }
-      ep_sync();
     };
 
     constexpr int kGPre = 4;
     float pv_n[KP], g_n[kGPre];
-    auto prefetch = [&](long long tl) {
-      const int ti = (int)(tl / A.nbt);
-      const int bn = (int)(tl % A.nbt) * kRows + r;
+    auto prefetch = [&](int ti, int bi) {
+      const int bn = bi * kRows + r;
       const bool ok = bn < A.B;
 #pragma unroll
       for (int j = 0; j < KP; ++j) pv_n[j] = (ok && j < K) ? __ldg(A.p + (size_t)bn * K + j) : 0.f;
@@ -1168,7 +1244,10 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
       for (int dd = 0; dd < kGPre; ++dd)
         g_n[dd] = (ok && dd < D) ? __ldg(A.gx + ((size_t)bn * A.T + ti) * D + dd) : 0.f;
     };
-    if (tile_lo < tile_hi) prefetch(tile_lo);
+    // (time index, batch block) of the current tile, advanced incrementally: a 64-bit division per thread and
+  // tile cost ~1500 clk of issue slots per tile
+  int t_cur = (int)(tile_lo / A.nbt), b_cur = (int)(tile_lo % A.nbt);
+  if (tile_lo < tile_hi) prefetch(t_cur, b_cur);
     const int ncols_real = min(NP, (2 * A.kc + 3) & ~3);
     const int cw = (((ncols_real + kEWG - 1) / kEWG) + 3) & ~3;
 
@@ -1176,39 +1255,28 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
     long long prof_acc[12] = {0}, prof_last = clock64();
 #endif
     for (long long tile = tile_lo; tile < tile_hi; ++tile) {
-      const int t_idx = (int)(tile / A.nbt);
-      const int b = (int)(tile % A.nbt) * kRows + r;
+      const int t_idx = t_cur;
+      const int b = b_cur * kRows + r;
+      if (++b_cur == A.nbt) {
+        b_cur = 0;
+        ++t_cur;
+      }
       const bool valid = b < A.B;
       float pv[KP], graw[kGPre];
 #pragma unroll
       for (int j = 0; j < KP; ++j) pv[j] = pv_n[j];
 #pragma unroll
       for (int dd = 0; dd < kGPre; ++dd) graw[dd] = g_n[dd];
-      if (tile + 1 < tile_hi) prefetch(tile + 1);
+      if (tile + 1 < tile_hi) prefetch(t_cur, b_cur);
 
-      // ---- slot context: sphere features (for the rank-1 dW1s update) and reduction coefficients
+      // ---- slot context: the reduction coefficients of this time index (time_tables_kernel)
       if (t_idx != cur_t) {
         flush_slot();
         cur_t = t_idx;
-        const TimeCtx<float> c = make_time_ctx<float>(P, __ldg(A.t + t_idx), nullptr, 0);
-        if (tid == 0) smisc[0] = c.pref;
-        for (int k = tid; k < n; k += kEpi) {
-          float f0, f1;
-          s_features(P, s_point(P, c, k), &f0, &f1);
-          su[k] = f0;
-          su[n + k] = f1;
-        }
-        for (int idx = tid; idx < A.nkc * (NP / 2); idx += kEpi) {
-          const int kci = idx / (NP / 2), q = idx - kci * (NP / 2);
-          const int k = kci * A.kc + q;
-          Cx<float> w{0.f, 0.f};
-          if (q < A.kc && k < n) w = reduce_coef(P, c, k);
-          sCoef[kci * NP + 2 * q] = w.re;
-          sCoef[kci * NP + 2 * q + 1] = w.im;
-        }
+        for (int idx = tid; idx < A.nkc * NP; idx += kEpi)
+          sCoef[idx] = __ldg(A.tabCoef + (size_t)t_idx * A.nkc * NP + idx);  // pref * (cr, ci)
         ep_sync();
       }
-      const float pref = smisc[0];
       NL_PROF(0);
 
       // ---- 1. D1 of the previous tile reads Z1g in the dO image, which the head stage rewrites
@@ -1240,7 +1308,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
         } else if (valid) {
           gr = __ldg(A.gx + ((size_t)b * A.T + t_idx) * D + d);
         }
-        const float g = gr * pref;
+        const float g = gr;
         const float* cf = sCoef + kci * NP;
         const float* bb3 = sb3 + ch * NP;
         for (int c0 = wg * cw; c0 < min((wg + 1) * cw, ncols_real); c0 += 4) {
@@ -1486,7 +1554,10 @@ TcPlan tc_plan(const nl_desc* d, int pass) {
                           (size_t)2 * d->D * d->n;
   const size_t pack = tc_align((size_t)g.nch * 2 * tc::image_bytes(g.NP, tc::kH), 256) +
                       tc_align((size_t)g.nch * g.NP * 4, 256);
-  pl.ws_bytes = pack + (bwd ? tc_align(slab_len * 4 * pl.grid, 256) : 0) + 512;
+  // per-time-point tables (S1, coefficients, features) + G1 accumulator of the saved backward
+  const size_t tabs = tc_align((size_t)d->T * tc::kH * 4, 256) + tc_align((size_t)d->T * g.nkc * g.NP * 4, 256) +
+                      tc_align((size_t)d->T * 2 * d->n * 4, 256) + (bwd ? tc_align((size_t)d->T * tc::kH * 8 * 4, 256) : 0);
+  pl.ws_bytes = pack + tabs + (bwd ? tc_align(slab_len * 4 * pl.grid, 256) : 0) + 512;
   pl.ok = 1;
   return pl;
 }
@@ -1564,6 +1635,26 @@ cudaError_t launch_fused_tc(const nl_desc* d, bool bwd, const void* p, const voi
   float* b3pack = (float*)w;
   w += tc_align((size_t)g.nch * g.NP * 4, 256);
   A.w3pack = w3pack; A.b3pack = b3pack;
+  float* tabS1 = (float*)w;
+  w += tc_align((size_t)d->T * tc::kH * 4, 256);
+  float* tabCoef = (float*)w;
+  w += tc_align((size_t)d->T * g.nkc * g.NP * 4, 256);
+  float* tabU = (float*)w;
+  w += tc_align((size_t)d->T * 2 * d->n * 4, 256);
+  float* g1buf = nullptr;
+  if (bwd) {
+    g1buf = (float*)w;
+    w += tc_align((size_t)d->T * tc::kH * 8 * 4, 256);
+  }
+  const bool use_tables = !bwd || bg.ok;  // the recomputing backward keeps its in-kernel slot context
+  if (use_tables && d->T > 0) {
+    tc::time_tables_kernel<<<d->T, 128, (size_t)2 * d->n * sizeof(float), st>>>(
+        A.P, A.t, A.W1, A.b1, d->K, g.nkc, g.kc, g.NP, tabS1, tabCoef, tabU);
+    cudaError_t e0 = cudaGetLastError();
+    if (e0 != cudaSuccess) return e0;
+    if (launches) *launches += 1;
+    A.tabS1 = tabS1; A.tabCoef = tabCoef; A.tabU = tabU;
+  }
   {
     const int total = g.nch * g.NP, threads = 128;
     tc::pack_w3_kernel<<<(total + threads - 1) / threads, threads, 0, st>>>(
@@ -1583,6 +1674,11 @@ cudaError_t launch_fused_tc(const nl_desc* d, bool bwd, const void* p, const voi
     A.dp = (float*)grads[6];
     e = cudaMemsetAsync(A.dp, 0, (size_t)d->B * d->K * 4, st);
     if (e != cudaSuccess) return e;
+    if (bg.ok) {
+      A.g1buf = g1buf;
+      e = cudaMemsetAsync(g1buf, 0, (size_t)d->T * tc::kH * 8 * 4, st);
+      if (e != cudaSuccess) return e;
+    }
     if (bg.ok)
       e = d->K <= 2 ? launch_bs<2>(A, pl.grid, bg.smem, bg.zsep, st) : launch_bs<tc::kMaxK>(A, pl.grid, bg.smem, bg.zsep, st);
     else
@@ -1596,6 +1692,13 @@ cudaError_t launch_fused_tc(const nl_desc* d, bool bwd, const void* p, const voi
     e = launch_reduce_slabs_f32(A.slab, A.slab_len, pl.grid, grads, d, st);
     if (e != cudaSuccess) return e;
     if (launches) *launches += 1;
+    if (bg.ok && d->T > 0) {
+      tc::dw1_from_g1_kernel<<<dim3(tc::kH, (d->T + 127) / 128), 128, 0, st>>>(g1buf, tabU, d->T, d->n, d->K,
+                                                                                (float*)grads[0], (float*)grads[1]);
+      e = cudaGetLastError();
+      if (e != cudaSuccess) return e;
+      if (launches) *launches += 1;
+    }
   }
   return cudaSuccess;
 }

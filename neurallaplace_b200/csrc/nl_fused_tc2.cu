@@ -352,9 +352,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_tc2_kernel(Args A) {
     };
 
     float pv_n[KP], g_n[kGPre];
-    auto prefetch = [&](long long tl) {
-      const int ti = (int)(tl / A.nbt);
-      const int bn = (int)(tl % A.nbt) * kRows + r;
+    auto prefetch = [&](int ti, int bi) {
+      const int bn = bi * kRows + r;
       const bool ok = bn < A.B;
 #pragma unroll
       for (int j = 0; j < KP; ++j) pv_n[j] = (ok && j < K) ? __ldg(A.p + (size_t)bn * K + j) : 0.f;
@@ -365,20 +364,27 @@ __global__ void __launch_bounds__(kThreads, 1) fused_tc2_kernel(Args A) {
       }
     };
     const long long tile_lo = s_lo[s], tile_hi = s_lo[s] + s_n[s];
-    if (tile_lo < tile_hi) prefetch(tile_lo);
+    // (time index, batch block) of the current tile, advanced incrementally: a 64-bit division per thread and
+  // tile cost ~1500 clk of issue slots per tile
+  int t_cur = (int)(tile_lo / A.nbt), b_cur = (int)(tile_lo % A.nbt);
+  if (tile_lo < tile_hi) prefetch(t_cur, b_cur);
     const int ncols_real = min(NP, (2 * A.kc + 3) & ~3);
     const int cw = (((ncols_real + 1) / 2) + 3) & ~3;
 
     for (long long tile = tile_lo; tile < tile_hi; ++tile) {
-      const int t_idx = (int)(tile / A.nbt);
-      const int b = (int)(tile % A.nbt) * kRows + r;
+      const int t_idx = t_cur;
+      const int b = b_cur * kRows + r;
+      if (++b_cur == A.nbt) {
+        b_cur = 0;
+        ++t_cur;
+      }
       const bool valid = b < A.B;
       float pv[KP], graw[kGPre];
 #pragma unroll
       for (int j = 0; j < KP; ++j) pv[j] = pv_n[j];
 #pragma unroll
       for (int dd = 0; dd < kGPre; ++dd) graw[dd] = BWD ? g_n[dd] : 0.f;
-      if (tile + 1 < tile_hi) prefetch(tile + 1);
+      if (tile + 1 < tile_hi) prefetch(t_cur, b_cur);
 
       if (t_idx != cur_t) {
         flush_slot();
