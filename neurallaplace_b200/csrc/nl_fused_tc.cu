@@ -50,6 +50,17 @@ namespace tc {
 #define NL_PROF(i) do { } while (0)
 #endif
 
+#ifdef NL_TC_PROFILE
+// NL_TRACE(slot): CTA 0 stamps clock64 for tiles tile_lo+4 .. tile_lo+6 (slot + 20 * (tile - tile_lo - 4))
+#define NL_TRACE(slot)                                                                                   \
+  do {                                                                                                   \
+    if (blockIdx.x == 0 && A.prof && tile >= tile_lo + 4 && tile < tile_lo + 7)                           \
+      A.prof[12 + (slot) + 20 * (int)(tile - tile_lo - 4)] = clock64();                                   \
+  } while (0)
+#else
+#define NL_TRACE(slot) do { } while (0)
+#endif
+
 constexpr int kH = 64;
 constexpr int kRows = 128;
 constexpr int kEwgFwd = 2;  // warpgroups splitting the columns of a tile: forward runs 2 CTAs / SM x 256 threads,
@@ -88,6 +99,7 @@ struct TcArgs {
   const float* tabCoef;  // [T][nkc][NP]   pref * (cr, ci) interleaved, zero in padded columns
   const float* tabU;     // [T][2n]        (theta_s | phi_s) or (Re s | Im s)
   float* g1buf;          // [T][64][8]     saved backward: sum over the batch of Z1g (x) [1 p]
+  float* dp_part;        // [ntiles][128][K] saved backward: per-tile dp contributions (summed over t afterwards)
   unsigned char* stash;  // optional [ntiles][h1_hi | h1_lo | h2_hi | h2_lo] operand images (16 KB each), see kStashTile
   long long* prof;  // optional: per-phase clock totals of thread 0 (NL_TC_PROFILE builds)
 };
@@ -252,7 +264,20 @@ __global__ void __launch_bounds__(128) dw1_from_g1_kernel(const float* __restric
   for (int j = tid; j < ldw1 + 1; j += blockDim.x) {
     float acc = 0.f;
     if (j < 2 * n) {
-      for (int tt = 0; tt < nt; ++tt) acc = fmaf(sg[tt][0], __ldg(tabU + (size_t)(t0 + tt) * 2 * n + j), acc);
+      const float* u = tabU + (size_t)t0 * 2 * n + j;
+      float a[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) a[q] = 0.f;
+      int tt = 0;
+      for (; tt + 7 < nt; tt += 8) {  // 8 independent loads in flight (a rolled loop exposed the L2 latency 128 times)
+        float uv[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) uv[q] = __ldg(u + (size_t)(tt + q) * 2 * n);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) a[q] = fmaf(sg[tt + q][0], uv[q], a[q]);
+      }
+      for (; tt < nt; ++tt) a[0] = fmaf(sg[tt][0], __ldg(u + (size_t)tt * 2 * n), a[0]);
+      acc = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
       atomicAdd(dW1 + (size_t)c * ldw1 + j, acc);
     } else if (j < ldw1) {
       for (int tt = 0; tt < nt; ++tt) acc += sg[tt][1 + (j - 2 * n)];
@@ -264,6 +289,37 @@ __global__ void __launch_bounds__(128) dw1_from_g1_kernel(const float* __restric
   }
 }
 
+// dp[b][q] += sum over a slice of the time tiles of the per-tile partial sums written by the saved backward
+// (dp is zeroed before the backward kernel).  grid = (batch blocks of 128 rows, time slices); thread = (row, q);
+// tile(t, bt) = t * nbt + bt.
+constexpr int kDpSlices = 16;
+__global__ void __launch_bounds__(256) dp_reduce_kernel(const float* __restrict__ part, int B, int T, int K, int nbt,
+                                                        float* __restrict__ dp) {
+  const int bt = blockIdx.x;
+  const int per = (T + gridDim.y - 1) / gridDim.y;
+  const int t_lo = blockIdx.y * per, t_hi = min(T, t_lo + per);
+  for (int e = threadIdx.x; e < kRows * K; e += blockDim.x) {
+    const int r = e / K, q = e - r * K;
+    const int b = bt * kRows + r;
+    if (b >= B) continue;
+    const float* src = part + ((size_t)bt * kRows) * K + e;
+    const size_t stride = (size_t)nbt * kRows * K;
+    float a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = 0.f;
+    int t = t_lo;
+    for (; t + 7 < t_hi; t += 8) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = __ldg(src + (size_t)(t + i) * stride);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] += v[i];
+    }
+    for (; t < t_hi; ++t) a[0] += __ldg(src + (size_t)t * stride);
+    atomicAdd(dp + (size_t)b * K + q, ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7])));
+  }
+}
+
 // GENERAL = false: every W3 chunk is shared-memory resident and every dW3 accumulator TMEM resident (the
 // streaming / scratch-flush code is compiled out of the hot loop); GENERAL = true: any d_obs x terms.
 template <bool BWD, int KP, bool GENERAL>
@@ -272,7 +328,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
   constexpr int kThreadsTc = 128 * kEWG;
   constexpr int kColsPerWg = kH / kEWG;
   constexpr uint32_t kTmemCols = BWD ? 512 : 256;
-  extern __shared__ __align__(1024) unsigned char smem[];
+  extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar_main;
   __shared__ __align__(8) uint64_t bar_aux[3];  // weight-gradient GEMMs: 0 = dW3, 1 = dW2, 2 = D1
   __shared__ __align__(8) uint64_t bar_w3[kStages];
@@ -897,12 +953,14 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
 struct BsSmem {
   size_t dO, Z, H1, H2, W2, W3, small, total;
   size_t dO_img, Z_img, H1_img, H2_img, W2_img, W3_img;
-  int W1p, b3, coef, nfloats;
+  int W1p, b3, coef, dp, nfloats;
   bool zsep;
+  int h2bufs;  // 2: the h2 image is double-buffered (the next tile's h2 streams in a whole tile ahead)
 };
-__host__ __device__ inline BsSmem bs_smem(int NP, int nch, int nkc, int n, bool zsep) {
+__host__ __device__ inline BsSmem bs_smem(int NP, int nch, int nkc, int n, int K, bool zsep, int h2bufs = 1) {
   BsSmem L;
   L.zsep = zsep;
+  L.h2bufs = h2bufs;
   L.dO_img = image_bytes(kRows, NP > kH ? NP : kH);
   L.Z_img = zsep ? image_bytes(kRows, kH) : 0;
   L.H1_img = image_bytes(kRows, kH1Cols);
@@ -913,7 +971,7 @@ __host__ __device__ inline BsSmem bs_smem(int NP, int nch, int nkc, int n, bool 
   L.dO = o; o += 2 * L.dO_img;
   L.Z = zsep ? o : L.dO; o += 2 * L.Z_img;
   L.H1 = o; o += 2 * L.H1_img;
-  L.H2 = o; o += 2 * L.H2_img;
+  L.H2 = o; o += 2 * L.H2_img * h2bufs;
   L.W2 = o; o += 2 * L.W2_img;
   L.W3 = o; o += 2 * L.W3_img * nch;
   L.small = o;
@@ -921,6 +979,7 @@ __host__ __device__ inline BsSmem bs_smem(int NP, int nch, int nkc, int n, bool 
   L.W1p = f; f += kH * 8;
   L.b3 = f; f += nch * NP;
   L.coef = f; f += nkc * NP;
+  L.dp = f; f += kEwgBwd * kRows * K;  // per-warpgroup partial dp of the current tile
   L.nfloats = f;
   L.total = o + (size_t)f * 4 + 64;
   return L;
@@ -961,17 +1020,19 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 // weight-gradient GEMM), so no epilogue warp ever issues one.  640 threads cap the kernel at 96 registers per
 // thread; the epilogue (16 columns per thread, h1 / h2 re-read from shared memory) needs 86.
 template <int KP>
-__global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArgs A, int zsep_i) {
+__global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArgs A, int zsep_i, int h2bufs) {
   constexpr int kEWG = kEwgBwd;
   constexpr int kEpi = 128 * kEWG;
   constexpr int kColsPerWg = kH / kEWG;
   constexpr uint32_t kTmemCols = 512;
-  extern __shared__ __align__(1024) unsigned char smem[];
+  // (un-swizzled operand images need 16-byte alignment only; 1024 would cost 1 KB of the 227 KB budget)
+  extern __shared__ __align__(128) unsigned char smem_bs[];
+  unsigned char* smem = smem_bs;
   __shared__ __align__(8) uint64_t bar_main;    // dH2(ch) [+ L3(ch+1)], dH1            issuer 16 -> epilogue
   __shared__ __align__(8) uint64_t bar_l3;      // L3(0) of a tile                       issuer 16 -> epilogue
   __shared__ __align__(8) uint64_t bar_aux[3];  // dW3 / dW2 / D1 complete               issuer 17 -> epilogue, 17
   __shared__ __align__(8) uint64_t bar_h1;      // stashed h1 image landed               TMA -> epilogue, 17
-  __shared__ __align__(8) uint64_t bar_h2;      // stashed h2 image landed               TMA -> epilogue, 16
+  __shared__ __align__(8) uint64_t bar_h2[2];   // stashed h2 image landed (per buffer)   TMA -> epilogue, 16
   __shared__ __align__(8) uint64_t rdy_dO;      // dO(ch) image stored                   epilogue -> 16, 17
   __shared__ __align__(8) uint64_t rdy_z2;      // Z2g image stored                      epilogue -> 16, 17
   __shared__ __align__(8) uint64_t rdy_z1;      // Z1g image stored                      epilogue -> 17
@@ -981,7 +1042,8 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
   const IltParams<float> P = A.P;
   const int n = A.n, K = A.K, D = A.D, NP = A.NP, nch = A.nch;
   const bool zsep = zsep_i != 0;
-  const BsSmem L = bs_smem(NP, nch, A.nkc, n, zsep);
+  const BsSmem L = bs_smem(NP, nch, A.nkc, n, K, zsep, h2bufs);
+  const bool h2db = h2bufs == 2;
   const TcTmem TM = tc_tmem(true, NP, nch);
   unsigned char* dO_hi = smem + L.dO;
   unsigned char* dO_lo = dO_hi + L.dO_img;
@@ -989,8 +1051,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
   unsigned char* Z_lo = Z_hi + (zsep ? L.Z_img : L.dO_img);
   unsigned char* H1_hi = smem + L.H1;
   unsigned char* H1_lo = H1_hi + L.H1_img;
-  unsigned char* H2_hi = smem + L.H2;
-  unsigned char* H2_lo = H2_hi + L.H2_img;
+  unsigned char* H2_base = smem + L.H2;  // buffer q: hi image at q * 2 * H2_img, lo image right behind it
   unsigned char* W2_hi = smem + L.W2;
   unsigned char* W2_lo = W2_hi + L.W2_img;
   unsigned char* W3_base = smem + L.W3;
@@ -998,6 +1059,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
   float* sW1p = sf + L.W1p;
   float* sb3 = sf + L.b3;
   float* sCoef = sf + L.coef;
+  float* sdp = sf + L.dp;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wg = tid >> 7;
@@ -1023,14 +1085,18 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
   }
   for (int idx = tid; idx < nch * NP; idx += kBsThreads) sb3[idx] = __ldg(A.b3pack + idx);
   // constant "ones" column of the h2 image (chunk 8; the streamed images only cover chunks 0-7) -> db3
-  if (tid < kRows) *reinterpret_cast<uint32_t*>(H2_hi + (size_t)8 * (kRows * 16) + (size_t)tid * 16) = 0x00003F80u;
+  if (tid < kRows)
+    for (int q = 0; q < h2bufs; ++q)
+      *reinterpret_cast<uint32_t*>(H2_base + (size_t)q * 2 * L.H2_img + (size_t)8 * (kRows * 16) + (size_t)tid * 16) =
+          0x00003F80u;
   if (warp == 0) tmem_alloc(&tmem_slot, kTmemCols);
   if (tid == 0) {
     mbar_init(&bar_main, 1);
     mbar_init(&bar_l3, 1);
     for (int j = 0; j < 3; ++j) mbar_init(&bar_aux[j], 1);
     mbar_init(&bar_h1, 1);
-    mbar_init(&bar_h2, 1);
+    mbar_init(&bar_h2[0], 1);
+    mbar_init(&bar_h2[1], 1);
     mbar_init(&rdy_dO, 1);
     mbar_init(&rdy_z2, 1);
     mbar_init(&rdy_z1, 1);
@@ -1045,8 +1111,10 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
 
-  const uint32_t aH1 = smem_u32(H1_hi), aH2 = smem_u32(H2_hi), aW2 = smem_u32(W2_hi), adO = smem_u32(dO_hi),
+  const uint32_t aH1 = smem_u32(H1_hi), aH2_0 = smem_u32(H2_base), aW2 = smem_u32(W2_hi), adO = smem_u32(dO_hi),
                  aZ = smem_u32(Z_hi);
+  const uint32_t h2_stride = (uint32_t)(2 * L.H2_img);  // bytes between the two h2 buffers
+  // tile i of this CTA uses h2 buffer (i - tile_lo) & 1 (double-buffered) or 0
   const uint32_t z_lo_off = (uint32_t)(zsep ? L.Z_img : L.dO_img);
 
   if (warp >= kEpi / 32) {
@@ -1060,37 +1128,43 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
         if (tile_lo < tile_hi)
           for (int ch = 0; ch < nch; ++ch) {
             bulk_load(W3_base + (size_t)ch * w3_bytes, A.w3pack + (size_t)ch * w3_bytes, w3_bytes, &bar_w3);
-            mbar_wait(&bar_w3, ch & 1);
+            mbar_wait_relaxed(&bar_w3, ch & 1);
           }
-        uint32_t p_h2 = 0, p_dO = 0, p_z2 = 0;
+        uint32_t p_h2[2] = {0, 0}, p_dO = 0, p_z2 = 0;
         for (long long tile = tile_lo; tile < tile_hi; ++tile) {
+          const int hb = h2db ? (int)((tile - tile_lo) & 1) : 0;
+          const uint32_t aH2 = aH2_0 + hb * h2_stride;
           auto issue_L3 = [&](int ch) {
             const GemmOp gg = make_gemm(aH2, (uint32_t)L.H2_img, kRows, 0, smem_u32(W3_base + (size_t)ch * w3_bytes),
                                         (uint32_t)L.W3_img, NP, 0, 128, NP, kH);
             issue_gemm(gg, tmem + TM.O, false);
           };
           // O is free: the heads of the previous tile were done before its last rdy_dO (consumed below)
-          mbar_wait(&bar_h2, p_h2);
-          p_h2 ^= 1;
+          mbar_wait_relaxed(&bar_h2[hb], p_h2[hb]);
+          p_h2[hb] ^= 1;
           tc_fence_after();
+          NL_TRACE(10);
           issue_L3(0);
           umma_commit(&bar_l3);
+          NL_TRACE(11);
           mbar_arrive(&seq_l3);  // releases dW2 of the previous tile (runs behind this L3, under the head math)
           for (int ch = 0; ch < nch; ++ch) {
-            mbar_wait(&rdy_dO, p_dO);
+            mbar_wait_relaxed(&rdy_dO, p_dO);
             p_dO ^= 1;
             tc_fence_after();
             const uint32_t w3 = smem_u32(W3_base + (size_t)ch * w3_bytes);
             const GemmOp gdh = make_gemm(adO, (uint32_t)L.dO_img, kRows, 0, w3, (uint32_t)L.W3_img, NP, 1, 128, kH, NP);
+            NL_TRACE(12);
             issue_gemm(gdh, tmem + TM.S, ch > 0);
             if (ch + 1 < nch) issue_L3(ch + 1);
             umma_commit(&bar_main);
             mbar_arrive(&seq_dh2);
           }
-          mbar_wait(&rdy_z2, p_z2);
+          mbar_wait_relaxed(&rdy_z2, p_z2);
           p_z2 ^= 1;
           tc_fence_after();
           const GemmOp gdh1 = make_gemm(aZ, z_lo_off, kRows, 0, aW2, (uint32_t)L.W2_img, kH, 1, 128, kH, kH);
+          NL_TRACE(13);
           issue_gemm(gdh1, tmem + TM.S, false);
           umma_commit(&bar_main);
           mbar_arrive(&seq_dh1);
@@ -1106,10 +1180,12 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
           bulk_load_tx(H1_lo, src + kStashImg, kStashImg, &bar_h1);
         };
         auto load_h2 = [&](long long tl) {
+          const int hb = h2db ? (int)((tl - tile_lo) & 1) : 0;
+          unsigned char* dst = H2_base + (size_t)hb * 2 * L.H2_img;
           const unsigned char* src = A.stash + (size_t)tl * kStashTile + 2 * kStashImg;
-          mbar_expect_tx(&bar_h2, 2 * kStashImg);
-          bulk_load_tx(H2_hi, src, kStashImg, &bar_h2);
-          bulk_load_tx(H2_lo, src + kStashImg, kStashImg, &bar_h2);
+          mbar_expect_tx(&bar_h2[hb], 2 * kStashImg);
+          bulk_load_tx(dst, src, kStashImg, &bar_h2[hb]);
+          bulk_load_tx(dst + L.H2_img, src + kStashImg, kStashImg, &bar_h2[hb]);
         };
         if (tile_lo < tile_hi) {
           load_h2(tile_lo);
@@ -1124,7 +1200,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
         // stage (an SS-mode MMA saturates the shared-memory port: issued right after dH1 it starved the
         // epilogue's Z1g stage, measured 3000 clk instead of 900).
         auto issue_dw2 = [&](bool accumulate) {
-          mbar_wait(&bar_h1, p_h1);
+          mbar_wait_relaxed(&bar_h1, p_h1);
           p_h1 ^= 1;
           tc_fence_after();
           const GemmOp gdw2 = make_gemm(aZ, z_lo_off, kRows, 1, aH1, (uint32_t)L.H1_img, kRows, 1, 64, kH1Cols, kRows);
@@ -1140,50 +1216,61 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
           }
           const bool first_in_slot = t_idx != cur_t;
           cur_t = t_idx;
-          mbar_wait(&seq_l3, p_sl3);  // L3(0) of this tile is queued
+          mbar_wait_relaxed(&seq_l3, p_sl3);  // L3(0) of this tile is queued
           p_sl3 ^= 1;
           if (tile > tile_lo) {
+            NL_TRACE(17);
             issue_dw2(tile > tile_lo + 1);
+            NL_TRACE(18);
             // the h1 image is free once D1 and dW2 of the previous tile have executed: request this tile's h1
-            mbar_wait(&bar_aux[2], p_a2);
+            mbar_wait_relaxed(&bar_aux[2], p_a2);
             p_a2 ^= 1;
-            mbar_wait(&bar_aux[1], p_a1);
+            mbar_wait_relaxed(&bar_aux[1], p_a1);
             p_a1 ^= 1;
             load_h1(tile);
           }
+          // double-buffered h2: the other buffer was last read by tile-1 (L3, dW3, the Z2g stage), all finished
+          if (h2db && tile + 1 < tile_hi) {
+            load_h2(tile + 1);
+            if (tile + 2 < tile_hi) bulk_prefetch_l2(A.stash + (size_t)(tile + 2) * kStashTile, (uint32_t)kStashTile);
+          }
+          const uint32_t aH2 = aH2_0 + (h2db ? (uint32_t)((tile - tile_lo) & 1) : 0u) * h2_stride;
           for (int ch = 0; ch < nch; ++ch) {
-            mbar_wait(&rdy_dO, p_dO);
+            mbar_wait_relaxed(&rdy_dO, p_dO);
             p_dO ^= 1;
-            mbar_wait(&seq_dh2, p_sdh2);  // dH2(ch) is queued first
+            mbar_wait_relaxed(&seq_dh2, p_sdh2);  // dH2(ch) is queued first
             p_sdh2 ^= 1;
             if (ch > 0) {  // keep the parity of bar_aux[0] in step (the epilogue waited for it before dO(ch))
-              mbar_wait(&bar_aux[0], p_a0);
+              mbar_wait_relaxed(&bar_aux[0], p_a0);
               p_a0 ^= 1;
             }
             tc_fence_after();
             const GemmOp gdw = make_gemm(adO, (uint32_t)L.dO_img, kRows, 1, aH2, (uint32_t)L.H2_img, kRows, 1, 128,
                                          kH2Cols, kRows);
+            NL_TRACE(14);
             issue_gemm(gdw, tmem + TM.dW3 + 80 * ch, !first_tile);
             umma_commit(&bar_aux[0]);
           }
           // the h2 image is free once the last dW3 has executed: request the next tile's h2
-          mbar_wait(&bar_aux[0], p_a0);
+          mbar_wait_relaxed(&bar_aux[0], p_a0);
           p_a0 ^= 1;
-          if (tile + 1 < tile_hi) {
+          if (!h2db && tile + 1 < tile_hi) {
             load_h2(tile + 1);
             if (tile + 2 < tile_hi) bulk_prefetch_l2(A.stash + (size_t)(tile + 2) * kStashTile, (uint32_t)kStashTile);
           }
-          mbar_wait(&rdy_z2, p_z2);  // (consumed to stay in step; dW2 is deferred)
+          mbar_wait_relaxed(&rdy_z2, p_z2);  // (consumed to stay in step; dW2 is deferred)
           p_z2 ^= 1;
-          mbar_wait(&seq_dh1, p_sdh1);  // dH1 queued
+          mbar_wait_relaxed(&seq_dh1, p_sdh1);  // dH1 queued
           p_sdh1 ^= 1;
-          mbar_wait(&rdy_z1, p_z1);
+          mbar_wait_relaxed(&rdy_z1, p_z1);
           p_z1 ^= 1;
           tc_fence_after();
           const GemmOp gd1 = make_gemm(adO, (uint32_t)L.dO_img, kRows, 1, aH1 + 8 * (kRows * 16), (uint32_t)L.H1_img,
                                        kRows, 1, 64, 8, kRows);
+          NL_TRACE(15);
           issue_gemm(gd1, tmem + TM.D1, !first_in_slot);
           umma_commit(&bar_aux[2]);
+          NL_TRACE(16);
           first_tile = false;
         }
         if (tile_lo < tile_hi) issue_dw2(tile_hi - tile_lo > 1);
@@ -1193,7 +1280,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
     // =============================== epilogue warpgroups ===============================
     const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     auto ep_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kEpi) : "memory"); };
-    uint32_t ph_main = 0, ph_l3 = 0, ph_h1 = 0, ph_h2 = 0;
+    uint32_t ph_main = 0, ph_l3 = 0, ph_h1 = 0, ph_h2a = 0, ph_h2b = 0;
     uint32_t ph_aux0 = 0, ph_aux1 = 0, ph_aux2 = 0;
     bool pend_aux0 = false, pend_aux1 = false, pend_aux2 = false;
     auto wait_dw3 = [&]() {
@@ -1268,6 +1355,9 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
 #pragma unroll
       for (int dd = 0; dd < kGPre; ++dd) graw[dd] = g_n[dd];
       if (tile + 1 < tile_hi) prefetch(t_cur, b_cur);
+      const int hb = h2db ? (int)((tile - tile_lo) & 1) : 0;
+      const unsigned char* H2_hi = H2_base + (size_t)hb * 2 * L.H2_img;
+      const unsigned char* H2_lo = H2_hi + L.H2_img;
 
       // ---- slot context: the reduction coefficients of this time index (time_tables_kernel)
       if (t_idx != cur_t) {
@@ -1278,10 +1368,12 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
         ep_sync();
       }
       NL_PROF(0);
+      if (tid == 0) NL_TRACE(0);
 
       // ---- 1. D1 of the previous tile reads Z1g in the dO image, which the head stage rewrites
       wait_d1();
       NL_PROF(1);
+      if (tid == 0) NL_TRACE(1);
 
       // ---- 2. chunks of layer 3 + heads + dO
       for (int ch = 0; ch < nch; ++ch) {
@@ -1291,8 +1383,8 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
           ph_l3 ^= 1;
           // landed before L3 could run; waiting here (never blocks) makes the bulk-async writes of the h2 image
           // visible to this thread's loads in stage 3 and keeps this thread's parity in step with the loads
-          mbar_wait(&bar_h2, ph_h2);
-          ph_h2 ^= 1;
+          if (hb == 0) { mbar_wait(&bar_h2[0], ph_h2a); ph_h2a ^= 1; }
+          else         { mbar_wait(&bar_h2[1], ph_h2b); ph_h2b ^= 1; }
         } else {
           mbar_wait(&bar_main, ph_main);
           ph_main ^= 1;
@@ -1300,6 +1392,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
         }
         tc_fence_after();
         NL_PROF(4);
+        if (tid == 0) NL_TRACE(2);
         float gr = 0.f;
         if (d < kGPre) {
 #pragma unroll
@@ -1330,6 +1423,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
         if (tid == 0) mbar_arrive(&rdy_dO);
         pend_aux0 = true;
         NL_PROF(6);
+        if (tid == 0) NL_TRACE(3);
       }
 
       // ---- 3. Z2g = dH2 (1 - h2^2) -> its own image (zsep) or the dO image
@@ -1337,6 +1431,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
       ph_main ^= 1;
       tc_fence_after();
       NL_PROF(7);
+      if (tid == 0) NL_TRACE(4);
       float z[kColsPerWg];
 #pragma unroll
       for (int i = 0; i < kColsPerWg; i += 16) {
@@ -1367,12 +1462,14 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
       ep_sync();
       if (tid == 0) mbar_arrive(&rdy_z2);
       NL_PROF(8);
+      if (tid == 0) NL_TRACE(5);
 
       // ---- 4. Z1g = dH1 (1 - h1^2) -> dO image ; dp
       mbar_wait(&bar_main, ph_main);
       ph_main ^= 1;
       tc_fence_after();
       NL_PROF(9);
+      if (tid == 0) NL_TRACE(6);
       mbar_wait(&bar_h1, ph_h1);
       ph_h1 ^= 1;
       float dpv[KP];
@@ -1397,11 +1494,12 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
           }
         }
       }
-      if (valid) {
+      // dp of this tile: the warpgroups' partial sums meet in shared memory (ordered by the barrier below) and
+      // warpgroup 0 writes their sum to the per-tile scratch -- plain stores, summed over t by dp_reduce_kernel.
+      // (atomicAdd on dp[b] from every warpgroup of every CTA cost 13 % of this kernel.)
 #pragma unroll
-        for (int q = 0; q < KP; ++q)
-          if (q < K) atomicAdd(A.dp + (size_t)b * K + q, dpv[q]);
-      }
+      for (int q = 0; q < KP; ++q)
+        if (q < K) sdp[(wg * kRows + r) * K + q] = dpv[q];
       wait_dw3();  // dW3 of the last chunk reads the dO image
 #pragma unroll
       for (int i = 0; i < kColsPerWg; i += 8) store_chunk8(dO_hi, dO_lo, kRows, r, wg * kColsPerWg + i, &z[i]);
@@ -1409,9 +1507,19 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
       tc_fence_before();
       ep_sync();
       if (tid == 0) mbar_arrive(&rdy_z1);
+      if (wg == 0) {
+        float* dst = A.dp_part + ((size_t)tile * kRows + r) * K;
+        for (int q = 0; q < K; ++q) {
+          float sum = 0.f;
+#pragma unroll
+          for (int w = 0; w < kEWG; ++w) sum += sdp[(w * kRows + r) * K + q];
+          dst[q] = valid ? sum : 0.f;
+        }
+      }
       pend_aux2 = true;  // D1 of this tile
       pend_aux1 = true;  // dW2 of this tile (issued behind the next tile's L3, or after the loop)
       NL_PROF(10);
+      if (tid == 0) NL_TRACE(7);
     }
 #ifdef NL_TC_PROFILE
     if (tid == 0 && A.prof)
@@ -1507,18 +1615,22 @@ static TcGeom tc_geom(const nl_desc* d, bool bwd, bool stash = false) {
 // geometry of the "saved" backward (activation stash): everything resident
 struct BsGeom {
   bool ok, zsep;
+  int h2bufs;
   size_t smem;
 };
 static BsGeom bs_geom(const nl_desc* d, const TcGeom& g) {
   BsGeom b{};
   const int room = (512 - (64 + g.NP + 80 + 16)) / 80;
   if (g.nch > room) return b;
-  const size_t limit = 227 * 1024 - 1024;
-  for (int zs = 1; zs >= 1; --zs) {  // Z2g must own its image: dW2 is deferred past the Z1g store
-    const tc::BsSmem L = tc::bs_smem(g.NP, g.nch, g.nkc, d->n, zs != 0);
+  const size_t limit = 227 * 1024 - 256;  // static shared memory of the kernel: 16 mbarriers + the TMEM slot (<= 256 B)
+  // Z2g must own its image (dW2 is deferred past the Z1g store); the h2 image is double-buffered when it fits
+  // (double-buffering the h2 image -- hb = 2 -- fits at terms = 33 but measured no gain: the chain is not waiting for it)
+  for (int hb = 1; hb >= 1; --hb) {
+    const tc::BsSmem L = tc::bs_smem(g.NP, g.nch, g.nkc, d->n, d->K, true, hb);
     if (L.total <= limit) {
       b.ok = true;
-      b.zsep = zs != 0;
+      b.zsep = true;
+      b.h2bufs = hb;
       b.smem = L.total;
       return b;
     }
@@ -1556,7 +1668,10 @@ TcPlan tc_plan(const nl_desc* d, int pass) {
                       tc_align((size_t)g.nch * g.NP * 4, 256);
   // per-time-point tables (S1, coefficients, features) + G1 accumulator of the saved backward
   const size_t tabs = tc_align((size_t)d->T * tc::kH * 4, 256) + tc_align((size_t)d->T * g.nkc * g.NP * 4, 256) +
-                      tc_align((size_t)d->T * 2 * d->n * 4, 256) + (bwd ? tc_align((size_t)d->T * tc::kH * 8 * 4, 256) : 0);
+                      tc_align((size_t)d->T * 2 * d->n * 4, 256) +
+                      (bwd ? tc_align((size_t)d->T * tc::kH * 8 * 4, 256) +
+                                 tc_align((size_t)ntiles * tc::kRows * d->K * 4, 256)
+                           : 0);
   pl.ws_bytes = pack + tabs + (bwd ? tc_align(slab_len * 4 * pl.grid, 256) : 0) + 512;
   pl.ok = 1;
   return pl;
@@ -1580,11 +1695,11 @@ static cudaError_t launch_tc1(const tc::TcArgs& A, int grid, size_t smem, cudaSt
 }
 
 template <int KP>
-static cudaError_t launch_bs(const tc::TcArgs& A, int grid, size_t smem, bool zsep, cudaStream_t st) {
+static cudaError_t launch_bs(const tc::TcArgs& A, int grid, size_t smem, bool zsep, int h2bufs, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(tc::fused_tc_bwd_saved_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem);
   if (e != cudaSuccess) return e;
-  tc::fused_tc_bwd_saved_kernel<KP><<<grid, tc::kBsThreads, smem, st>>>(A, zsep ? 1 : 0);
+  tc::fused_tc_bwd_saved_kernel<KP><<<grid, tc::kBsThreads, smem, st>>>(A, zsep ? 1 : 0, h2bufs);
   return cudaGetLastError();
 }
 
@@ -1623,8 +1738,8 @@ cudaError_t launch_fused_tc(const nl_desc* d, bool bwd, const void* p, const voi
   A.stash = (unsigned char*)saved;
 #ifdef NL_TC_PROFILE
   if (!g_prof_buf) {
-    cudaMalloc(&g_prof_buf, 2 * 12 * sizeof(long long));
-    cudaMemset(g_prof_buf, 0, 2 * 12 * sizeof(long long));
+    cudaMalloc(&g_prof_buf, (2 * 12 + 64) * sizeof(long long));
+    cudaMemset(g_prof_buf, 0, (2 * 12 + 64) * sizeof(long long));
   }
   A.prof = g_prof_buf + (bwd ? 12 : 0);
 #endif
@@ -1642,9 +1757,12 @@ cudaError_t launch_fused_tc(const nl_desc* d, bool bwd, const void* p, const voi
   float* tabU = (float*)w;
   w += tc_align((size_t)d->T * 2 * d->n * 4, 256);
   float* g1buf = nullptr;
+  float* dp_part = nullptr;
   if (bwd) {
     g1buf = (float*)w;
     w += tc_align((size_t)d->T * tc::kH * 8 * 4, 256);
+    dp_part = (float*)w;
+    w += tc_align((size_t)A.ntiles * tc::kRows * d->K * 4, 256);
   }
   const bool use_tables = !bwd || bg.ok;  // the recomputing backward keeps its in-kernel slot context
   if (use_tables && d->T > 0) {
@@ -1676,11 +1794,13 @@ cudaError_t launch_fused_tc(const nl_desc* d, bool bwd, const void* p, const voi
     if (e != cudaSuccess) return e;
     if (bg.ok) {
       A.g1buf = g1buf;
+      A.dp_part = dp_part;
       e = cudaMemsetAsync(g1buf, 0, (size_t)d->T * tc::kH * 8 * 4, st);
       if (e != cudaSuccess) return e;
     }
     if (bg.ok)
-      e = d->K <= 2 ? launch_bs<2>(A, pl.grid, bg.smem, bg.zsep, st) : launch_bs<tc::kMaxK>(A, pl.grid, bg.smem, bg.zsep, st);
+      e = d->K <= 2 ? launch_bs<2>(A, pl.grid, bg.smem, bg.zsep, bg.h2bufs, st)
+                    : launch_bs<tc::kMaxK>(A, pl.grid, bg.smem, bg.zsep, bg.h2bufs, st);
     else
       e = d->K <= 2 ? launch_tc1<true, 2>(A, pl.grid, pl.smem, st) : launch_tc1<true, tc::kMaxK>(A, pl.grid, pl.smem, st);
   } else {
@@ -1698,6 +1818,10 @@ cudaError_t launch_fused_tc(const nl_desc* d, bool bwd, const void* p, const voi
       e = cudaGetLastError();
       if (e != cudaSuccess) return e;
       if (launches) *launches += 1;
+      tc::dp_reduce_kernel<<<dim3((unsigned)A.nbt, tc::kDpSlices), 256, 0, st>>>(dp_part, d->B, d->T, d->K, A.nbt, A.dp);
+      e = cudaGetLastError();
+      if (e != cudaSuccess) return e;
+      if (launches) *launches += 1;
     }
   }
   return cudaSuccess;
@@ -1707,6 +1831,13 @@ cudaError_t launch_fused_tc(const nl_desc* d, bool bwd, const void* p, const voi
 
 #ifdef NL_TC_PROFILE
 // profiling build only (scripts/gpu_phase_profile.sh): per-phase clock totals of thread 0, summed over CTAs
+// event trace of one tile of CTA 0 (saved backward): 64 raw clock64 stamps
+extern "C" int nl_debug_tc_trace(long long* out64) {
+  if (!nl::g_prof_buf) return -1;
+  cudaDeviceSynchronize();
+  cudaMemcpy(out64, nl::g_prof_buf + 24, 64 * sizeof(long long), cudaMemcpyDeviceToHost);
+  return 0;
+}
 extern "C" int nl_debug_tc_profile(long long* out24, int reset) {
   if (!nl::g_prof_buf) return -1;
   cudaDeviceSynchronize();

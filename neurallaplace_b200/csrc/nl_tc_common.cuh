@@ -66,6 +66,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   __trap();
 }
 
+// Same, for the dedicated issuer warps: they wait most of the time, and a hot polling loop would take issue
+// slots from the epilogue warps of the same scheduler; back off between polls.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t spin = 0; spin < (1u << 16); ++spin) {
+    // suspend-time hint (ns): the thread sleeps in hardware until the phase completes or the hint expires
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity), "r"(100000u)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+
 // ---- proxy / tcgen05 fences ----------------------------------------------------------------
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

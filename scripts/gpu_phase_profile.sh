@@ -5,7 +5,7 @@ set -euo pipefail
 cd "$(dirname "$0")/.."
 SRC=neurallaplace_b200/csrc
 mkdir -p /tmp/nlprof
-FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --extended-lambda -DNL_TC_PROFILE"
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --extended-lambda -DNL_TC_PROFILE ${NL_EXTRA:-}"
 for f in nl_api nl_elementwise nl_fused_simt nl_fused_tc nl_fused_tc2 nl_tc_selftest; do
   nvcc $FLAGS -c $SRC/$f.cu -o /tmp/nlprof/$f.o 2>/dev/null &
 done; wait
@@ -35,4 +35,20 @@ for k, nm in ((0, "forward"), (12, "backward")):
     print(nm, "total clocks (sum over CTAs) %.3e  per CTA %.0f" % (tot, tot/296 if k == 0 else tot/148))
     for i in range(12):
         if v[i]: print("   %-28s %5.1f%%" % (names[i], 100.0*v[i]/tot))
+tr = (ctypes.c_longlong * 64)()
+if hasattr(lib, "nl_debug_tc_trace") and lib.nl_debug_tc_trace(tr) == 0:
+    tnames = {0: "E tile start (after slot)", 1: "E after wait_d1", 2: "E after L3+h2 wait", 3: "E dO stored+arrive", 4: "E dH2 done",
+             5: "E Z2g stored+arrive", 6: "E dH1 done", 7: "E Z1g stored+arrive", 10: "I16 L3 issue", 11: "I16 L3 issued",
+             12: "I16 dH2 issue", 13: "I16 dH1 issue", 14: "I17 dW3 issue", 15: "I17 D1 issue", 16: "I17 D1 issued",
+             17: "I17 dW2(prev) issue", 18: "I17 dW2(prev) issued"}
+    ev = []
+    for k in range(3):
+        for sl, nm in tnames.items():
+            v = tr[sl + 20 * k]
+            if v: ev.append((v, "tile+%d %s" % (4 + k, nm)))
+    ev.sort()
+    if ev:
+        t0 = ev[0][0]
+        print("event trace of CTA 0 (saved backward), clocks relative to the first event")
+        for v, nm in ev: print("   %8d  %s" % (v - t0, nm))
 PY
