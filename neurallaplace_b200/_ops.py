@@ -117,6 +117,15 @@ def fused_supported(consts, dtype, B, T, K, H, D, t_mode, head, impl=0):
   return lib.nl_selected_impl(ctypes.byref(d), 0) != 0 and lib.nl_selected_impl(ctypes.byref(d), 1) != 0
 
 
+def saved_bytes(consts, dtype, B, T, K, H, D, t_mode, head, impl=0):
+  """Bytes of hidden activations the training forward keeps for backward (0: backward recomputes them)."""
+  if os.environ.get("NL_B200_STASH", "1") == "0":
+    return 0
+  lib = _lib.load()
+  d = _desc(consts, dtype, B, T, K, H, D, t_mode, head, impl)
+  return int(lib.nl_saved_bytes(ctypes.byref(d)))
+
+
 def selected_impl(consts, dtype, B, T, K, H, D, t_mode, head, which=0, impl=0):
   lib = _lib.load()
   d = _desc(consts, dtype, B, T, K, H, D, t_mode, head, impl)

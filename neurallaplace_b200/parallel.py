@@ -83,3 +83,61 @@ def allreduce_gradients(module_or_params, group=None, average=False):
   params = list(module_or_params.parameters()) if isinstance(module_or_params, torch.nn.Module) else list(
       module_or_params)
   GradientAllReducer(params, group, average)()
+
+
+class HostStagedStep:
+  """One training step of the reconstruction path with HOST (pinned) operands and results.
+
+  ``laplace_reconstruct`` itself takes device tensors (like the reference).  A caller whose minibatch lives in
+  host memory pays three PCIe transfers per step: p / t / upstream gradient in, x and the MLP gradients out.
+  This helper keeps them off the kernels' critical path with two copy streams:
+
+    main   : H2D p, t (small) -> fused forward ------------------> fused backward -> all-reduce -> D2H grads
+    upload :      H2D upstream gradient  (concurrent with forward) ----^
+    download:                            D2H x (concurrent with backward)
+
+  Buffers that cross streams are registered with the caching allocator (``record_stream``).
+  """
+
+  def __init__(self, laplace_rep_func, recon_dim, ilt_algorithm="fourier", ilt_reconstruction_terms=33,
+               use_sphere_projection=True, reducer=None, device=None):
+    from .core import laplace_reconstruct  # local import: parallel.py is importable without the CUDA library
+    self._reconstruct = laplace_reconstruct
+    self.f = laplace_rep_func
+    self.kw = dict(recon_dim=recon_dim, ilt_algorithm=ilt_algorithm,
+                   ilt_reconstruction_terms=ilt_reconstruction_terms, use_sphere_projection=use_sphere_projection)
+    self.params = [q for q in laplace_rep_func.parameters() if q.requires_grad]
+    self.reducer = reducer
+    self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    self.upload = torch.cuda.Stream(self.device)
+    self.download = torch.cuda.Stream(self.device)
+
+  def __call__(self, p_host, t_host, grad_x_host, x_host_out, grads_host_out=None):
+    """Runs forward + backward of sum(grad_x * x); writes x into ``x_host_out`` and the flattened MLP gradients
+    into ``grads_host_out`` (both pinned).  Returns the device ``p`` (its ``.grad`` holds dL/dp).
+    The copies are asynchronous: synchronise (``torch.cuda.synchronize``) before reading the host buffers."""
+    dev = self.device
+    main = torch.cuda.current_stream(dev)
+    with torch.cuda.stream(self.upload):
+      g_d = grad_x_host.to(dev, non_blocking=True)
+    p_d = p_host.to(dev, non_blocking=True).requires_grad_(True)
+    t_d = t_host.to(dev, non_blocking=True)
+    for q in self.params:
+      q.grad = None
+    x = self._reconstruct(self.f, p_d, t_d, **self.kw)
+    self.download.wait_stream(main)
+    with torch.cuda.stream(self.download):
+      x_host_out.copy_(x.detach(), non_blocking=True)
+    x.record_stream(self.download)
+    main.wait_stream(self.upload)
+    g_d.record_stream(main)
+    x.backward(g_d)
+    if self.reducer is not None:
+      self.reducer()
+    if grads_host_out is not None:
+      off = 0
+      for q in self.params:
+        k = q.numel()
+        grads_host_out[off:off + k].copy_(q.grad.reshape(-1), non_blocking=True)
+        off += k
+    return p_d
