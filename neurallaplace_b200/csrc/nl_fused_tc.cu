@@ -1612,6 +1612,13 @@ static TcGeom tc_geom(const nl_desc* d, bool bwd, bool stash = false) {
   return g;
 }
 
+// W3 operand images + b3 pack + per-time-point tables (S1, coefficients, features), each 256-byte aligned
+static size_t tc_aux_bytes(const nl_desc* d, const TcGeom& g) {
+  return tc_align((size_t)g.nch * 2 * tc::image_bytes(g.NP, tc::kH), 256) + tc_align((size_t)g.nch * g.NP * 4, 256) +
+         tc_align((size_t)d->T * tc::kH * 4, 256) + tc_align((size_t)d->T * g.nkc * g.NP * 4, 256) +
+         tc_align((size_t)d->T * 2 * d->n * 4, 256);
+}
+
 // geometry of the "saved" backward (activation stash): everything resident
 struct BsGeom {
   bool ok, zsep;
@@ -1642,7 +1649,8 @@ size_t tc_saved_bytes(const nl_desc* d) {
   if (!tc_plan(d, 0).ok || !tc_plan(d, 1).ok) return 0;
   if (!tc_geom(d, false, true).ok || !bs_geom(d, tc_geom(d, true)).ok) return 0;
   const long long nbt = (d->B + tc::kRows - 1) / tc::kRows;
-  return (size_t)(nbt * d->T) * tc::kStashTile;
+  // [activation stash | W3 operand images | b3 pack | time tables]: the backward reuses what the forward built
+  return (size_t)(nbt * d->T) * tc::kStashTile + tc_aux_bytes(d, tc_geom(d, false, true)) + 256;
 }
 
 TcPlan tc_plan(const nl_desc* d, int pass) {
@@ -1743,19 +1751,23 @@ cudaError_t launch_fused_tc(const nl_desc* d, bool bwd, const void* p, const voi
   }
   A.prof = g_prof_buf + (bwd ? 12 : 0);
 #endif
-  // workspace: [W3 operand images | b3 pack | slabs]
+  // workspace: [W3 operand images | b3 pack | time tables | G1 | dp partials | slabs]; with an activation stash the
+  // first three live behind the stash instead: the forward builds them, the saved backward reuses them
   unsigned char* w = (unsigned char*)tc_align((size_t)ws, 256);
-  unsigned char* w3pack = w;
-  w += tc_align((size_t)g.nch * 2 * tc::image_bytes(g.NP, tc::kH), 256);
-  float* b3pack = (float*)w;
-  w += tc_align((size_t)g.nch * g.NP * 4, 256);
+  unsigned char* aux = saved ? (unsigned char*)tc_align((size_t)saved + (size_t)A.ntiles * tc::kStashTile, 256) : w;
+  unsigned char* w3pack = aux;
+  aux += tc_align((size_t)g.nch * 2 * tc::image_bytes(g.NP, tc::kH), 256);
+  float* b3pack = (float*)aux;
+  aux += tc_align((size_t)g.nch * g.NP * 4, 256);
   A.w3pack = w3pack; A.b3pack = b3pack;
-  float* tabS1 = (float*)w;
-  w += tc_align((size_t)d->T * tc::kH * 4, 256);
-  float* tabCoef = (float*)w;
-  w += tc_align((size_t)d->T * g.nkc * g.NP * 4, 256);
-  float* tabU = (float*)w;
-  w += tc_align((size_t)d->T * 2 * d->n * 4, 256);
+  float* tabS1 = (float*)aux;
+  aux += tc_align((size_t)d->T * tc::kH * 4, 256);
+  float* tabCoef = (float*)aux;
+  aux += tc_align((size_t)d->T * g.nkc * g.NP * 4, 256);
+  float* tabU = (float*)aux;
+  aux += tc_align((size_t)d->T * 2 * d->n * 4, 256);
+  if (!saved) w = aux;
+  const bool reuse_aux = bwd && bg.ok;  // built by nl_reconstruct_forward_save into the same buffer
   float* g1buf = nullptr;
   float* dp_part = nullptr;
   if (bwd) {
@@ -1765,15 +1777,17 @@ cudaError_t launch_fused_tc(const nl_desc* d, bool bwd, const void* p, const voi
     w += tc_align((size_t)A.ntiles * tc::kRows * d->K * 4, 256);
   }
   const bool use_tables = !bwd || bg.ok;  // the recomputing backward keeps its in-kernel slot context
-  if (use_tables && d->T > 0) {
+  if (use_tables) {
+    A.tabS1 = tabS1; A.tabCoef = tabCoef; A.tabU = tabU;
+  }
+  if (use_tables && !reuse_aux && d->T > 0) {
     tc::time_tables_kernel<<<d->T, 128, (size_t)2 * d->n * sizeof(float), st>>>(
         A.P, A.t, A.W1, A.b1, d->K, g.nkc, g.kc, g.NP, tabS1, tabCoef, tabU);
     cudaError_t e0 = cudaGetLastError();
     if (e0 != cudaSuccess) return e0;
     if (launches) *launches += 1;
-    A.tabS1 = tabS1; A.tabCoef = tabCoef; A.tabU = tabU;
   }
-  {
+  if (!reuse_aux) {
     const int total = g.nch * g.NP, threads = 128;
     tc::pack_w3_kernel<<<(total + threads - 1) / threads, threads, 0, st>>>(
         (const float*)weights[4], (const float*)weights[5], d->D, d->n, g.nkc, g.kc, g.NP, g.nch, w3pack, b3pack);
