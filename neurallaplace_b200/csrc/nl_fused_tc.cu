@@ -951,13 +951,15 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
 // GEMM no longer blocks the Z2g store.  Requires every W3 chunk resident in shared memory and every
 // dW3 accumulator resident in TMEM (d_obs x terms beyond that uses the recomputing kernel).
 struct BsSmem {
-  size_t dO, Z, H1, H2, W2, W3, small, total;
-  size_t dO_img, Z_img, H1_img, H2_img, W2_img, W3_img;
+  size_t dO, Z, Z1, H1, H2, W2, W3, small, total;
+  size_t dO_img, Z_img, Z1_img, H1_img, H2_img, W2_img, W3_img;
+  bool z1sep;  // Z1g owns an image: D1 of tile i then no longer blocks the head stage of tile i+1 (which rewrites dO)
   int W1p, b3, coef, dp, nfloats;
   bool zsep;
   int h2bufs;  // 2: the h2 image is double-buffered (the next tile's h2 streams in a whole tile ahead)
 };
-__host__ __device__ inline BsSmem bs_smem(int NP, int nch, int nkc, int n, int K, bool zsep, int h2bufs = 1) {
+__host__ __device__ inline BsSmem bs_smem(int NP, int nch, int nkc, int n, int K, bool zsep, int h2bufs = 1,
+                                           bool z1sep = false) {
   BsSmem L;
   L.zsep = zsep;
   L.h2bufs = h2bufs;
@@ -970,6 +972,9 @@ __host__ __device__ inline BsSmem bs_smem(int NP, int nch, int nkc, int n, int K
   size_t o = 0;
   L.dO = o; o += 2 * L.dO_img;
   L.Z = zsep ? o : L.dO; o += 2 * L.Z_img;
+  L.z1sep = z1sep;
+  L.Z1_img = z1sep ? image_bytes(kRows, kH) : 0;
+  L.Z1 = z1sep ? o : L.dO; o += 2 * L.Z1_img;
   L.H1 = o; o += 2 * L.H1_img;
   L.H2 = o; o += 2 * L.H2_img * h2bufs;
   L.W2 = o; o += 2 * L.W2_img;
@@ -1020,7 +1025,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 // weight-gradient GEMM), so no epilogue warp ever issues one.  640 threads cap the kernel at 96 registers per
 // thread; the epilogue (16 columns per thread, h1 / h2 re-read from shared memory) needs 86.
 template <int KP>
-__global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArgs A, int zsep_i, int h2bufs) {
+__global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArgs A, int zsep_i, int h2bufs, int z1sep_i) {
   constexpr int kEWG = kEwgBwd;
   constexpr int kEpi = 128 * kEWG;
   constexpr int kColsPerWg = kH / kEWG;
@@ -1042,13 +1047,16 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
   const IltParams<float> P = A.P;
   const int n = A.n, K = A.K, D = A.D, NP = A.NP, nch = A.nch;
   const bool zsep = zsep_i != 0;
-  const BsSmem L = bs_smem(NP, nch, A.nkc, n, K, zsep, h2bufs);
+  const bool z1sep = z1sep_i != 0;
+  const BsSmem L = bs_smem(NP, nch, A.nkc, n, K, zsep, h2bufs, z1sep);
   const bool h2db = h2bufs == 2;
   const TcTmem TM = tc_tmem(true, NP, nch);
   unsigned char* dO_hi = smem + L.dO;
   unsigned char* dO_lo = dO_hi + L.dO_img;
   unsigned char* Z_hi = smem + L.Z;
   unsigned char* Z_lo = Z_hi + (zsep ? L.Z_img : L.dO_img);
+  unsigned char* Z1_hi = smem + L.Z1;
+  unsigned char* Z1_lo = Z1_hi + (z1sep ? L.Z1_img : L.dO_img);
   unsigned char* H1_hi = smem + L.H1;
   unsigned char* H1_lo = H1_hi + L.H1_img;
   unsigned char* H2_base = smem + L.H2;  // buffer q: hi image at q * 2 * H2_img, lo image right behind it
@@ -1116,6 +1124,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
   const uint32_t h2_stride = (uint32_t)(2 * L.H2_img);  // bytes between the two h2 buffers
   // tile i of this CTA uses h2 buffer (i - tile_lo) & 1 (double-buffered) or 0
   const uint32_t z_lo_off = (uint32_t)(zsep ? L.Z_img : L.dO_img);
+  const uint32_t aZ1 = smem_u32(Z1_hi), z1_lo_off = (uint32_t)(z1sep ? L.Z1_img : L.dO_img);
 
   if (warp >= kEpi / 32) {
     // =============================== issuer warpgroup ===============================
@@ -1265,7 +1274,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
           mbar_wait_relaxed(&rdy_z1, p_z1);
           p_z1 ^= 1;
           tc_fence_after();
-          const GemmOp gd1 = make_gemm(adO, (uint32_t)L.dO_img, kRows, 1, aH1 + 8 * (kRows * 16), (uint32_t)L.H1_img,
+          const GemmOp gd1 = make_gemm(aZ1, z1_lo_off, kRows, 1, aH1 + 8 * (kRows * 16), (uint32_t)L.H1_img,
                                        kRows, 1, 64, 8, kRows);
           NL_TRACE(15);
           issue_gemm(gd1, tmem + TM.D1, !first_in_slot);
@@ -1370,8 +1379,8 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
       NL_PROF(0);
       if (tid == 0) NL_TRACE(0);
 
-      // ---- 1. D1 of the previous tile reads Z1g in the dO image, which the head stage rewrites
-      wait_d1();
+      // ---- 1. D1 of the previous tile reads Z1g: in the dO image (rewritten by the head stage) unless Z1g owns one
+      if (!z1sep) wait_d1();
       NL_PROF(1);
       if (tid == 0) NL_TRACE(1);
 
@@ -1448,6 +1457,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
       }
       if (!zsep) wait_dw3();  // dW3 of the last chunk reads the dO image
       wait_dw2();             // dW2 of the PREVIOUS tile (deferred behind this tile's L3) reads the Z2g and h1 images
+      wait_d1();              // D1 of the previous tile reads the [1 p] chunk (and the Z1g image, rewritten in stage 4)
       if (wg == 0) {          // this tile's [1 p] chunk of the h1 image (B operand of dW2 and D1)
         float q[8];
         q[0] = valid ? 1.f : 0.f;
@@ -1502,7 +1512,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
         if (q < K) sdp[(wg * kRows + r) * K + q] = dpv[q];
       wait_dw3();  // dW3 of the last chunk reads the dO image
 #pragma unroll
-      for (int i = 0; i < kColsPerWg; i += 8) store_chunk8(dO_hi, dO_lo, kRows, r, wg * kColsPerWg + i, &z[i]);
+      for (int i = 0; i < kColsPerWg; i += 8) store_chunk8(Z1_hi, Z1_lo, kRows, r, wg * kColsPerWg + i, &z[i]);
       fence_async_smem();
       tc_fence_before();
       ep_sync();
@@ -1621,7 +1631,7 @@ static size_t tc_aux_bytes(const nl_desc* d, const TcGeom& g) {
 
 // geometry of the "saved" backward (activation stash): everything resident
 struct BsGeom {
-  bool ok, zsep;
+  bool ok, zsep, z1sep;
   int h2bufs;
   size_t smem;
 };
@@ -1632,12 +1642,13 @@ static BsGeom bs_geom(const nl_desc* d, const TcGeom& g) {
   const size_t limit = 227 * 1024 - 256;  // static shared memory of the kernel: 16 mbarriers + the TMEM slot (<= 256 B)
   // Z2g must own its image (dW2 is deferred past the Z1g store); the h2 image is double-buffered when it fits
   // (double-buffering the h2 image -- hb = 2 -- fits at terms = 33 but measured no gain: the chain is not waiting for it)
-  for (int hb = 1; hb >= 1; --hb) {
-    const tc::BsSmem L = tc::bs_smem(g.NP, g.nch, g.nkc, d->n, d->K, true, hb);
+  for (int z1 = 1; z1 >= 0; --z1) {  // Z1g in its own image when that fits
+    const tc::BsSmem L = tc::bs_smem(g.NP, g.nch, g.nkc, d->n, d->K, true, 1, z1 != 0);
     if (L.total <= limit) {
       b.ok = true;
       b.zsep = true;
-      b.h2bufs = hb;
+      b.z1sep = z1 != 0;
+      b.h2bufs = 1;
       b.smem = L.total;
       return b;
     }
@@ -1703,11 +1714,12 @@ static cudaError_t launch_tc1(const tc::TcArgs& A, int grid, size_t smem, cudaSt
 }
 
 template <int KP>
-static cudaError_t launch_bs(const tc::TcArgs& A, int grid, size_t smem, bool zsep, int h2bufs, cudaStream_t st) {
+static cudaError_t launch_bs(const tc::TcArgs& A, int grid, size_t smem, bool zsep, int h2bufs, bool z1sep,
+                             cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(tc::fused_tc_bwd_saved_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem);
   if (e != cudaSuccess) return e;
-  tc::fused_tc_bwd_saved_kernel<KP><<<grid, tc::kBsThreads, smem, st>>>(A, zsep ? 1 : 0, h2bufs);
+  tc::fused_tc_bwd_saved_kernel<KP><<<grid, tc::kBsThreads, smem, st>>>(A, zsep ? 1 : 0, h2bufs, z1sep ? 1 : 0);
   return cudaGetLastError();
 }
 
@@ -1813,8 +1825,8 @@ cudaError_t launch_fused_tc(const nl_desc* d, bool bwd, const void* p, const voi
       if (e != cudaSuccess) return e;
     }
     if (bg.ok)
-      e = d->K <= 2 ? launch_bs<2>(A, pl.grid, bg.smem, bg.zsep, bg.h2bufs, st)
-                    : launch_bs<tc::kMaxK>(A, pl.grid, bg.smem, bg.zsep, bg.h2bufs, st);
+      e = d->K <= 2 ? launch_bs<2>(A, pl.grid, bg.smem, bg.zsep, bg.h2bufs, bg.z1sep, st)
+                    : launch_bs<tc::kMaxK>(A, pl.grid, bg.smem, bg.zsep, bg.h2bufs, bg.z1sep, st);
     else
       e = d->K <= 2 ? launch_tc1<true, 2>(A, pl.grid, pl.smem, st) : launch_tc1<true, tc::kMaxK>(A, pl.grid, pl.smem, st);
   } else {
