@@ -100,6 +100,7 @@ struct TcArgs {
   const float* tabU;     // [T][2n]        (theta_s | phi_s) or (Re s | Im s)
   float* g1buf;          // [T][64][8]     saved backward: sum over the batch of Z1g (x) [1 p]
   float* dp_part;        // [ntiles][128][K] saved backward: per-tile dp contributions (summed over t afterwards)
+  int h2sep;             // forward + stash: h2 has its own image (else it aliases h1 and two more barriers order the bulk stores)
   unsigned char* stash;  // optional [ntiles][h1_hi | h1_lo | h2_hi | h2_lo] operand images (16 KB each), see kStashTile
   long long* prof;  // optional: per-phase clock totals of thread 0 (NL_TC_PROFILE builds)
 };
@@ -110,11 +111,11 @@ struct TcSmem {
   int S1b, W1p, b2, b3, coef, u, G1, xacc, misc, nfloats;  // float offsets inside `small`
 };
 
-__host__ __device__ inline TcSmem tc_smem(bool bwd, int NP, int nch, int nkc, int w3_slots, int n, bool stash = false) {
+__host__ __device__ inline TcSmem tc_smem(bool bwd, int NP, int nch, int nkc, int w3_slots, int n, bool h2sep = false) {
   TcSmem L;
   L.dO_img = bwd ? image_bytes(kRows, NP > kH ? NP : kH) : 0;  // also hosts Z2g / Z1g (64 columns)
   L.H1_img = image_bytes(kRows, bwd ? kH1Cols : kH);
-  L.H2_img = bwd ? image_bytes(kRows, kH2Cols) : (stash ? image_bytes(kRows, kH) : 0);  // forward: h2 aliases h1 unless stashing
+  L.H2_img = bwd ? image_bytes(kRows, kH2Cols) : (h2sep ? image_bytes(kRows, kH) : 0);  // forward: h2 aliases h1 unless h2sep
   L.W2_img = image_bytes(kH, kH);
   L.W3_img = image_bytes(NP, kH);
   size_t o = 0;
@@ -322,7 +323,9 @@ __global__ void __launch_bounds__(256) dp_reduce_kernel(const float* __restrict_
 
 // GENERAL = false: every W3 chunk is shared-memory resident and every dW3 accumulator TMEM resident (the
 // streaming / scratch-flush code is compiled out of the hot loop); GENERAL = true: any d_obs x terms.
-template <bool BWD, int KP, bool GENERAL>
+// ALIAS = true (forward + stash only): h2 shares the h1 image and two extra barriers per tile order the bulk
+// stores of the stash against the rewrites (used when a separate h2 image would cost the 2-CTA co-residency).
+template <bool BWD, int KP, bool GENERAL, bool ALIAS = false>
 __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 : 2) fused_tc_kernel(TcArgs A) {
   constexpr int kEWG = BWD ? kEwgBwd : kEwgFwd;
   constexpr int kThreadsTc = 128 * kEWG;
@@ -340,14 +343,15 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
   const int n_resident = GENERAL ? A.resident : nch;
   const int acc_slots = BWD ? (n_resident < nch ? n_resident + 1 : n_resident) : 0;
   const bool stash = !BWD && A.stash != nullptr;
-  const TcSmem L = tc_smem(BWD, NP, nch, A.nkc, A.w3_slots, n, stash);
+  const bool h2sep = stash && !ALIAS;  // (A.h2sep selects the instantiation on the host)
+  const TcSmem L = tc_smem(BWD, NP, nch, A.nkc, A.w3_slots, n, h2sep);
   const TcTmem TM = tc_tmem(BWD, NP, acc_slots);
   unsigned char* dO_hi = smem + L.dO;
   unsigned char* dO_lo = dO_hi + L.dO_img;
   unsigned char* H1_hi = smem + L.H1;
   unsigned char* H1_lo = H1_hi + L.H1_img;
-  unsigned char* H2_hi = (BWD || stash) ? smem + L.H2 : H1_hi;
-  unsigned char* H2_lo = (BWD || stash) ? H2_hi + L.H2_img : H1_lo;
+  unsigned char* H2_hi = (BWD || h2sep) ? smem + L.H2 : H1_hi;
+  unsigned char* H2_lo = (BWD || h2sep) ? H2_hi + L.H2_img : H1_lo;
   unsigned char* W2_hi = smem + L.W2;
   unsigned char* W2_lo = W2_hi + L.W2_img;
   unsigned char* W3_base = smem + L.W3;
@@ -638,6 +642,10 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
       h1[i] = fast::tanh_fast(z);
     }
     if (BWD) wait_d1();  // the previous tile's D1 GEMM reads the [1 p] chunk of the h1 image (and Z1g in the dO image)
+    if (ALIAS) {  // aliased images: the bulk store of the previous tile's h2 must have read them
+      if (warp == 0 && elect_one()) bulk_wait_read_all();
+      __syncthreads();
+    }
 #pragma unroll
     for (int i = 0; i < kColsPerWg; i += 8) store_chunk8(H1_hi, H1_lo, kRows, r, wg * kColsPerWg + i, &h1[i]);
     if (BWD && wg == 0) {
@@ -681,6 +689,10 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
 #pragma unroll
       for (int j = 0; j < 16; ++j) h2[i + j] = fast::tanh_fast(v[j] + sb2[wg * kColsPerWg + i + j]);
     }
+    if (ALIAS) {  // aliased images: the bulk store of h1 must have read them
+      if (warp == 0 && elect_one()) bulk_wait_read_all();
+      __syncthreads();
+    }
 #pragma unroll
     for (int i = 0; i < kColsPerWg; i += 8) store_chunk8(H2_hi, H2_lo, kRows, r, wg * kColsPerWg + i, &h2[i]);
     fence_async_smem();
@@ -694,7 +706,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
     auto issue_L3 = [&](long long g) {  // thread 0
       w3_wait(g);
       tc_fence_after();
-      const GemmOp gg = make_gemm(aH2, (uint32_t)((BWD || stash) ? L.H2_img : L.H1_img), kRows, 0, w3_slot_addr(g),
+      const GemmOp gg = make_gemm(aH2, (uint32_t)((BWD || h2sep) ? L.H2_img : L.H1_img), kRows, 0, w3_slot_addr(g),
                                   (uint32_t)L.W3_img, NP, 0, 128, NP, kH);
       issue_gemm(gg, tmem + TM.O, false);
     };
@@ -1593,6 +1605,7 @@ static long long* g_prof_buf = nullptr;
 static size_t tc_align(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct TcGeom {
+  int h2sep;
   int nkc, kc, NP, nch, w3_slots, resident;
   size_t smem;
   bool ok;
@@ -1609,14 +1622,25 @@ static TcGeom tc_geom(const nl_desc* d, bool bwd, bool stash = false) {
   g.resident = bwd ? (g.nch <= room ? g.nch : room - 1) : 0;
   // shared memory: all chunks resident if they fit (forward: within half an SM so that 2 CTAs co-reside)
   const size_t limit = 227 * 1024 - 1024, half = limit / 2;
-  const tc::TcSmem Lr = tc::tc_smem(bwd, g.NP, g.nch, g.nkc, g.nch, d->n, stash);
-  const tc::TcSmem Ls = tc::tc_smem(bwd, g.NP, g.nch, g.nkc, tc::kStages, d->n, stash);
-  if (g.nch <= tc::kStages || Lr.total <= (bwd ? limit : half)) {
-    g.w3_slots = g.nch;
-    g.smem = Lr.total;
-  } else {
-    g.w3_slots = tc::kStages;
-    g.smem = Ls.total;
+  auto place = [&](bool h2sep) {
+    const tc::TcSmem Lr = tc::tc_smem(bwd, g.NP, g.nch, g.nkc, g.nch, d->n, h2sep);
+    const tc::TcSmem Ls = tc::tc_smem(bwd, g.NP, g.nch, g.nkc, tc::kStages, d->n, h2sep);
+    if (g.nch <= tc::kStages || Lr.total <= (bwd ? limit : half)) {
+      g.w3_slots = g.nch;
+      g.smem = Lr.total;
+    } else {
+      g.w3_slots = tc::kStages;
+      g.smem = Ls.total;
+    }
+    g.h2sep = h2sep ? 1 : 0;
+  };
+  // forward + stash: h2 gets its own image (its bulk store then overlaps the next tile's h1 without extra barriers)
+  // unless that costs the 2-CTAs-per-SM co-residency the forward kernel relies on
+  place(!bwd && stash);
+  if (!bwd && stash && g.smem > half) {
+    const TcGeom sep = g;
+    place(false);
+    if (g.smem > half) g = sep;
   }
   g.ok = g.smem <= limit;
   return g;
@@ -1699,17 +1723,19 @@ TcPlan tc_plan(const nl_desc* d, int pass) {
 cudaError_t launch_reduce_slabs_f32(const float* slab, long long slab_len, int nslabs, void* const* grads,
                                     const nl_desc* d, cudaStream_t st);
 
-template <bool BWD, int KP, bool GENERAL>
+template <bool BWD, int KP, bool GENERAL, bool ALIAS = false>
 static cudaError_t launch_tc1_g(const tc::TcArgs& A, int grid, size_t smem, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(tc::fused_tc_kernel<BWD, KP, GENERAL>,
+  cudaError_t e = cudaFuncSetAttribute(tc::fused_tc_kernel<BWD, KP, GENERAL, ALIAS>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  tc::fused_tc_kernel<BWD, KP, GENERAL><<<grid, 128 * (BWD ? tc::kEwgBwd : tc::kEwgFwd), smem, st>>>(A);
+  tc::fused_tc_kernel<BWD, KP, GENERAL, ALIAS><<<grid, 128 * (BWD ? tc::kEwgBwd : tc::kEwgFwd), smem, st>>>(A);
   return cudaGetLastError();
 }
 template <bool BWD, int KP>
 static cudaError_t launch_tc1(const tc::TcArgs& A, int grid, size_t smem, cudaStream_t st) {
   const bool general = A.w3_slots < A.nch || (BWD && A.resident < A.nch);
+  if (!BWD && A.stash && !A.h2sep)  // (the stash needs every W3 chunk resident, so this is never the general kernel)
+    return launch_tc1_g<false, KP, false, true>(A, grid, smem, st);
   return general ? launch_tc1_g<BWD, KP, true>(A, grid, smem, st) : launch_tc1_g<BWD, KP, false>(A, grid, smem, st);
 }
 
@@ -1756,6 +1782,7 @@ cudaError_t launch_fused_tc(const nl_desc* d, bool bwd, const void* p, const voi
   A.b2 = (const float*)weights[3];
   A.x = (float*)x; A.gx = (const float*)gx;
   A.stash = (unsigned char*)saved;
+  A.h2sep = g.h2sep;
 #ifdef NL_TC_PROFILE
   if (!g_prof_buf) {
     cudaMalloc(&g_prof_buf, (2 * 12 + 64) * sizeof(long long));
