@@ -28,6 +28,7 @@
 // (deterministic).  A tiny second kernel reduces the slabs over CTAs.  dp uses atomics.
 // The (batch x time x terms x d_obs) complex intermediate only ever exists in registers.
 #include <algorithm>
+#include <cstdlib>
 
 #include "nl_common.cuh"
 #include "nl_fastmath.cuh"
@@ -74,6 +75,12 @@ constexpr int kMaxB3Smem = 4096;  // floats of packed b3 kept in shared memory
 // columns, 128 rows x 64 x 2 B = 16 KB per image) per tile; the "saved" backward kernel streams them back
 // with bulk-async copies instead of recomputing layers 1-2 (512 B per (b,t) point each way through HBM
 // against ~40 % of the backward's CUDA-core work).
+// The tensor core TRUNCATES when it adds into a TMEM accumulator: a weight-gradient accumulator that lives for a
+// CTA's whole tile range (221 tiles x 24 accumulating MMAs at the headline size) picks up a relative bias of
+// ~ #MMAs * 2^-25 = 2.5e-4, measured against the float64 kernels (scripts/dbg_trunc.py) -- above the 1e-4 bar.
+// Every kFlushTiles tiles the accumulators are therefore drained into the CTA's slab with round-to-nearest
+// float adds and restarted (bias <= ~1e-5).
+constexpr int kFlushTiles = 16;
 constexpr uint32_t kStashImg = 128 * 64 * 2;
 constexpr size_t kStashTile = 4 * (size_t)kStashImg;
 
@@ -475,8 +482,8 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
   float* gW3 = gb2 + kH;
   float* gb3 = gW3 + (long long)2 * D * n * kH;
 
-  int cur_t = -1;
-  bool first_tile = true, first_in_slot = true;
+  int cur_t = -1, slot_tiles = 0;
+  bool first_in_slot = true;
 
   // W3 row of accumulator lane r in chunk ch (-1: padding lane)
   auto w3_row_of = [&](int ch) {
@@ -512,6 +519,26 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
         if (add) atomicAdd(gb3 + row, v[0]);
         else     gb3[row] = v[0];
       }
+    }
+  };
+
+  // dW2 accumulator (M=64: rows 16w..16w+15 in lanes 32w..32w+15; column 64 = db2) -> slab, fire-and-forget adds
+  auto dw2_to_slab = [&]() {
+    const int j = (warp & 3) * 16 + lane;
+    const bool ok = lane < 16;
+    for (int i = 0; i < kColsPerWg; i += 16) {
+      float v[16];
+      tmem_ld16(lane_addr + TM.dW2 + wg * kColsPerWg + i, v);
+      tmem_ld_wait();
+      if (ok)
+#pragma unroll
+        for (int q = 0; q < 16; ++q) atomicAdd(gW2 + j * kH + wg * kColsPerWg + i + q, v[q]);
+    }
+    if (wg == 0) {
+      float v[8];
+      tmem_ld8(lane_addr + TM.dW2 + kH, v);
+      tmem_ld_wait();
+      if (ok) atomicAdd(gb2 + j, v[0]);
     }
   };
 
@@ -585,9 +612,23 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
     if (tile + 1 < tile_hi) prefetch(t_cur, b_cur);
 
     // ---- slot context: s points, sphere features, S1 + b1, reduction coefficients
+    // bounded accumulation chains in TMEM (kFlushTiles): drain dW3 / dW2 every kFlushTiles tiles, D1 also
+    // within a long time slot
+    const bool restart = BWD && (tile - tile_lo) % kFlushTiles == 0;
+    if (BWD && restart && tile > tile_lo) {  // every GEMM of the previous tile except D1 has been waited for
+      tc_fence_after();
+      for (int ch = 0; ch < min(nch, n_resident); ++ch) dw3_to_slab(ch, TM.dW3 + 80 * ch, true);
+      dw2_to_slab();
+      tc_fence_before();
+    }
+    if (BWD && t_idx == cur_t && slot_tiles % kFlushTiles == 0) {
+      flush_slot();
+      first_in_slot = true;
+    }
     if (t_idx != cur_t) {
       flush_slot();
       cur_t = t_idx;
+      slot_tiles = 0;
       first_in_slot = true;
       if (!BWD && A.tabCoef) {
         // forward: everything that depends on the time index only comes from the tables (pref is folded in)
@@ -812,7 +853,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
             const GemmOp gdw = make_gemm(adO, (uint32_t)L.dO_img, kRows, 1, aH2, (uint32_t)L.H2_img, kRows, 1, 128,
                                          kH2Cols, kRows);
             const bool res = ch < n_resident;
-            issue_gemm(gdw, tmem + TM.dW3 + 80 * (res ? ch : n_resident), res ? !first_tile : false);
+            issue_gemm(gdw, tmem + TM.dW3 + 80 * (res ? ch : n_resident), res ? !restart : false);
             umma_commit(&bar_aux[0]);
           }
           __syncwarp();
@@ -863,7 +904,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
           tc_fence_after();
           const GemmOp gdw2 = make_gemm(adO, (uint32_t)L.dO_img, kRows, 1, aH1, (uint32_t)L.H1_img, kRows, 1, 64,
                                         kH1Cols, kRows);
-          issue_gemm(gdw2, tmem + TM.dW2, !first_tile);
+          issue_gemm(gdw2, tmem + TM.dW2, !restart);
           umma_commit(&bar_aux[1]);
         }
         __syncwarp();
@@ -913,7 +954,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
       }
       pend_aux2 = true;
     }
-    first_tile = false;
+    ++slot_tiles;
     first_in_slot = false;
     NL_PROF(11);
   }
@@ -922,29 +963,13 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
     for (int i = 0; i < 12; ++i) atomicAdd((unsigned long long*)A.prof + i, (unsigned long long)prof_acc[i]);
 #endif
 
-  // ---- epilogue: flush the TMEM-resident weight gradients to this CTA's slab
+  // ---- epilogue: what is left in the TMEM-resident weight-gradient accumulators -> this CTA's slab
   if (BWD) {
     flush_slot();
     if (tile_hi > tile_lo) {
       tc_fence_after();
-      for (int ch = 0; ch < min(nch, n_resident); ++ch) dw3_to_slab(ch, TM.dW3 + 80 * ch, false);
-      // dW2: M=64 accumulator
-      const int j = (warp & 3) * 16 + lane;
-      const bool ok = lane < 16;
-      for (int i = 0; i < kColsPerWg; i += 16) {
-        float v[16];
-        tmem_ld16(lane_addr + TM.dW2 + wg * kColsPerWg + i, v);
-        tmem_ld_wait();
-        if (ok)
-#pragma unroll
-          for (int q = 0; q < 16; ++q) gW2[j * kH + wg * kColsPerWg + i + q] = v[q];
-      }
-      if (wg == 0) {
-        float v[8];
-        tmem_ld8(lane_addr + TM.dW2 + kH, v);
-        tmem_ld_wait();
-        if (ok) gb2[j] = v[0];
-      }
+      for (int ch = 0; ch < min(nch, n_resident); ++ch) dw3_to_slab(ch, TM.dW3 + 80 * ch, true);
+      dw2_to_slab();
     }
   }
   if (!BWD && stash && warp == 0 && elect_one()) bulk_wait_all();
@@ -1214,12 +1239,14 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
           if (tile_lo + 1 < tile_hi) bulk_prefetch_l2(A.stash + (size_t)(tile_lo + 1) * kStashTile, (uint32_t)kStashTile);
         }
         uint32_t p_dO = 0, p_z2 = 0, p_z1 = 0, p_sl3 = 0, p_sdh2 = 0, p_sdh1 = 0, p_h1 = 0, p_a0 = 0, p_a1 = 0, p_a2 = 0;
-        bool first_tile = true;
-        int cur_t = -1;
+        int cur_t = -1, slot_tiles = 0;
         // dW2(i) = Z2g^T.[h1 | 1 p] only has to finish before tile i+1 rewrites the Z2g image / reloads h1, so it is
         // issued behind L3 of tile i+1 and streams its operands while the epilogue is in its math-heavy head
         // stage (an SS-mode MMA saturates the shared-memory port: issued right after dH1 it starved the
         // epilogue's Z1g stage, measured 3000 clk instead of 900).
+        // accumulate flags follow the drain schedule of the epilogue: tile j of this CTA restarts the dW3 / dW2
+        // accumulators when j % kFlushTiles == 0, the D1 accumulator when its time slot starts or every
+        // kFlushTiles tiles within the slot
         auto issue_dw2 = [&](bool accumulate) {
           mbar_wait_relaxed(&bar_h1, p_h1);
           p_h1 ^= 1;
@@ -1235,13 +1262,15 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
             b_run = 0;
             ++t_run;
           }
-          const bool first_in_slot = t_idx != cur_t;
+          if (t_idx != cur_t) slot_tiles = 0;
+          const bool first_in_slot = slot_tiles % kFlushTiles == 0;
+          ++slot_tiles;
           cur_t = t_idx;
           mbar_wait_relaxed(&seq_l3, p_sl3);  // L3(0) of this tile is queued
           p_sl3 ^= 1;
           if (tile > tile_lo) {
             NL_TRACE(17);
-            issue_dw2(tile > tile_lo + 1);
+            issue_dw2((tile - 1 - tile_lo) % kFlushTiles != 0);
             NL_TRACE(18);
             // the h1 image is free once D1 and dW2 of the previous tile have executed: request this tile's h1
             mbar_wait_relaxed(&bar_aux[2], p_a2);
@@ -1269,7 +1298,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
             const GemmOp gdw = make_gemm(adO, (uint32_t)L.dO_img, kRows, 1, aH2, (uint32_t)L.H2_img, kRows, 1, 128,
                                          kH2Cols, kRows);
             NL_TRACE(14);
-            issue_gemm(gdw, tmem + TM.dW3 + 80 * ch, !first_tile);
+            issue_gemm(gdw, tmem + TM.dW3 + 80 * ch, (tile - tile_lo) % kFlushTiles != 0);
             umma_commit(&bar_aux[0]);
           }
           // the h2 image is free once the last dW3 has executed: request the next tile's h2
@@ -1292,9 +1321,8 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
           issue_gemm(gd1, tmem + TM.D1, !first_in_slot);
           umma_commit(&bar_aux[2]);
           NL_TRACE(16);
-          first_tile = false;
         }
-        if (tile_lo < tile_hi) issue_dw2(tile_hi - tile_lo > 1);
+        if (tile_lo < tile_hi) issue_dw2((tile_hi - 1 - tile_lo) % kFlushTiles != 0);
       }
     }
   } else {
@@ -1320,7 +1348,56 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
     float* gW3 = gb2 + kH;
     float* gb3 = gW3 + (long long)2 * D * n * kH;
 
-    int cur_t = -1;
+    // drain of the TMEM-resident weight-gradient accumulators into this CTA's slab (owner thread, round to nearest)
+    auto drain_dw3 = [&]() {
+      tc_fence_after();
+      for (int ch = 0; ch < nch; ++ch) {
+        const int d = ch / A.nkc, k = (ch % A.nkc) * A.kc + (r >> 1);
+        const bool ok = (r >> 1) < A.kc && k < n && r < NP;
+        const int row = ((r & 1) ? (D + d) : d) * n + k;
+        for (int i = 0; i < kColsPerWg; i += 16) {
+          float v[16];
+          tmem_ld16(lane_addr + TM.dW3 + 80 * ch + wg * kColsPerWg + i, v);
+          tmem_ld_wait();
+          if (ok) {
+            float* dst = gW3 + (long long)row * kH + wg * kColsPerWg + i;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) dst[j] += v[j];
+          }
+        }
+        if (wg == 0) {
+          float v[8];
+          tmem_ld8(lane_addr + TM.dW3 + 80 * ch + kH, v);
+          tmem_ld_wait();
+          if (ok) gb3[row] += v[0];
+        }
+      }
+      tc_fence_before();
+    };
+    auto drain_dw2 = [&]() {
+      tc_fence_after();
+      const int j = (warp & 3) * 16 + lane;  // M=64 accumulator: rows 16w..16w+15 in lanes 32w..32w+15
+      const bool ok = lane < 16;
+      for (int i = 0; i < kColsPerWg; i += 16) {
+        float v[16];
+        tmem_ld16(lane_addr + TM.dW2 + wg * kColsPerWg + i, v);
+        tmem_ld_wait();
+        if (ok) {
+          float* dst = gW2 + j * kH + wg * kColsPerWg + i;
+#pragma unroll
+          for (int q = 0; q < 16; ++q) dst[q] += v[q];
+        }
+      }
+      if (wg == 0) {
+        float v[8];
+        tmem_ld8(lane_addr + TM.dW2 + kH, v);
+        tmem_ld_wait();
+        if (ok) gb2[j] += v[0];
+      }
+      tc_fence_before();
+    };
+
+    int cur_t = -1, slot_tiles = 0;
     // per-slot accumulator D1 = Z1g^T.[1 p] -> G1[t] (a time index can be shared by two CTAs -> atomics);
     // dw1_from_g1_kernel turns G1 into dW1 / db1 afterwards
     auto flush_slot = [&]() {
@@ -1381,9 +1458,11 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
       const unsigned char* H2_lo = H2_hi + L.H2_img;
 
       // ---- slot context: the reduction coefficients of this time index (time_tables_kernel)
+      if (t_idx == cur_t && slot_tiles % kFlushTiles == 0) flush_slot();  // bounded D1 chain within a long slot
       if (t_idx != cur_t) {
         flush_slot();
         cur_t = t_idx;
+        slot_tiles = 0;
         for (int idx = tid; idx < A.nkc * NP; idx += kEpi)
           sCoef[idx] = __ldg(A.tabCoef + (size_t)t_idx * A.nkc * NP + idx);  // pref * (cr, ci)
         ep_sync();
@@ -1391,6 +1470,10 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
       NL_PROF(0);
       if (tid == 0) NL_TRACE(0);
 
+      ++slot_tiles;
+      // bounded accumulation chains: dW3 of the previous tile has executed (waited for in its stage 4)
+      const bool drain = tile > tile_lo && (tile - tile_lo) % kFlushTiles == 0;
+      if (drain) drain_dw3();
       // ---- 1. D1 of the previous tile reads Z1g: in the dO image (rewritten by the head stage) unless Z1g owns one
       if (!z1sep) wait_d1();
       NL_PROF(1);
@@ -1469,6 +1552,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
       }
       if (!zsep) wait_dw3();  // dW3 of the last chunk reads the dO image
       wait_dw2();             // dW2 of the PREVIOUS tile (deferred behind this tile's L3) reads the Z2g and h1 images
+      if (drain) drain_dw2();  // (dW2 of this tile restarts the accumulator; it is issued after stage 4)
       wait_d1();              // D1 of the previous tile reads the [1 p] chunk (and the Z1g image, rewritten in stage 4)
       if (wg == 0) {          // this tile's [1 p] chunk of the h1 image (B operand of dW2 and D1)
         float q[8];
@@ -1548,48 +1632,486 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
       for (int i = 0; i < 12; ++i) atomicAdd((unsigned long long*)A.prof + i, (unsigned long long)prof_acc[i]);
 #endif
 
-    // ---- TMEM-resident weight gradients -> this CTA's slab
+    // ---- what is left in the TMEM-resident weight-gradient accumulators -> this CTA's slab
     flush_slot();
     wait_dw2();
     wait_dw3();
     if (tile_hi > tile_lo) {
+      drain_dw3();
+      drain_dw2();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, kTmemCols);
+}
+
+
+// =============================================================================================
+// Saved backward with TWO tiles in flight (single W3 chunk: terms <= 64, d_obs = 1).
+// The one-stream kernel above runs a dependent chain per tile (L3 -> heads -> dH2 -> Z2g -> dH1 -> Z1g) with
+// every epilogue warp in the same stage, so each GEMM round trip is idle time.  Here two streams of 256
+// epilogue threads work on different tiles; each stream has its own pair of issuer warps (main chain /
+// weight gradients + loads), its own TMEM accumulators (the layer-3 output and the dH accumulator share
+// columns) and -- because two full sets of operand images do not fit in 227 KB -- only TWO images:
+//   X : dO -> Z2g -> Z1g      (each rewrite waits for the weight-gradient GEMM that still reads it)
+//   H : h2 -> h1 of the same tile, streamed in one after the other ([ones] / [1 p] chunk rewritten in place)
+// While a stream waits for a GEMM or an image, the other stream's epilogue has the SM.
+struct Bs2Smem {
+  size_t X[2], Hb[2], W2, W3, small, total;
+  size_t X_img, H_img, W2_img, W3_img;
+  int W1p, b3, coef[2], dp[2], nfloats;
+};
+__host__ __device__ inline Bs2Smem bs2_smem(int NP, int nkc, int K) {
+  Bs2Smem L;
+  L.X_img = image_bytes(kRows, NP > kH ? NP : kH);
+  L.H_img = image_bytes(kRows, kH2Cols);
+  L.W2_img = image_bytes(kH, kH);
+  L.W3_img = image_bytes(NP, kH);
+  size_t o = 0;
+  for (int s = 0; s < 2; ++s) { L.X[s] = o; o += 2 * L.X_img; }
+  for (int s = 0; s < 2; ++s) { L.Hb[s] = o; o += 2 * L.H_img; }
+  L.W2 = o; o += 2 * L.W2_img;
+  L.W3 = o; o += 2 * L.W3_img;
+  L.small = o;
+  int f = 0;
+  L.W1p = f; f += kH * 8;
+  L.b3 = f; f += NP;
+  for (int s = 0; s < 2; ++s) { L.coef[s] = f; f += nkc * NP; }
+  for (int s = 0; s < 2; ++s) { L.dp[s] = f; f += 2 * kRows * K; }
+  L.nfloats = f;
+  L.total = o + (size_t)f * 4 + 64;
+  return L;
+}
+
+template <int KP>
+__global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcArgs A) {
+  constexpr int kStreamThreads = 256;
+  constexpr int kCols = 32;  // hidden columns per thread (two warpgroups per stream)
+  constexpr uint32_t kTmemCols = 512;
+  extern __shared__ __align__(128) unsigned char smem_bs2[];
+  unsigned char* smem = smem_bs2;
+  __shared__ __align__(8) uint64_t bar_l3[2], bar_main[2], bar_aux[2][3], bar_h1[2], bar_h2[2];
+  __shared__ __align__(8) uint64_t rdy_dO[2], rdy_z2[2], rdy_z1[2], seq_dh2[2], seq_dh1[2];
+  __shared__ uint32_t tmem_slot;
+
+  const int n = A.n, K = A.K, NP = A.NP;
+  const Bs2Smem L = bs2_smem(NP, A.nkc, K);
+  const int so_cols = NP > kH ? NP : kH;
+  // TMEM per stream: [SO (layer-3 output, then dH2 / dH1) | dW2 80 | dW3 80 | D1 16]
+  const int tm_stream = so_cols + 80 + 80 + 16;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ldw1 = 2 * n + K;
+  float* sf = reinterpret_cast<float*>(smem + L.small);
+  float* sW1p = sf + L.W1p;
+  float* sb3 = sf + L.b3;
+  unsigned char* W2_hi = smem + L.W2;
+  unsigned char* W2_lo = W2_hi + L.W2_img;
+  unsigned char* W3_hi = smem + L.W3;
+  const uint32_t w3_bytes = (uint32_t)(2 * L.W3_img);
+
+  // tile ranges: the CTA's contiguous range split in two halves, one per stream
+  const long long per = A.ntiles / gridDim.x, rem = A.ntiles % gridDim.x;
+  const long long cta_lo = blockIdx.x * per + min((long long)blockIdx.x, rem);
+  const long long cta_n = per + (blockIdx.x < rem ? 1 : 0);
+  const long long n0 = (cta_n + 1) / 2;
+  const long long s_lo[2] = {cta_lo, cta_lo + n0};
+  const long long s_n[2] = {n0, cta_n - n0};
+
+  // ---- prologue (all 640 threads)
+  for (size_t i = tid; i < L.total / 16; i += kBsThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  if (tid < kH) {
+    for (int c0 = 0; c0 < kH; c0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = __ldg(A.W2 + tid * kH + c0 + i);
+      store_chunk8(W2_hi, W2_lo, kH, tid, c0, v);
+    }
+    for (int j = 0; j < K; ++j) sW1p[tid * 8 + j] = __ldg(A.W1 + (size_t)tid * ldw1 + 2 * n + j);
+  }
+  for (int idx = tid; idx < NP; idx += kBsThreads) sb3[idx] = __ldg(A.b3pack + idx);
+  if (warp == 0) tmem_alloc(&tmem_slot, kTmemCols);
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bar_l3[s], 1);
+      mbar_init(&bar_main[s], 1);
+      for (int j = 0; j < 3; ++j) mbar_init(&bar_aux[s][j], 1);
+      mbar_init(&bar_h1[s], 1);
+      mbar_init(&bar_h2[s], 1);
+      mbar_init(&rdy_dO[s], 1);
+      mbar_init(&rdy_z2[s], 1);
+      mbar_init(&rdy_z1[s], 1);
+      mbar_init(&seq_dh2[s], 1);
+      mbar_init(&seq_dh1[s], 1);
+    }
+    fence_mbar_init();
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (cta_n > 0 && warp == 0 && elect_one()) {  // the single W3 chunk, resident for the whole kernel
+    __shared__ __align__(8) uint64_t bar_w3;
+    mbar_init(&bar_w3, 1);
+    fence_mbar_init();
+    bulk_load(W3_hi, A.w3pack, w3_bytes, &bar_w3);
+    mbar_wait(&bar_w3, 0);
+  }
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t aW2 = smem_u32(W2_hi), aW3 = smem_u32(W3_hi);
+
+  if (warp >= 2 * kStreamThreads / 32) {
+    // =============================== issuer warps: 16 / 17 -> stream 0, 18 / 19 -> stream 1 ===============================
+    const int iw = warp - 2 * kStreamThreads / 32;
+    const int s = iw >> 1;
+    const bool is_main = (iw & 1) == 0;
+    const uint32_t aX = smem_u32(smem + L.X[s]), aH = smem_u32(smem + L.Hb[s]);
+    const uint32_t x_lo = (uint32_t)L.X_img, h_lo = (uint32_t)L.H_img;
+    const uint32_t tSO = tmem + s * tm_stream, tdW2 = tSO + so_cols, tdW3 = tdW2 + 80, tD1 = tdW3 + 80;
+    const long long tile_lo = s_lo[s], tile_hi = s_lo[s] + s_n[s];
+    if (is_main) {
+      if (elect_one()) {
+        uint32_t p_h2 = 0, p_dO = 0, p_z2 = 0;
+        for (long long tile = tile_lo; tile < tile_hi; ++tile) {
+          mbar_wait_relaxed(&bar_h2[s], p_h2);
+          p_h2 ^= 1;
+          tc_fence_after();
+          issue_gemm(make_gemm(aH, h_lo, kRows, 0, aW3, (uint32_t)L.W3_img, NP, 0, 128, NP, kH), tSO, false);  // L3
+          umma_commit(&bar_l3[s]);
+          mbar_wait_relaxed(&rdy_dO[s], p_dO);
+          p_dO ^= 1;
+          tc_fence_after();
+          issue_gemm(make_gemm(aX, x_lo, kRows, 0, aW3, (uint32_t)L.W3_img, NP, 1, 128, kH, NP), tSO, false);  // dH2
+          umma_commit(&bar_main[s]);
+          mbar_arrive(&seq_dh2[s]);
+          mbar_wait_relaxed(&rdy_z2[s], p_z2);
+          p_z2 ^= 1;
+          tc_fence_after();
+          issue_gemm(make_gemm(aX, x_lo, kRows, 0, aW2, (uint32_t)L.W2_img, kH, 1, 128, kH, kH), tSO, false);  // dH1
+          umma_commit(&bar_main[s]);
+          mbar_arrive(&seq_dh1[s]);
+        }
+      }
+    } else {
+      if (elect_one()) {
+        unsigned char* H_hi = smem + L.Hb[s];
+        unsigned char* H_lo = H_hi + L.H_img;
+        auto load_img = [&](long long tl, int which, uint64_t* bar) {  // which: 0 = h1, 1 = h2
+          const unsigned char* src = A.stash + (size_t)tl * kStashTile + (size_t)which * 2 * kStashImg;
+          mbar_expect_tx(bar, 2 * kStashImg);
+          bulk_load_tx(H_hi, src, kStashImg, bar);
+          bulk_load_tx(H_lo, src + kStashImg, kStashImg, bar);
+        };
+        if (tile_lo < tile_hi) {
+          load_img(tile_lo, 1, &bar_h2[s]);
+          bulk_prefetch_l2(A.stash + (size_t)tile_lo * kStashTile, 2 * kStashImg);
+        }
+        uint32_t p_dO = 0, p_z2 = 0, p_z1 = 0, p_sdh2 = 0, p_sdh1 = 0, p_h1 = 0, p_a0 = 0, p_a1 = 0, p_a2 = 0;
+        int cur_t = -1, slot_tiles = 0;
+        int t_run = (int)(tile_lo / A.nbt), b_run = (int)(tile_lo % A.nbt);
+        for (long long tile = tile_lo; tile < tile_hi; ++tile) {
+          const int t_idx = t_run;
+          if (++b_run == A.nbt) {
+            b_run = 0;
+            ++t_run;
+          }
+          if (t_idx != cur_t) slot_tiles = 0;
+          const bool first_in_slot = slot_tiles % kFlushTiles == 0;  // (drain schedule of the epilogue)
+          ++slot_tiles;
+          cur_t = t_idx;
+          const bool restart = (tile - tile_lo) % kFlushTiles == 0;   // dW3 / dW2 accumulators drained before this tile
+          // dW3 += dO^T . [h2 | 1]   (behind dH2)
+          mbar_wait_relaxed(&rdy_dO[s], p_dO);
+          p_dO ^= 1;
+          mbar_wait_relaxed(&seq_dh2[s], p_sdh2);
+          p_sdh2 ^= 1;
+          tc_fence_after();
+          issue_gemm(make_gemm(aX, x_lo, kRows, 1, aH, h_lo, kRows, 1, 128, kH2Cols, kRows), tdW3, !restart);
+          umma_commit(&bar_aux[s][0]);
+          // the H image is free for h1 once dW3 has executed and the epilogue has read h2 (Z2g stage)
+          mbar_wait_relaxed(&bar_aux[s][0], p_a0);
+          p_a0 ^= 1;
+          mbar_wait_relaxed(&rdy_z2[s], p_z2);
+          p_z2 ^= 1;
+          load_img(tile, 0, &bar_h1[s]);
+          if (tile + 1 < tile_hi) bulk_prefetch_l2(A.stash + (size_t)(tile + 1) * kStashTile, (uint32_t)kStashTile);
+          // dW2 += Z2g^T . [h1 | 1 p]   (behind dH1)
+          mbar_wait_relaxed(&seq_dh1[s], p_sdh1);
+          p_sdh1 ^= 1;
+          mbar_wait_relaxed(&bar_h1[s], p_h1);
+          p_h1 ^= 1;
+          tc_fence_after();
+          issue_gemm(make_gemm(aX, x_lo, kRows, 1, aH, h_lo, kRows, 1, 64, kH1Cols, kRows), tdW2, !restart);
+          umma_commit(&bar_aux[s][1]);
+          // D1 (+)= Z1g^T . [1 p]
+          mbar_wait_relaxed(&rdy_z1[s], p_z1);
+          p_z1 ^= 1;
+          tc_fence_after();
+          issue_gemm(make_gemm(aX, x_lo, kRows, 1, aH + 8 * (kRows * 16), h_lo, kRows, 1, 64, 8, kRows), tD1,
+                     !first_in_slot);
+          umma_commit(&bar_aux[s][2]);
+          // the H image is free for the next tile's h2 once dW2 and D1 have executed
+          mbar_wait_relaxed(&bar_aux[s][1], p_a1);
+          p_a1 ^= 1;
+          mbar_wait_relaxed(&bar_aux[s][2], p_a2);
+          p_a2 ^= 1;
+          if (tile + 1 < tile_hi) load_img(tile + 1, 1, &bar_h2[s]);
+        }
+      }
+    }
+  } else {
+    // =============================== epilogue streams ===============================
+    const int s = warp / (kStreamThreads / 32);
+    const int stid = tid - s * kStreamThreads;
+    const int wg = stid >> 7;
+    const int r = stid & 127;
+    unsigned char* X_hi = smem + L.X[s];
+    unsigned char* X_lo = X_hi + L.X_img;
+    unsigned char* H_hi = smem + L.Hb[s];
+    unsigned char* H_lo = H_hi + L.H_img;
+    float* sCoef = sf + L.coef[s];
+    float* sdp = sf + L.dp[s];
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t tSO = s * tm_stream, tdW2 = tSO + so_cols, tdW3 = tdW2 + 80, tD1 = tdW3 + 80;
+    auto st_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + s), "n"(kStreamThreads) : "memory"); };
+    uint32_t ph_main = 0, ph_l3 = 0, ph_h1 = 0, ph_h2 = 0;
+    uint32_t ph_aux0 = 0, ph_aux1 = 0, ph_aux2 = 0;
+    bool pend_aux0 = false, pend_aux1 = false, pend_aux2 = false;
+    auto wait_dw3 = [&]() {
+      if (pend_aux0) { mbar_wait(&bar_aux[s][0], ph_aux0); ph_aux0 ^= 1; pend_aux0 = false; }
+    };
+    auto wait_dw2 = [&]() {
+      if (pend_aux1) { mbar_wait(&bar_aux[s][1], ph_aux1); ph_aux1 ^= 1; pend_aux1 = false; }
+    };
+    auto wait_d1 = [&]() {
+      if (pend_aux2) { mbar_wait(&bar_aux[s][2], ph_aux2); ph_aux2 ^= 1; pend_aux2 = false; }
+    };
+    const long long tile_lo = s_lo[s], tile_hi = s_lo[s] + s_n[s];
+
+    // drain of this stream's TMEM-resident dW3 / dW2 accumulators into the CTA slab (shared with the other
+    // stream -> atomics; round-to-nearest adds, see kFlushTiles)
+    float* slab = A.slab + (long long)blockIdx.x * A.slab_len;
+    float* gW2 = slab + (long long)kH * ldw1 + kH;
+    float* gb2 = gW2 + kH * kH;
+    float* gW3 = gb2 + kH;
+    float* gb3 = gW3 + (long long)2 * n * kH;
+    auto drain = [&]() {
       tc_fence_after();
-      for (int ch = 0; ch < nch; ++ch) {
-        const int d = ch / A.nkc, k = (ch % A.nkc) * A.kc + (r >> 1);
-        const bool ok = (r >> 1) < A.kc && k < n && r < NP;
-        const int row = ((r & 1) ? (D + d) : d) * n + k;
-        for (int i = 0; i < kColsPerWg; i += 16) {
+      {
+        const int k = r >> 1;
+        const bool ok = k < A.kc && k < n && r < NP;
+        const int row = ((r & 1) ? 1 : 0) * n + k;  // d_obs == 1: theta rows [0, n), phi rows [n, 2n)
+        for (int i = 0; i < kCols; i += 16) {
           float v[16];
-          tmem_ld16(lane_addr + TM.dW3 + 80 * ch + wg * kColsPerWg + i, v);
+          tmem_ld16(lane_addr + tdW3 + wg * kCols + i, v);
           tmem_ld_wait();
           if (ok)
 #pragma unroll
-            for (int j = 0; j < 16; ++j) gW3[(long long)row * kH + wg * kColsPerWg + i + j] = v[j];
+            for (int j = 0; j < 16; ++j) atomicAdd(gW3 + (long long)row * kH + wg * kCols + i + j, v[j]);
         }
         if (wg == 0) {
           float v[8];
-          tmem_ld8(lane_addr + TM.dW3 + 80 * ch + kH, v);
+          tmem_ld8(lane_addr + tdW3 + kH, v);
           tmem_ld_wait();
-          if (ok) gb3[row] = v[0];
+          if (ok) atomicAdd(gb3 + row, v[0]);
         }
       }
       const int j = (warp & 3) * 16 + lane;
       const bool ok = lane < 16;
-      for (int i = 0; i < kColsPerWg; i += 16) {
+      for (int i = 0; i < kCols; i += 16) {
         float v[16];
-        tmem_ld16(lane_addr + TM.dW2 + wg * kColsPerWg + i, v);
+        tmem_ld16(lane_addr + tdW2 + wg * kCols + i, v);
         tmem_ld_wait();
         if (ok)
 #pragma unroll
-          for (int q = 0; q < 16; ++q) gW2[j * kH + wg * kColsPerWg + i + q] = v[q];
+          for (int q = 0; q < 16; ++q) atomicAdd(gW2 + j * kH + wg * kCols + i + q, v[q]);
       }
       if (wg == 0) {
         float v[8];
-        tmem_ld8(lane_addr + TM.dW2 + kH, v);
+        tmem_ld8(lane_addr + tdW2 + kH, v);
         tmem_ld_wait();
-        if (ok) gb2[j] = v[0];
+        if (ok) atomicAdd(gb2 + j, v[0]);
       }
+      tc_fence_before();
+    };
+
+    int cur_t = -1, slot_tiles = 0;
+    auto flush_slot = [&]() {
+      if (cur_t < 0) return;
+      wait_d1();
+      tc_fence_after();
+      if (wg == 0) {
+        float v[8];
+        tmem_ld8(lane_addr + tD1, v);
+        tmem_ld_wait();
+        if (lane < 16) {
+          float* dst = A.g1buf + ((size_t)cur_t * kH + (warp & 3) * 16 + lane) * 8;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (i <= K) atomicAdd(dst + i, v[i]);
+        }
+      }
+      tc_fence_before();
+    };
+
+    constexpr int kGPre = 1;  // d_obs == 1
+    float pv_n[KP], g_n;
+    auto prefetch = [&](int ti, int bi) {
+      const int bn = bi * kRows + r;
+      const bool ok = bn < A.B;
+#pragma unroll
+      for (int j = 0; j < KP; ++j) pv_n[j] = (ok && j < K) ? __ldg(A.p + (size_t)bn * K + j) : 0.f;
+      g_n = ok ? __ldg(A.gx + ((size_t)bn * A.T + ti)) : 0.f;
+    };
+    int t_cur = (int)(tile_lo / A.nbt), b_cur = (int)(tile_lo % A.nbt);
+    if (tile_lo < tile_hi) prefetch(t_cur, b_cur);
+    const int ncols_real = min(NP, (2 * A.kc + 3) & ~3);
+    const int cw = (((ncols_real + 1) / 2) + 3) & ~3;
+    (void)kGPre;
+
+    for (long long tile = tile_lo; tile < tile_hi; ++tile) {
+      const int t_idx = t_cur;
+      const int b = b_cur * kRows + r;
+      if (++b_cur == A.nbt) {
+        b_cur = 0;
+        ++t_cur;
+      }
+      const bool valid = b < A.B;
+      float pv[KP];
+#pragma unroll
+      for (int j = 0; j < KP; ++j) pv[j] = pv_n[j];
+      const float g = g_n;
+      if (tile + 1 < tile_hi) prefetch(t_cur, b_cur);
+
+      if (t_idx == cur_t && slot_tiles % kFlushTiles == 0) flush_slot();  // bounded D1 chain within a long slot
+      if (t_idx != cur_t) {
+        flush_slot();
+        cur_t = t_idx;
+        slot_tiles = 0;
+        for (int idx = stid; idx < A.nkc * NP; idx += kStreamThreads)
+          sCoef[idx] = __ldg(A.tabCoef + (size_t)t_idx * A.nkc * NP + idx);  // pref * (cr, ci)
+        st_sync();  // the head stage reads coefficients written by other threads of the stream
+      }
+      ++slot_tiles;
+      // bounded accumulation chains: dW3 / dW2 of the previous tile have executed (waited for in its stages 3 / 4)
+      if (tile > tile_lo && (tile - tile_lo) % kFlushTiles == 0) drain();
+      // ---- 1. X and the [1 p] chunk of H are still read by D1 of the previous tile
+      wait_d1();
+      if (wg == 0) {  // chunk 8 of the H image = [1 0 ...] while it holds h2 (-> db3)
+        const size_t off = (size_t)8 * (kRows * 16) + (size_t)r * 16;
+        *reinterpret_cast<uint4*>(H_hi + off) = make_uint4(0x00003F80u, 0, 0, 0);
+        *reinterpret_cast<uint4*>(H_lo + off) = make_uint4(0, 0, 0, 0);
+      }
+      mbar_wait(&bar_l3[s], ph_l3);
+      ph_l3 ^= 1;
+      mbar_wait(&bar_h2[s], ph_h2);  // landed before L3 could run; makes the bulk-async writes visible to this thread
+      ph_h2 ^= 1;
+      tc_fence_after();
+
+      // ---- 2. heads forward + backward -> dO image
+      for (int c0 = wg * cw; c0 < min((wg + 1) * cw, ncols_real); c0 += 4) {
+        float v[4], dv[4];
+        tmem_ld4(lane_addr + tSO + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int c = c0 + 2 * i;
+          const fast::Head h = fast::head_forward(A.P.head, v[2 * i] + sb3[c], v[2 * i + 1] + sb3[c + 1]);
+          fast::head_backward(A.P.head, h, g * sCoef[c], -g * sCoef[c + 1], &dv[2 * i], &dv[2 * i + 1]);
+        }
+        store_chunk4(X_hi, X_lo, kRows, r, c0, dv);
+      }
+      fence_async_smem();
+      tc_fence_before();
+      st_sync();
+      if (stid == 0) mbar_arrive(&rdy_dO[s]);
+      pend_aux0 = true;
+
+      // ---- 3. Z2g = dH2 (1 - h2^2) -> X (after dW3, which still reads dO there)
+      mbar_wait(&bar_main[s], ph_main);
+      ph_main ^= 1;
+      tc_fence_after();
+      wait_dw3();
+#pragma unroll
+      for (int hf = 0; hf < kCols; hf += 16) {
+        float v[16], z[16];
+        tmem_ld16(lane_addr + tSO + wg * kCols + hf, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 16; q += 8) {
+          float hv[8];
+          load_chunk8(H_hi, H_lo, kRows, r, wg * kCols + hf + q, hv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) z[q + j] = v[q + j] * (1.f - hv[j] * hv[j]);
+        }
+#pragma unroll
+        for (int q = 0; q < 16; q += 8) store_chunk8(X_hi, X_lo, kRows, r, wg * kCols + hf + q, &z[q]);
+      }
+      if (wg == 0) {  // chunk 8 of the H image = [1 p] for its life as h1 (B operand of dW2 and D1)
+        float q[8];
+        q[0] = valid ? 1.f : 0.f;
+#pragma unroll
+        for (int j = 0; j < kMaxK; ++j) q[1 + j] = (j < KP) ? pv[j < KP ? j : 0] : 0.f;
+        store_chunk8(H_hi, H_lo, kRows, r, kH, q);
+      }
+      fence_async_smem();
+      tc_fence_before();
+      st_sync();
+      if (stid == 0) mbar_arrive(&rdy_z2[s]);
+      pend_aux1 = true;
+
+      // ---- 4. Z1g = dH1 (1 - h1^2) -> X (after dW2, which still reads Z2g there) ; dp
+      mbar_wait(&bar_main[s], ph_main);
+      ph_main ^= 1;
+      tc_fence_after();
+      mbar_wait(&bar_h1[s], ph_h1);
+      ph_h1 ^= 1;
+      wait_dw2();
+      float dpv[KP];
+#pragma unroll
+      for (int j = 0; j < KP; ++j) dpv[j] = 0.f;
+#pragma unroll
+      for (int hf = 0; hf < kCols; hf += 16) {
+        float v[16], z[16];
+        tmem_ld16(lane_addr + tSO + wg * kCols + hf, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 16; q += 8) {
+          float hv[8];
+          load_chunk8(H_hi, H_lo, kRows, r, wg * kCols + hf + q, hv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float zz = v[q + j] * (1.f - hv[j] * hv[j]);
+            z[q + j] = zz;
+            const int c = wg * kCols + hf + q + j;
+#pragma unroll
+            for (int qq = 0; qq < KP; ++qq) dpv[qq] = fmaf(zz, sW1p[c * 8 + qq], dpv[qq]);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 16; q += 8) store_chunk8(X_hi, X_lo, kRows, r, wg * kCols + hf + q, &z[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < KP; ++q)
+        if (q < K) sdp[(wg * kRows + r) * K + q] = dpv[q];
+      fence_async_smem();
+      tc_fence_before();
+      st_sync();
+      if (stid == 0) mbar_arrive(&rdy_z1[s]);
+      if (wg == 0) {
+        float* dst = A.dp_part + ((size_t)tile * kRows + r) * K;
+        for (int q = 0; q < K; ++q) dst[q] = valid ? sdp[r * K + q] + sdp[(kRows + r) * K + q] : 0.f;
+      }
+      pend_aux2 = true;
     }
+
+    // ---- what is left in this stream's accumulators -> the CTA slab
+    flush_slot();
+    wait_dw2();
+    wait_dw3();
+    if (tile_hi > tile_lo) drain();
   }
   tc_fence_before();
   __syncthreads();
@@ -1658,6 +2180,8 @@ struct BsGeom {
   bool ok, zsep, z1sep;
   int h2bufs;
   size_t smem;
+  bool two;          // two tiles in flight (fused_tc_bwd_saved2_kernel): one W3 chunk, d_obs = 1, terms <= 40
+  size_t smem_two;
 };
 static BsGeom bs_geom(const nl_desc* d, const TcGeom& g) {
   BsGeom b{};
@@ -1666,6 +2190,14 @@ static BsGeom bs_geom(const nl_desc* d, const TcGeom& g) {
   const size_t limit = 227 * 1024 - 256;  // static shared memory of the kernel: 16 mbarriers + the TMEM slot (<= 256 B)
   // Z2g must own its image (dW2 is deferred past the Z1g store); the h2 image is double-buffered when it fits
   // (double-buffering the h2 image -- hb = 2 -- fits at terms = 33 but measured no gain: the chain is not waiting for it)
+  {
+    const char* bs2_env = getenv("NL_B200_BS2");
+    const int bs2 = bs2_env ? atoi(bs2_env) : 1;
+    const int so_cols = g.NP > tc::kH ? g.NP : tc::kH;
+    const tc::Bs2Smem L2 = tc::bs2_smem(g.NP, g.nkc, d->K);
+    b.two = bs2 != 0 && g.nch == 1 && d->D == 1 && 2 * (so_cols + 176) <= 512 && L2.total <= limit;
+    b.smem_two = L2.total;
+  }
   for (int z1 = 1; z1 >= 0; --z1) {  // Z1g in its own image when that fits
     const tc::BsSmem L = tc::bs_smem(g.NP, g.nch, g.nkc, d->n, d->K, true, 1, z1 != 0);
     if (L.total <= limit) {
@@ -1737,6 +2269,15 @@ static cudaError_t launch_tc1(const tc::TcArgs& A, int grid, size_t smem, cudaSt
   if (!BWD && A.stash && !A.h2sep)  // (the stash needs every W3 chunk resident, so this is never the general kernel)
     return launch_tc1_g<false, KP, false, true>(A, grid, smem, st);
   return general ? launch_tc1_g<BWD, KP, true>(A, grid, smem, st) : launch_tc1_g<BWD, KP, false>(A, grid, smem, st);
+}
+
+template <int KP>
+static cudaError_t launch_bs2(const tc::TcArgs& A, int grid, size_t smem, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(tc::fused_tc_bwd_saved2_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem);
+  if (e != cudaSuccess) return e;
+  tc::fused_tc_bwd_saved2_kernel<KP><<<grid, tc::kBsThreads, smem, st>>>(A);
+  return cudaGetLastError();
 }
 
 template <int KP>
@@ -1851,7 +2392,9 @@ cudaError_t launch_fused_tc(const nl_desc* d, bool bwd, const void* p, const voi
       e = cudaMemsetAsync(g1buf, 0, (size_t)d->T * tc::kH * 8 * 4, st);
       if (e != cudaSuccess) return e;
     }
-    if (bg.ok)
+    if (bg.ok && bg.two)
+      e = d->K <= 2 ? launch_bs2<2>(A, pl.grid, bg.smem_two, st) : launch_bs2<tc::kMaxK>(A, pl.grid, bg.smem_two, st);
+    else if (bg.ok)
       e = d->K <= 2 ? launch_bs<2>(A, pl.grid, bg.smem, bg.zsep, bg.h2bufs, bg.z1sep, st)
                     : launch_bs<tc::kMaxK>(A, pl.grid, bg.smem, bg.zsep, bg.h2bufs, bg.z1sep, st);
     else

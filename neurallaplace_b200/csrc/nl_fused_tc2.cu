@@ -645,6 +645,10 @@ static Tc2Geom tc2_geom(const nl_desc* d) {
 TcPlan tc2_plan(const nl_desc* d, int pass) {
   TcPlan pl{};
   const bool bwd = pass != 0;
+  // Forward only.  The backward instantiation below keeps its weight-gradient accumulators in TMEM for the CTA's
+  // whole tile range; the tensor core truncates on accumulation, which biases them by ~2.5e-4 at the headline
+  // size (nl_fused_tc.cu: kFlushTiles).  The one-stream kernels drain theirs periodically; this one is not used.
+  if (bwd) return pl;
   if (d->dtype != NL_F32 || d->H != tc2::kH || d->t_mode != NL_T_SHARED) return pl;
   if (d->family != NL_FOURIER && d->family != NL_AW) return pl;
   if (d->K < 1 || d->K > 7 || d->n < 1 || d->D < 1) return pl;
