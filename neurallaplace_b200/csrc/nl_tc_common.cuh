@@ -214,14 +214,23 @@ struct GemmOp {
   int ksteps;
 };
 
+#ifndef NL_TC_PASS_MODE
+#define NL_TC_PASS_MODE 0
+#endif
 __device__ __forceinline__ void issue_gemm(const GemmOp& g, uint32_t d_tmem, bool accumulate) {
   // descriptors are built once per pass; a K step only bumps the 14-bit start-address field
   const uint64_t a_inc = (uint64_t)(g.a_step >> 4), b_inc = (uint64_t)(g.b_step >> 4);
   uint32_t acc = accumulate ? 1u : 0u;
+  // NL_TC_PASS_MODE (experiments): 0 = hi.hi, hi.lo, lo.hi ; 1 = lo.hi, hi.lo, hi.hi ; 2 = lo.lo, lo.hi, hi.lo, hi.hi
+  constexpr int kPasses = NL_TC_PASS_MODE == 2 ? 4 : 3;
 #pragma unroll 1
-  for (int pass = 0; pass < 3; ++pass) {
-    uint64_t ad = make_sdesc(g.a_hi + (pass == 2 ? g.a_lo_off : 0), g.a_lbo, g.a_sbo);
-    uint64_t bd = make_sdesc(g.b_hi + (pass == 1 ? g.b_lo_off : 0), g.b_lbo, g.b_sbo);
+  for (int pass = 0; pass < kPasses; ++pass) {
+    int a_lo, b_lo;
+    if (NL_TC_PASS_MODE == 0) { a_lo = pass == 2; b_lo = pass == 1; }
+    else if (NL_TC_PASS_MODE == 1) { a_lo = pass == 0; b_lo = pass == 1; }
+    else { a_lo = pass <= 1; b_lo = pass == 0 || pass == 2; }
+    uint64_t ad = make_sdesc(g.a_hi + (a_lo ? g.a_lo_off : 0), g.a_lbo, g.a_sbo);
+    uint64_t bd = make_sdesc(g.b_hi + (b_lo ? g.b_lo_off : 0), g.b_lbo, g.b_sbo);
 #pragma unroll 4
     for (int ks = 0; ks < g.ksteps; ++ks) {
       umma_bf16(d_tmem, ad, bd, g.idesc, acc);
