@@ -79,8 +79,8 @@ constexpr int kMaxB3Smem = 4096;  // floats of packed b3 kept in shared memory
 // CTA's whole tile range (221 tiles x 24 accumulating MMAs at the headline size) picks up a relative bias of
 // ~ #MMAs * 2^-25 = 2.5e-4, measured against the float64 kernels (scripts/dbg_trunc.py) -- above the 1e-4 bar.
 // Every kFlushTiles tiles the accumulators are therefore drained into the CTA's slab with round-to-nearest
-// float adds and restarted (bias <= ~1e-5).
-constexpr int kFlushTiles = 16;
+// float adds (16-byte vector reductions) and restarted: bias <= 32 * 24 * 2^-25 = 2e-5.
+constexpr int kFlushTiles = 32;
 constexpr uint32_t kStashImg = 128 * 64 * 2;
 constexpr size_t kStashTile = 4 * (size_t)kStashImg;
 
@@ -504,7 +504,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
         // result is still deterministic, and no load latency is exposed
         if (add) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) atomicAdd(dst + j, v[j]);
+          for (int j = 0; j < 16; j += 4) red_add4(dst + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j) dst[j] = v[j];
@@ -532,7 +532,8 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
       tmem_ld_wait();
       if (ok)
 #pragma unroll
-        for (int q = 0; q < 16; ++q) atomicAdd(gW2 + j * kH + wg * kColsPerWg + i + q, v[q]);
+        for (int q = 0; q < 16; q += 4)
+          red_add4(gW2 + j * kH + wg * kColsPerWg + i + q, v[q], v[q + 1], v[q + 2], v[q + 3]);
     }
     if (wg == 0) {
       float v[8];
@@ -1088,6 +1089,8 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
   const BsSmem L = bs_smem(NP, nch, A.nkc, n, K, zsep, h2bufs, z1sep);
   const bool h2db = h2bufs == 2;
   const TcTmem TM = tc_tmem(true, NP, nch);
+  // (Tried: A operands of dH2 / dH1 also written to TMEM with tcgen05.st and those GEMMs in TS mode -- 32 instead
+  // of 50 clk per dispatch in isolation, parity green, but 1.712 vs 1.708 ms here: no gain, removed.)
   unsigned char* dO_hi = smem + L.dO;
   unsigned char* dO_lo = dO_hi + L.dO_img;
   unsigned char* Z_hi = smem + L.Z;
@@ -1155,7 +1158,6 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-
   const uint32_t aH1 = smem_u32(H1_hi), aH2_0 = smem_u32(H2_base), aW2 = smem_u32(W2_hi), adO = smem_u32(dO_hi),
                  aZ = smem_u32(Z_hi);
   const uint32_t h2_stride = (uint32_t)(2 * L.H2_img);  // bytes between the two h2 buffers
@@ -1362,14 +1364,14 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
           if (ok) {
             float* dst = gW3 + (long long)row * kH + wg * kColsPerWg + i;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) dst[j] += v[j];
+            for (int j = 0; j < 16; j += 4) red_add4(dst + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
           }
         }
         if (wg == 0) {
           float v[8];
           tmem_ld8(lane_addr + TM.dW3 + 80 * ch + kH, v);
           tmem_ld_wait();
-          if (ok) gb3[row] += v[0];
+          if (ok) atomicAdd(gb3 + row, v[0]);
         }
       }
       tc_fence_before();
@@ -1385,14 +1387,14 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
         if (ok) {
           float* dst = gW2 + j * kH + wg * kColsPerWg + i;
 #pragma unroll
-          for (int q = 0; q < 16; ++q) dst[q] += v[q];
+          for (int q = 0; q < 16; q += 4) red_add4(dst + q, v[q], v[q + 1], v[q + 2], v[q + 3]);
         }
       }
       if (wg == 0) {
         float v[8];
         tmem_ld8(lane_addr + TM.dW2 + kH, v);
         tmem_ld_wait();
-        if (ok) gb2[j] += v[0];
+        if (ok) atomicAdd(gb2 + j, v[0]);
       }
       tc_fence_before();
     };
@@ -1909,7 +1911,8 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcAr
           tmem_ld_wait();
           if (ok)
 #pragma unroll
-            for (int j = 0; j < 16; ++j) atomicAdd(gW3 + (long long)row * kH + wg * kCols + i + j, v[j]);
+            for (int j = 0; j < 16; j += 4)
+              red_add4(gW3 + (long long)row * kH + wg * kCols + i + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
         if (wg == 0) {
           float v[8];
@@ -1926,7 +1929,8 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcAr
         tmem_ld_wait();
         if (ok)
 #pragma unroll
-          for (int q = 0; q < 16; ++q) atomicAdd(gW2 + j * kH + wg * kCols + i + q, v[q]);
+          for (int q = 0; q < 16; q += 4)
+            red_add4(gW2 + j * kH + wg * kCols + i + q, v[q], v[q + 1], v[q + 2], v[q + 3]);
       }
       if (wg == 0) {
         float v[8];
@@ -2237,8 +2241,9 @@ TcPlan tc_plan(const nl_desc* d, int pass) {
   pl.smem = g.smem;
   pl.co_resident = !bwd && g.smem <= (227 * 1024 - 1024) / 2;
   const long long ldw1 = 2 * d->n + d->K;
-  const size_t slab_len = (size_t)d->H * ldw1 + d->H + (size_t)d->H * d->H + d->H + (size_t)2 * d->D * d->n * d->H +
-                          (size_t)2 * d->D * d->n;
+  // (padded to 4 floats: the accumulator drains use 16-byte vector reductions into the slab)
+  const size_t slab_len = ((size_t)d->H * ldw1 + d->H + (size_t)d->H * d->H + d->H + (size_t)2 * d->D * d->n * d->H +
+                           (size_t)2 * d->D * d->n + 3) & ~(size_t)3;
   const size_t pack = tc_align((size_t)g.nch * 2 * tc::image_bytes(g.NP, tc::kH), 256) +
                       tc_align((size_t)g.nch * g.NP * 4, 256);
   // per-time-point tables (S1, coefficients, features) + G1 accumulator of the saved backward
@@ -2378,8 +2383,8 @@ cudaError_t launch_fused_tc(const nl_desc* d, bool bwd, const void* p, const voi
   cudaError_t e;
   if (bwd) {
     const long long ldw1 = 2 * d->n + d->K;
-    A.slab_len = (long long)d->H * ldw1 + d->H + (long long)d->H * d->H + d->H + (long long)2 * d->D * d->n * d->H +
-                 (long long)2 * d->D * d->n;
+    A.slab_len = ((long long)d->H * ldw1 + d->H + (long long)d->H * d->H + d->H + (long long)2 * d->D * d->n * d->H +
+                  (long long)2 * d->D * d->n + 3) & ~3LL;
     A.slab = (float*)w;
     e = cudaMemsetAsync(A.slab, 0, (size_t)A.slab_len * 4 * pl.grid, st);
     if (e != cudaSuccess) return e;

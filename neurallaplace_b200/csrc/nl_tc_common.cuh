@@ -166,6 +166,36 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- TMEM stores (A operand of a TS-mode MMA): lane = 32*(warp%4) + thread-in-warp, N consecutive columns ----
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, uint32_t r0, uint32_t r1) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "r"(r0), "r"(r1) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem]  (A: lane = row, each 32-bit column = two consecutive K elements)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// fire-and-forget vector reduction: 4 consecutive floats (16-byte aligned) with ONE LSU operation per lane
+// (scalar REDs cost ~1.3 clk per lane each: draining a 128 x 80 accumulator with them took 16 k clk)
+__device__ __forceinline__ void red_add4(float* dst, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // ---- bf16 hi/lo split ------------------------------------------------------------------------
 // packs (v0, v1) -> hi = bf16x2(v0 | v1<<16), lo = bf16x2 of the residuals
 __device__ __forceinline__ void split2(float v0, float v1, uint32_t* hi, uint32_t* lo) {
@@ -199,6 +229,20 @@ __device__ __forceinline__ void store_chunk4(unsigned char* img_hi, unsigned cha
   const size_t off = (size_t)(c0 >> 3) * ((size_t)rows_in_image * 16) + (size_t)r * 16 + (size_t)(c0 & 7) * 2;
   *reinterpret_cast<uint2*>(img_hi + off) = make_uint2(h[0], h[1]);
   *reinterpret_cast<uint2*>(img_lo + off) = make_uint2(l[0], l[1]);
+}
+
+// the same in two steps, for callers that also want the packed words (TMEM copy of the operand)
+__device__ __forceinline__ void store_packed4(unsigned char* img_hi, unsigned char* img_lo, int rows_in_image, int r,
+                                              int c0, const uint32_t* h, const uint32_t* l) {
+  const size_t off = (size_t)(c0 >> 3) * ((size_t)rows_in_image * 16) + (size_t)r * 16 + (size_t)(c0 & 7) * 2;
+  *reinterpret_cast<uint2*>(img_hi + off) = make_uint2(h[0], h[1]);
+  *reinterpret_cast<uint2*>(img_lo + off) = make_uint2(l[0], l[1]);
+}
+__device__ __forceinline__ void store_packed8(unsigned char* img_hi, unsigned char* img_lo, int rows_in_image, int r,
+                                              int c0, const uint32_t* h, const uint32_t* l) {
+  const size_t off = (size_t)(c0 >> 3) * ((size_t)rows_in_image * 16) + (size_t)r * 16;
+  *reinterpret_cast<uint4*>(img_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(img_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 // bytes of one operand image (hi or lo) holding [rows][cols] bf16, cols % 8 == 0
@@ -236,6 +280,26 @@ __device__ __forceinline__ void issue_gemm(const GemmOp& g, uint32_t d_tmem, boo
       umma_bf16(d_tmem, ad, bd, g.idesc, acc);
       acc = 1u;
       ad += a_inc;
+      bd += b_inc;
+    }
+  }
+}
+
+// Same three passes with the A operand in TMEM (hi image at a_hi, lo image at a_lo, 8 columns per K step of 16):
+// the dispatch no longer streams 4 KB of A through the shared-memory port (measured 32 instead of 50 clk).
+__device__ __forceinline__ void issue_gemm_ts(const GemmOp& g, uint32_t a_hi, uint32_t a_lo, uint32_t d_tmem,
+                                              bool accumulate) {
+  const uint64_t b_inc = (uint64_t)(g.b_step >> 4);
+  uint32_t acc = accumulate ? 1u : 0u;
+#pragma unroll 1
+  for (int pass = 0; pass < 3; ++pass) {
+    uint32_t at = pass == 2 ? a_lo : a_hi;
+    uint64_t bd = make_sdesc(g.b_hi + (pass == 1 ? g.b_lo_off : 0), g.b_lbo, g.b_sbo);
+#pragma unroll 4
+    for (int ks = 0; ks < g.ksteps; ++ks) {
+      umma_bf16_ts(d_tmem, at, bd, g.idesc, acc);
+      acc = 1u;
+      at += 8;
       bd += b_inc;
     }
   }
