@@ -175,6 +175,14 @@ class ClockSampler(threading.Thread):
             "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def _device_sleep(cycles=int(4e6)):
+  """~2 ms of device-side spinning (private torch helper; skipped if a torch build does not have it)."""
+  try:
+    torch.cuda._sleep(cycles)  # pylint: disable=protected-access
+  except Exception:  # pylint: disable=broad-except
+    pass
+
+
 def run_b200(a):
   import torch.distributed as dist
   from neurallaplace_b200 import _consts, _lib, _ops, laplace_reconstruct, parallel
@@ -240,7 +248,7 @@ def run_b200(a):
   l0 = _ops.launches()
   barrier()
   # keep the host ahead of the device: the timed region must not contain launch latency of the Python layer
-  torch.cuda._sleep(int(4e6))  # pylint: disable=protected-access
+  _device_sleep()
   for s0, s1 in ev:
     flush.zero_()
     s0.record()
@@ -259,7 +267,7 @@ def run_b200(a):
     for q in params:
       q.grad = None
     p_d.grad = None
-    torch.cuda._sleep(int(4e6))  # pylint: disable=protected-access  (host runs ahead: events see kernels only)
+    _device_sleep()  # host runs ahead: the events then see kernels only
     flush.zero_()
     e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     e0.record()
