@@ -127,7 +127,9 @@ static int reconstruct(const nl_desc* d, bool bwd, const void* p, const void* t,
     const nl::TcPlan p1 = nl::tc_plan(d, pass);
     const bool ok1 = p1.ok, ok2 = nl::tc2_plan(d, pass).ok;
     // forward: one-stream kernel when two of its CTAs co-reside on an SM, else the two-stream kernel
-    bool use2 = bwd ? false : !(ok1 && p1.co_resident);
+    // (measured: with every W3 chunk resident the two-stream kernel beats two co-resident one-stream CTAs that
+    // stream W3 through a ring -- d_obs 4 x 33 terms: 2.12 vs 2.39 ms; beyond its shared-memory limit the ring wins)
+    bool use2 = bwd ? false : !(ok1 && p1.co_resident && !(p1.ring && ok2));
     if (force == 1) use2 = false;
     if (force == 2) use2 = true;
     if (use2 && !ok2) use2 = false;

@@ -69,7 +69,7 @@ constexpr int kEwgBwd = 4;  // backward 1 CTA / SM x 512 threads (its shared-mem
 constexpr int kH1Cols = 72;  // h1 image: 64 + [1, p_0..p_6]
 constexpr int kH2Cols = 80;  // h2 image: 64 + [1, 0 x 15]
 constexpr int kMaxK = 7;     // latent dim that fits the extra chunk of the h1 image
-constexpr int kStages = 3;   // W3 ring depth
+constexpr int kStages = 3;   // W3 ring depth (the forward also runs with 2 when that lets two CTAs share an SM)
 constexpr int kMaxB3Smem = 4096;  // floats of packed b3 kept in shared memory
 // Activation stash: the forward pass can save the bf16 hi/lo operand images of h1 and h2 (the first 64
 // columns, 128 rows x 64 x 2 B = 16 KB per image) per tile; the "saved" backward kernel streams them back
@@ -421,12 +421,13 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
 
   // ---- W3 staging: chunk use `g` (g-th chunk this CTA touches) lives in slot g % w3_slots
   // (resident mode: w3_slots == nch, every chunk loaded once; streamed: ring of kStages)
+  const int nst = A.w3_slots;  // ring depth when streamed (2 or kStages)
   long long w3_issued = 0;  // meaningful in the elected lane of warp 0 only (elect.sync is deterministic)
   auto w3_issue_upto = [&](long long upto) {  // thread 0: start the loads of chunk uses < upto
     if (!streamed) return;
     const long long lim = min(upto, total_chunks);
     for (; w3_issued < lim; ++w3_issued) {
-      const int ch = (int)(w3_issued % nch), slot = (int)(w3_issued % kStages);
+      const int ch = (int)(w3_issued % nch), slot = (int)(w3_issued % nst);
       bulk_load(W3_base + (size_t)slot * w3_bytes, A.w3pack + (size_t)ch * w3_bytes, w3_bytes, &bar_w3[slot]);
     }
   };
@@ -440,14 +441,14 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
     }
     __syncthreads();
   } else if (warp == 0 && elect_one()) {
-    w3_issue_upto(kStages);
+    w3_issue_upto(nst);
   }
   auto w3_slot_addr = [&](long long g) {
-    const int slot = streamed ? (int)(g % kStages) : (int)(g % nch);
+    const int slot = streamed ? (int)(g % nst) : (int)(g % nch);
     return smem_u32(W3_base + (size_t)slot * w3_bytes);
   };
   auto w3_wait = [&](long long g) {  // thread 0: chunk use g has landed
-    if (streamed) mbar_wait(&bar_w3[g % kStages], (uint32_t)((g / kStages) & 1));
+    if (streamed) mbar_wait(&bar_w3[g % nst], (uint32_t)((g / nst) & 1));
   };
 
   // bar_main: results the epilogue needs next (Z2, O, dH2, dH1), issued by warp 0.  bar_aux[j]: the
@@ -773,9 +774,9 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
         wait_dw3();  // dW3(ch-1) still reads the dO image
         tc_fence_after();
         if (GENERAL && ch - 1 >= n_resident) dw3_to_slab(ch - 1, TM.dW3 + 80 * n_resident, true);
-        if (warp == 0 && elect_one()) w3_issue_upto(g0 + ch - 1 + kStages + 1);  // the ring slot of chunk ch-1 is free again
+        if (warp == 0 && elect_one()) w3_issue_upto(g0 + ch - 1 + nst + 1);  // the ring slot of chunk ch-1 is free again
       }
-      if (!BWD && warp == 0 && elect_one()) w3_issue_upto(g0 + ch + kStages + 1);  // L3(ch) done -> its ring slot is free
+      if (!BWD && warp == 0 && elect_one()) w3_issue_upto(g0 + ch + nst + 1);  // L3(ch) done -> its ring slot is free
       tc_fence_after();
       NL_PROF(4);
       float g = 0.f;
@@ -882,7 +883,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
       wait_dw3();  // dW3 of the last chunk reads the dO image
       tc_fence_after();
       if (GENERAL && nch - 1 >= n_resident) dw3_to_slab(nch - 1, TM.dW3 + 80 * n_resident, true);
-      if (warp == 0 && elect_one()) w3_issue_upto(g0 + nch - 1 + kStages + 1);
+      if (warp == 0 && elect_one()) w3_issue_upto(g0 + nch - 1 + nst + 1);
 #pragma unroll
       for (int i = 0; i < kColsPerWg; i += 8) store_chunk8(dO_hi, dO_lo, kRows, r, wg * kColsPerWg + i, &z[i]);
       fence_async_smem();
@@ -2151,9 +2152,13 @@ static TcGeom tc_geom(const nl_desc* d, bool bwd, bool stash = false) {
   auto place = [&](bool h2sep) {
     const tc::TcSmem Lr = tc::tc_smem(bwd, g.NP, g.nch, g.nkc, g.nch, d->n, h2sep);
     const tc::TcSmem Ls = tc::tc_smem(bwd, g.NP, g.nch, g.nkc, tc::kStages, d->n, h2sep);
+    const tc::TcSmem L2s = tc::tc_smem(bwd, g.NP, g.nch, g.nkc, 2, d->n, h2sep);
     if (g.nch <= tc::kStages || Lr.total <= (bwd ? limit : half)) {
       g.w3_slots = g.nch;
       g.smem = Lr.total;
+    } else if (!bwd && Ls.total > half && L2s.total <= half) {
+      g.w3_slots = 2;  // forward: a 2-deep ring is enough (a slot is free as soon as its L3 has run) and lets 2 CTAs co-reside
+      g.smem = L2s.total;
     } else {
       g.w3_slots = tc::kStages;
       g.smem = Ls.total;
@@ -2240,6 +2245,7 @@ TcPlan tc_plan(const nl_desc* d, int pass) {
   pl.grid = (int)std::min<long long>(ntiles, (long long)device_sm_count() * (bwd ? 1 : 2));
   pl.smem = g.smem;
   pl.co_resident = !bwd && g.smem <= (227 * 1024 - 1024) / 2;
+  pl.ring = g.w3_slots < g.nch;
   const long long ldw1 = 2 * d->n + d->K;
   // (padded to 4 floats: the accumulator drains use 16-byte vector reductions into the slab)
   const size_t slab_len = ((size_t)d->H * ldw1 + d->H + (size_t)d->H * d->H + d->H + (size_t)2 * d->D * d->n * d->H +

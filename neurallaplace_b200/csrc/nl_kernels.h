@@ -41,6 +41,7 @@ struct TcPlan {
   size_t smem;
   size_t ws_bytes;
   int co_resident;  // forward: two CTAs fit on one SM (shared memory <= half)
+  int ring;         // W3 is streamed through a ring (does not fit resident)
 };
 TcPlan tc_plan(const nl_desc* d, int pass);
 // `saved`: optional activation stash of tc_saved_bytes(d) bytes -- written by the forward pass, consumed by the
