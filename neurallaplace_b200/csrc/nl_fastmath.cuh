@@ -4,7 +4,8 @@
 // fused kernels (~300 transcendentals against ~17 kFLOP of GEMM per point at d_obs=1,
 // 33 terms), so it is written for instruction count while staying ~1e-6 accurate:
 //   tanh(x)    = 1 - 2/(1 + e^{2x})            ex2.approx + rcp.approx    (abs err ~1e-7)
-//   1 -/+ tanh = 2/(1+E), 2E/(1+E)             relatively accurate near the poles of the sphere
+//   1 -/+ tanh = 2/(1+E), 2E/(1+E)             relatively accurate near the poles of the sphere; the two heads
+//                                               of a pair share one rcp: 1/(1+Ea) = (1+Eb) / ((1+Ea)(1+Eb))
 //   sin, cos   of theta = pi*tanh in (-pi, pi)  sin/cos.approx            (abs err 2^-21)
 //   r = tan(phi/2 + pi/4) = cot(w) or tan(w),  w = (pi/4) * min(1 - tau, 1 + tau) in (0, pi/4]
 //                                               degree-9/8 Taylor on the FMA pipe + one rcp.approx:
@@ -63,9 +64,13 @@ __device__ __forceinline__ Head head_forward(int head, float oa, float ob) {
     h.fre = oa; h.fim = ob; h.sn = 0.f; h.cs = 0.f; h.r = 0.f; h.da = 1.f; h.db = 1.f;
     return h;
   }
-  float Ea, Da, Eb, Db;
-  exp_pair(oa, &Ea, &Da);
-  exp_pair(ob, &Eb, &Db);
+  // The two tanh heads share ONE reciprocal: D_a = 1/(1+E_a) = R (1+E_b), D_b = R (1+E_a) with
+  // R = 1/((1+E_a)(1+E_b)) -- the epilogue is MUFU-bound (7 -> 6 MUFU ops per head pair).  E is clamped at 2^60
+  // (tanh is exactly +-1 in float there) so that the product stays finite.
+  const float Ea = ex2a(fminf(oa * kTwoLog2e, 60.f)), Eb = ex2a(fminf(ob * kTwoLog2e, 60.f));
+  const float pa = 1.f + Ea, pb = 1.f + Eb;
+  const float R = rcpa(pa * pb);
+  const float Da = R * pb, Db = R * pa;
   const float ta = fmaf(-2.f, Da, 1.f);
   h.da = (float)(4.0 * kPi) * Ea * Da * Da;
   const float theta = (float)kPi * ta;
