@@ -33,7 +33,9 @@ int check_fused(const nl_desc* d) {
 }
 
 // 1 = SIMT, 2 = tcgen05, 0 = neither covers the shape
-bool tc_any(const nl_desc* d, int pass) { return nl::tc2_plan(d, pass).ok || nl::tc_plan(d, pass).ok; }
+bool tc_any(const nl_desc* d, int pass) {
+  return nl::tc2_plan(d, pass).ok || nl::tc_plan(d, pass).ok || nl::tc_pr_plan(d, pass).ok;
+}
 
 int pick_impl(const nl_desc* d, int pass) {
   if (d->impl == 1) return nl::simt_plan(d, pass).ok ? 1 : 0;
@@ -73,6 +75,8 @@ size_t nl_workspace_bytes(const nl_desc* d, int pass) {
   if (tp.ok) b = tp.ws_bytes;
   nl::TcPlan tp2 = nl::tc2_plan(d, pass);
   if (tp2.ok && tp2.ws_bytes > b) b = tp2.ws_bytes;
+  nl::TcPlan tpr = nl::tc_pr_plan(d, pass);
+  if (tpr.ok && tpr.ws_bytes > b) b = tpr.ws_bytes;
   return (a > b ? a : b) + 256;
 }
 
@@ -119,7 +123,9 @@ static int reconstruct(const nl_desc* d, bool bwd, const void* p, const void* t,
   if (need > 0 && (!ws || ws_bytes < need)) return NL_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
-  if (impl == 2) {
+  if (impl == 2 && d->t_mode == NL_T_PER_ROW) {
+    e = nl::launch_fused_tc_per_row(d, bwd, p, t, weights, beta, eta, x, gx, grads, ws, st, &g_launches, saved);
+  } else if (impl == 2) {
     // Two tensor-core variants exist (nl_fused_tc.cu: one stream per CTA, nl_fused_tc2.cu: two streams + a
     // dedicated MMA-issuer warp).  Measured on B200: backward -> one stream; forward -> one stream at 2 CTAs/SM
     // while W3 is small enough for that, else two streams.  NL_B200_TC_STREAMS=1|2 forces one (profiling).

@@ -28,6 +28,7 @@
 // (deterministic).  A tiny second kernel reduces the slabs over CTAs.  dp uses atomics.
 // The (batch x time x terms x d_obs) complex intermediate only ever exists in registers.
 #include <algorithm>
+#include <cuda_bf16.h>
 #include <cstdlib>
 
 #include "nl_common.cuh"
@@ -107,6 +108,11 @@ struct TcArgs {
   const float* tabU;     // [T][2n]        (theta_s | phi_s) or (Re s | Im s)
   float* g1buf;          // [T][64][8]     saved backward: sum over the batch of Z1g (x) [1 p]
   float* dp_part;        // [ntiles][128][K] saved backward: per-tile dp contributions (summed over t afterwards)
+  // per-row time grids (see point_layer1_kernel): per-point scale of x / grad_x, h1 streamed from the stash,
+  // exported Z1g images
+  const float* row_scale;
+  int h1_from_stash, store_h2;
+  unsigned char* zstash;
   int h2sep;             // forward + stash: h2 has its own image (else it aliases h1 and two more barriers order the bulk stores)
   unsigned char* stash;  // optional [ntiles][h1_hi | h1_lo | h2_hi | h2_lo] operand images (16 KB each), see kStashTile
   long long* prof;  // optional: per-phase clock totals of thread 0 (NL_TC_PROFILE builds)
@@ -222,7 +228,8 @@ __global__ void pack_w3_kernel(const float* __restrict__ W3, const float* __rest
 __global__ void __launch_bounds__(128) time_tables_kernel(IltParams<float> P, const float* __restrict__ t,
                                                            const float* __restrict__ W1, const float* __restrict__ b1,
                                                            int K, int nkc, int kc, int NP, float* __restrict__ tabS1,
-                                                           float* __restrict__ tabCoef, float* __restrict__ tabU) {
+                                                           float* __restrict__ tabCoef, float* __restrict__ tabU,
+                                                           int unit_pref) {
   extern __shared__ float su[];  // [2n]
   const int ti = blockIdx.x, tid = threadIdx.x, n = P.n;
   const TimeCtx<float> c = make_time_ctx<float>(P, __ldg(t + ti), nullptr, 0);
@@ -239,8 +246,9 @@ __global__ void __launch_bounds__(128) time_tables_kernel(IltParams<float> P, co
     const int k = kci * kc + q;
     Cx<float> w{0.f, 0.f};
     if (q < kc && k < n) w = reduce_coef(P, c, k);
-    tabCoef[((size_t)ti * nkc + kci) * NP + 2 * q] = c.pref * w.re;
-    tabCoef[((size_t)ti * nkc + kci) * NP + 2 * q + 1] = c.pref * w.im;
+    const float pf = unit_pref ? 1.f : c.pref;  // per-row time grids: the prefactor is applied per point
+    tabCoef[((size_t)ti * nkc + kci) * NP + 2 * q] = pf * w.re;
+    tabCoef[((size_t)ti * nkc + kci) * NP + 2 * q + 1] = pf * w.im;
   }
   __syncthreads();
   if (tid < kH) {
@@ -332,7 +340,9 @@ __global__ void __launch_bounds__(256) dp_reduce_kernel(const float* __restrict_
 // streaming / scratch-flush code is compiled out of the hot loop); GENERAL = true: any d_obs x terms.
 // ALIAS = true (forward + stash only): h2 shares the h1 image and two extra barriers per tile order the bulk
 // stores of the stash against the rewrites (used when a separate h2 image would cost the 2-CTA co-residency).
-template <bool BWD, int KP, bool GENERAL, bool ALIAS = false>
+// PR = true (forward only): per-row time grids -- h1 is not computed here but streamed from the stash (written by
+// point_layer1_kernel), x is scaled by the per-point prefactor.
+template <bool BWD, int KP, bool GENERAL, bool ALIAS = false, bool PR = false>
 __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 : 2) fused_tc_kernel(TcArgs A) {
   constexpr int kEWG = BWD ? kEwgBwd : kEwgFwd;
   constexpr int kThreadsTc = 128 * kEWG;
@@ -342,6 +352,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
   __shared__ __align__(8) uint64_t bar_main;
   __shared__ __align__(8) uint64_t bar_aux[3];  // weight-gradient GEMMs: 0 = dW3, 1 = dW2, 2 = D1
   __shared__ __align__(8) uint64_t bar_w3[kStages];
+  __shared__ __align__(8) uint64_t bar_h1s;  // PR: streamed h1 image landed
   __shared__ uint32_t tmem_slot;
 
   const IltParams<float> P = A.P;
@@ -410,6 +421,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
     mbar_init(&bar_main, 1);
     for (int j = 0; j < 3; ++j) mbar_init(&bar_aux[j], 1);
     for (int s = 0; s < kStages; ++s) mbar_init(&bar_w3[s], 1);
+    if (PR) mbar_init(&bar_h1s, 1);
     fence_mbar_init();
   }
   fence_async_smem();  // the zero fill / generic stores above precede the async-proxy traffic below
@@ -576,11 +588,13 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
   // software prefetch of the next tile's per-row inputs (p row, upstream gradient) hides their latency
   constexpr int kGPre = 4;
   float pv_n[KP], g_n[kGPre];
+  float rs_n = 1.f;  // PR: prefactor of this row's point
   auto prefetch = [&](int ti, int bi) {
     const int bn = bi * kRows + r;
     const bool ok = bn < A.B;
 #pragma unroll
-    for (int j = 0; j < KP; ++j) pv_n[j] = (ok && j < K) ? __ldg(A.p + (size_t)bn * K + j) : 0.f;
+    for (int j = 0; j < KP; ++j) pv_n[j] = (!PR && ok && j < K) ? __ldg(A.p + (size_t)bn * K + j) : 0.f;
+    if (PR) rs_n = ok ? __ldg(A.row_scale + bn) : 0.f;
     if (BWD) {
 #pragma unroll
       for (int dd = 0; dd < kGPre; ++dd)
@@ -593,6 +607,22 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
   if (tile_lo < tile_hi) prefetch(t_cur, b_cur);
   const int ncols_real = min(NP, (2 * A.kc + 3) & ~3);
   const int cw = (((ncols_real + kEWG - 1) / kEWG) + 3) & ~3;
+  // PR: the h1 image of a tile is streamed in from the stash; the next one is requested as soon as L2 has run
+  auto load_h1_image = [&](long long tl) {  // elected lane of warp 0
+    const unsigned char* src = A.stash + (size_t)tl * kStashTile;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar_h1s)), "r"(2 * kStashImg)
+                 : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(H1_hi)),
+                 "l"(src), "r"(kStashImg), "r"(smem_u32(&bar_h1s))
+                 : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(H1_lo)),
+                 "l"(src + kStashImg), "r"(kStashImg), "r"(smem_u32(&bar_h1s))
+                 : "memory");
+  };
+  uint32_t ph_h1s = 0;
+  if (PR && tile_lo < tile_hi && warp == 0 && elect_one()) load_h1_image(tile_lo);
 
 #ifdef NL_TC_PROFILE
   long long prof_acc[12] = {0}, prof_last = clock64();
@@ -611,6 +641,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
     for (int j = 0; j < KP; ++j) pv[j] = pv_n[j];
 #pragma unroll
     for (int dd = 0; dd < kGPre; ++dd) graw[dd] = BWD ? g_n[dd] : 0.f;
+    const float row_scale = PR ? rs_n : 1.f;
     if (tile + 1 < tile_hi) prefetch(t_cur, b_cur);
 
     // ---- slot context: s points, sphere features, S1 + b1, reduction coefficients
@@ -674,23 +705,29 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
     const float pref = smisc[0];
     NL_PROF(0);
 
-    // ---- 1. h1 = tanh(S1b + W1p.p) -> smem
+    // ---- 1. h1 = tanh(S1b + W1p.p) -> smem   (PR: the image was streamed in)
     float h1[kColsPerWg];
+    if (PR) {
+      mbar_wait(&bar_h1s, ph_h1s);
+      ph_h1s ^= 1;
+    }
 #pragma unroll
     for (int i = 0; i < kColsPerWg; ++i) {
       const int c = wg * kColsPerWg + i;
       float z = sS1b[c];
 #pragma unroll
       for (int j = 0; j < KP; ++j) z = fmaf(sW1p[c * 8 + j], pv[j], z);
-      h1[i] = fast::tanh_fast(z);
+      h1[i] = PR ? 0.f : fast::tanh_fast(z);
     }
     if (BWD) wait_d1();  // the previous tile's D1 GEMM reads the [1 p] chunk of the h1 image (and Z1g in the dO image)
     if (ALIAS) {  // aliased images: the bulk store of the previous tile's h2 must have read them
       if (warp == 0 && elect_one()) bulk_wait_read_all();
       __syncthreads();
     }
+    if (!PR) {
 #pragma unroll
-    for (int i = 0; i < kColsPerWg; i += 8) store_chunk8(H1_hi, H1_lo, kRows, r, wg * kColsPerWg + i, &h1[i]);
+      for (int i = 0; i < kColsPerWg; i += 8) store_chunk8(H1_hi, H1_lo, kRows, r, wg * kColsPerWg + i, &h1[i]);
+    }
     if (BWD && wg == 0) {
       float q[8];
       q[0] = valid ? 1.f : 0.f;
@@ -710,7 +747,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
       tc_fence_after();
       issue_gemm(gL2, tmem + TM.S, false);
       umma_commit(&bar_main);
-      if (!BWD && stash) {
+      if (!BWD && stash && !PR) {
         unsigned char* dst = A.stash + (size_t)tile * kStashTile;
         bulk_store(dst, H1_hi, kStashImg);
         bulk_store(dst + kStashImg, H1_lo, kStashImg);
@@ -720,6 +757,8 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
     mbar_wait(&bar_main, ph_main);
     ph_main ^= 1;
     tc_fence_after();
+    // PR: L2 has read the h1 image -> stream the next tile's in
+    if (PR && tile + 1 < tile_hi && warp == 0 && elect_one()) load_h1_image(tile + 1);
     NL_PROF(2);
 
     // ---- 3. h2 = tanh(Z2 + b2) -> smem
@@ -757,7 +796,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
       tc_fence_after();
       issue_L3(g0);
       umma_commit(&bar_main);
-      if (!BWD && stash) {
+      if (!BWD && stash && (!PR || A.store_h2)) {
         unsigned char* dst = A.stash + (size_t)tile * kStashTile + 2 * kStashImg;
         bulk_store(dst, H2_hi, kStashImg);
         bulk_store(dst + kStashImg, H2_lo, kStashImg);
@@ -827,7 +866,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
             float s = 0.f;
 #pragma unroll
             for (int w = 0; w < kEWG; ++w) s += sxacc[w * kRows + r];
-            A.x[((size_t)b * A.T + t_idx) * D + d] = pref * s;
+            A.x[((size_t)b * A.T + t_idx) * D + d] = pref * row_scale * s;
           }
           __syncthreads();
         }
@@ -2123,6 +2162,164 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcAr
   if (warp == 0) tmem_dealloc(tmem, kTmemCols);
 }
 
+
+// =============================================================================================
+// Per-row time grids (t[B][T]): every (b, t) point has its own s points, so the s part of layer 1 is no longer
+// a per-time-point table.  The N = B*T points are treated as a batch of N rows with ONE (dummy) time index and
+//   point_layer1_kernel    builds, per tile of 128 points, the layer-1 input image A = [theta_s | phi_s | p | 1]
+//                          (bf16 hi/lo, the ONLY place the 2n sphere features of a point are evaluated), runs
+//                          z1 = A.[W1s | W1p | b1]^T on the tensor core and writes the h1 operand image into the
+//                          activation stash; it also keeps A (for dW1), the prefactor of every point and p per point;
+//   fused_tc_kernel<PR>    the forward above with h1 streamed from the stash instead of computed, x scaled per row;
+//   fused_tc_bwd_saved2    unchanged math, upstream gradient scaled per row, Z1g images exported;
+//   point_dw1_kernel       [dW1s | dW1p | db1] = sum over tiles of Z1g^T . A  (streams both images, HBM-bound).
+// The reduction coefficients do not depend on the time point apart from the prefactor (Fourier: exp(i pi k t/T)
+// with T = 2t is i^k; Abate-Whitt: eta_k), so one coefficient table serves every tile.
+constexpr int kPrMaxHalf = 32;  // s points per warpgroup in point_layer1_kernel (n <= 62)
+
+__device__ __forceinline__ void store_elem(unsigned char* img_hi, unsigned char* img_lo, int rows_in_image, int r, int c,
+                                           float v) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+  const size_t off = (size_t)(c >> 3) * ((size_t)rows_in_image * 16) + (size_t)r * 16 + (size_t)(c & 7) * 2;
+  *reinterpret_cast<__nv_bfloat16*>(img_hi + off) = h;
+  *reinterpret_cast<__nv_bfloat16*>(img_lo + off) = l;
+}
+
+struct PrArgs {
+  IltParams<float> P;
+  long long N;      // points = B * T
+  int T, K, n, NPu; // NPu = columns of the A image: 2n + K + 1 rounded up to 16
+  long long ntiles;
+  const float *p, *t, *W1, *b1;
+  unsigned char* stash;   // [ntiles][kStashTile]: the h1 slots are written here
+  unsigned char* ustash;  // [ntiles][A_hi | A_lo]
+  float* row_scale;       // [N] prefactor of every point
+  float* p_pt;            // [N][K] p of the point's batch row
+};
+
+__global__ void __launch_bounds__(256, 2) point_layer1_kernel(PrArgs A) {
+  extern __shared__ __align__(128) unsigned char smem_pr[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const IltParams<float> P = A.P;
+  const int n = A.n, K = A.K, NPu = A.NPu;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int wg = tid >> 7, r = tid & 127;
+  const size_t a_img = image_bytes(kRows, NPu), w_img = image_bytes(kH, NPu), h_img = image_bytes(kRows, kH);
+  unsigned char* A_hi = smem_pr;
+  unsigned char* A_lo = A_hi + a_img;
+  unsigned char* W_hi = A_lo + a_img;
+  unsigned char* W_lo = W_hi + w_img;
+  unsigned char* H_hi = W_lo + w_img;
+  unsigned char* H_lo = H_hi + h_img;
+  const size_t total = 2 * (a_img + w_img + h_img);
+  const int ldw1 = 2 * n + K;
+
+  for (size_t i = tid; i < total / 16; i += 256) reinterpret_cast<uint4*>(smem_pr)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  // B operand: row c = [W1[c][0 .. 2n+K) | b1[c] | 0 ...]
+  for (int idx = tid; idx < kH * (NPu / 8); idx += 256) {
+    const int c = idx / (NPu / 8), c0 = (idx % (NPu / 8)) * 8;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int j = c0 + i;
+      v[i] = j < ldw1 ? __ldg(A.W1 + (size_t)c * ldw1 + j) : (j == ldw1 ? __ldg(A.b1 + c) : 0.f);
+    }
+    store_chunk8(W_hi, W_lo, kH, c, c0, v);
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, 64);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  const GemmOp g1 = make_gemm(smem_u32(A_hi), (uint32_t)a_img, kRows, 0, smem_u32(W_hi), (uint32_t)w_img, kH, 0, 128, kH,
+                              NPu);
+  const int kh = (n + 1) / 2;  // s points per warpgroup
+  uint32_t ph = 0;
+  for (long long tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x) {
+    const long long pt = tile * kRows + r;
+    const bool valid = pt < A.N;
+    const long long b = valid ? pt / A.T : 0;
+    const TimeCtx<float> c = make_time_ctx<float>(P, valid ? __ldg(A.t + pt) : 1.f, nullptr, 0);
+    float f0[kPrMaxHalf], f1[kPrMaxHalf];
+#pragma unroll 1
+    for (int i = 0; i < kh; ++i) {
+      const int k = wg * kh + i;
+      float a = 0.f, bb = 0.f;
+      if (valid && k < n) s_features(P, s_point(P, c, k), &a, &bb);
+      f0[i] = a;
+      f1[i] = bb;
+    }
+    // the previous tile's bulk stores must have read the A / h1 images before they are rewritten
+    if (warp == 0 && elect_one()) bulk_wait_read_all();
+    __syncthreads();
+#pragma unroll 1
+    for (int i = 0; i < kh; ++i) {
+      const int k = wg * kh + i;
+      if (k < n) {
+        store_elem(A_hi, A_lo, kRows, r, k, f0[i]);
+        store_elem(A_hi, A_lo, kRows, r, n + k, f1[i]);
+      }
+    }
+    if (wg == 1) {
+      for (int j = 0; j < K; ++j) {
+        const float pj = valid ? __ldg(A.p + (size_t)b * K + j) : 0.f;
+        store_elem(A_hi, A_lo, kRows, r, 2 * n + j, pj);
+        if (valid) A.p_pt[(size_t)pt * K + j] = pj;
+      }
+      store_elem(A_hi, A_lo, kRows, r, 2 * n + K, valid ? 1.f : 0.f);
+    } else if (valid) {
+      A.row_scale[pt] = c.pref;
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0 && elect_one()) {
+      tc_fence_after();
+      issue_gemm(g1, tmem, false);
+      umma_commit(&bar);
+    }
+    mbar_wait(&bar, ph);
+    ph ^= 1;
+    tc_fence_after();
+    // h1 = tanh(z1) -> operand image (32 columns per thread)
+#pragma unroll
+    for (int i = 0; i < 32; i += 16) {
+      float v[16];
+      tmem_ld16(lane_addr + wg * 32 + i, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = valid ? fast::tanh_fast(v[j]) : 0.f;
+      store_chunk8(H_hi, H_lo, kRows, r, wg * 32 + i, &v[0]);
+      store_chunk8(H_hi, H_lo, kRows, r, wg * 32 + i + 8, &v[8]);
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0 && elect_one()) {
+      unsigned char* dst = A.stash + (size_t)tile * kStashTile;
+      bulk_store(dst, H_hi, kStashImg);
+      bulk_store(dst + kStashImg, H_lo, kStashImg);
+      unsigned char* du = A.ustash + (size_t)tile * 2 * a_img;
+      bulk_store(du, A_hi, (uint32_t)a_img);
+      bulk_store(du + a_img, A_lo, (uint32_t)a_img);
+      bulk_commit();
+    }
+  }
+  if (warp == 0 && elect_one()) bulk_wait_all();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 64);
+}
+
 }  // namespace tc
 
 // ---------------------------------------------------------------------------------------------
@@ -2266,17 +2463,19 @@ TcPlan tc_plan(const nl_desc* d, int pass) {
 cudaError_t launch_reduce_slabs_f32(const float* slab, long long slab_len, int nslabs, void* const* grads,
                                     const nl_desc* d, cudaStream_t st);
 
-template <bool BWD, int KP, bool GENERAL, bool ALIAS = false>
+template <bool BWD, int KP, bool GENERAL, bool ALIAS = false, bool PR = false>
 static cudaError_t launch_tc1_g(const tc::TcArgs& A, int grid, size_t smem, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(tc::fused_tc_kernel<BWD, KP, GENERAL, ALIAS>,
+  cudaError_t e = cudaFuncSetAttribute(tc::fused_tc_kernel<BWD, KP, GENERAL, ALIAS, PR>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  tc::fused_tc_kernel<BWD, KP, GENERAL, ALIAS><<<grid, 128 * (BWD ? tc::kEwgBwd : tc::kEwgFwd), smem, st>>>(A);
+  tc::fused_tc_kernel<BWD, KP, GENERAL, ALIAS, PR><<<grid, 128 * (BWD ? tc::kEwgBwd : tc::kEwgFwd), smem, st>>>(A);
   return cudaGetLastError();
 }
 template <bool BWD, int KP>
 static cudaError_t launch_tc1(const tc::TcArgs& A, int grid, size_t smem, cudaStream_t st) {
   const bool general = A.w3_slots < A.nch || (BWD && A.resident < A.nch);
+  if (!BWD && A.h1_from_stash)  // per-row time grids: h1 streamed from the stash (separate h2 image, resident W3)
+    return launch_tc1_g<false, KP, false, false, true>(A, grid, smem, st);
   if (!BWD && A.stash && !A.h2sep)  // (the stash needs every W3 chunk resident, so this is never the general kernel)
     return launch_tc1_g<false, KP, false, true>(A, grid, smem, st);
   return general ? launch_tc1_g<BWD, KP, true>(A, grid, smem, st) : launch_tc1_g<BWD, KP, false>(A, grid, smem, st);
@@ -2301,9 +2500,29 @@ static cudaError_t launch_bs(const tc::TcArgs& A, int grid, size_t smem, bool zs
   return cudaGetLastError();
 }
 
+// per-row time grids: what launch_fused_tc_per_row hands to the shared-grid launcher (d is its transformed
+// descriptor: B = points, T = 1)
+struct PrExtra {
+  const float* row_scale;
+  unsigned char* zstash;
+  int store_h2;
+};
+
+static cudaError_t launch_fused_tc_impl(const nl_desc* d, bool bwd, const void* p, const void* t,
+                                        const void* const* weights, const void* beta, const void* eta, void* x,
+                                        const void* gx, void* const* grads, void* ws, cudaStream_t st, int* launches,
+                                        void* saved, const PrExtra* pr);
+
 cudaError_t launch_fused_tc(const nl_desc* d, bool bwd, const void* p, const void* t, const void* const* weights,
                             const void* beta, const void* eta, void* x, const void* gx, void* const* grads, void* ws,
                             cudaStream_t st, int* launches, void* saved) {
+  return launch_fused_tc_impl(d, bwd, p, t, weights, beta, eta, x, gx, grads, ws, st, launches, saved, nullptr);
+}
+
+static cudaError_t launch_fused_tc_impl(const nl_desc* d, bool bwd, const void* p, const void* t,
+                                        const void* const* weights, const void* beta, const void* eta, void* x,
+                                        const void* gx, void* const* grads, void* ws, cudaStream_t st, int* launches,
+                                        void* saved, const PrExtra* pr) {
   TcPlan pl = tc_plan(d, bwd ? 1 : 0);
   if (!pl.ok) return cudaErrorInvalidValue;
   TcGeom g = tc_geom(d, bwd, !bwd && saved != nullptr);
@@ -2335,6 +2554,12 @@ cudaError_t launch_fused_tc(const nl_desc* d, bool bwd, const void* p, const voi
   A.x = (float*)x; A.gx = (const float*)gx;
   A.stash = (unsigned char*)saved;
   A.h2sep = g.h2sep;
+  if (pr) {
+    A.row_scale = pr->row_scale;
+    A.zstash = pr->zstash;
+    A.store_h2 = pr->store_h2;
+    A.h1_from_stash = bwd ? 0 : 1;
+  }
 #ifdef NL_TC_PROFILE
   if (!g_prof_buf) {
     cudaMalloc(&g_prof_buf, (2 * 12 + 64) * sizeof(long long));
@@ -2373,7 +2598,7 @@ cudaError_t launch_fused_tc(const nl_desc* d, bool bwd, const void* p, const voi
   }
   if (use_tables && !reuse_aux && d->T > 0) {
     tc::time_tables_kernel<<<d->T, 128, (size_t)2 * d->n * sizeof(float), st>>>(
-        A.P, A.t, A.W1, A.b1, d->K, g.nkc, g.kc, g.NP, tabS1, tabCoef, tabU);
+        A.P, A.t, A.W1, A.b1, d->K, g.nkc, g.kc, g.NP, tabS1, tabCoef, tabU, pr ? 1 : 0);
     cudaError_t e0 = cudaGetLastError();
     if (e0 != cudaSuccess) return e0;
     if (launches) *launches += 1;
@@ -2432,6 +2657,101 @@ cudaError_t launch_fused_tc(const nl_desc* d, bool bwd, const void* p, const voi
     }
   }
   return cudaSuccess;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Per-row time grids on the tensor-core path (see point_layer1_kernel).
+struct PrGeom {
+  bool ok;
+  nl_desc dd;  // transformed descriptor: B = points, T = 1, shared grid
+  long long N, ntiles;
+  int NPu;
+  size_t a_img, stash_bytes, ustash_bytes, scale_bytes, ppt_bytes, std_saved;
+};
+static PrGeom pr_geom(const nl_desc* d) {
+  PrGeom g{};
+  if (d->t_mode != NL_T_PER_ROW || d->dtype != NL_F32 || d->H != tc::kH) return g;
+  if (d->family != NL_FOURIER && d->family != NL_AW) return g;
+  if (d->K < 1 || d->K > tc::kMaxK || d->D != 1 || d->n < 1) return g;
+  const long long N = (long long)d->B * d->T;
+  if (N <= 0 || N >= (1LL << 31) - 256) return g;
+  if (d->impl == 0 && N < 64 * 128) return g;  // tiny problems: SIMT kernels
+  g.NPu = (2 * d->n + d->K + 1 + 15) / 16 * 16;
+  if (g.NPu > 128 || (d->n + 1) / 2 > tc::kPrMaxHalf) return g;
+  g.dd = *d;
+  g.dd.B = (int32_t)N;
+  g.dd.T = 1;
+  g.dd.t_mode = NL_T_SHARED;
+  g.dd.impl = 2;
+  const TcGeom tg = tc_geom(&g.dd, false, true);
+  if (!tg.ok || tg.nch != 1 || !tg.h2sep) return g;  // one resident W3 chunk, separate h2 image
+  if (!tc_plan(&g.dd, 0).ok) return g;
+  g.N = N;
+  g.ntiles = (N + tc::kRows - 1) / tc::kRows;
+  g.a_img = tc::image_bytes(tc::kRows, g.NPu);
+  g.stash_bytes = (size_t)g.ntiles * tc::kStashTile;
+  g.std_saved = g.stash_bytes + tc_aux_bytes(&g.dd, tg) + 256;
+  g.ustash_bytes = (size_t)g.ntiles * 2 * g.a_img;
+  g.scale_bytes = tc_align((size_t)N * 4, 256);
+  g.ppt_bytes = tc_align((size_t)N * d->K * 4, 256);
+  g.ok = true;
+  return g;
+}
+
+// buffer behind the forward: [stash | standard aux | A images | row scale | p per point]
+static size_t pr_buffer_bytes(const PrGeom& g) {
+  return tc_align(g.std_saved, 256) + g.ustash_bytes + g.scale_bytes + g.ppt_bytes + 256;
+}
+
+TcPlan tc_pr_plan(const nl_desc* d, int pass) {
+  TcPlan pl{};
+  const PrGeom g = pr_geom(d);
+  if (!g.ok || pass != 0) return pl;  // (backward: SIMT kernels for now)
+  const TcPlan inner = tc_plan(&g.dd, 0);
+  pl = inner;
+  pl.ws_bytes = inner.ws_bytes + pr_buffer_bytes(g) + 512;
+  pl.ok = 1;
+  return pl;
+}
+
+cudaError_t launch_fused_tc_per_row(const nl_desc* d, bool bwd, const void* p, const void* t,
+                                    const void* const* weights, const void* beta, const void* eta, void* x,
+                                    const void* gx, void* const* grads, void* ws, cudaStream_t st, int* launches,
+                                    void* saved) {
+  (void)gx; (void)grads; (void)saved;
+  const PrGeom g = pr_geom(d);
+  if (!g.ok || bwd) return cudaErrorInvalidValue;
+  unsigned char* buf = (unsigned char*)tc_align((size_t)ws, 256);
+  unsigned char* stash = buf;
+  unsigned char* ustash = buf + tc_align(g.std_saved, 256);
+  float* row_scale = (float*)(ustash + g.ustash_bytes);
+  float* p_pt = (float*)((unsigned char*)row_scale + g.scale_bytes);
+  unsigned char* inner_ws = (unsigned char*)p_pt + g.ppt_bytes;
+  {
+    tc::PrArgs A{};
+    A.P.family = d->family; A.P.n = d->n; A.P.head = d->head;
+    A.P.alpha = (float)d->alpha; A.P.log_tol = (float)d->log_tol; A.P.scale = (float)d->scale;
+    A.P.beta = (const float*)beta; A.P.eta = (const float*)eta;
+    A.N = g.N; A.T = d->T; A.K = d->K; A.n = d->n; A.NPu = g.NPu; A.ntiles = g.ntiles;
+    A.p = (const float*)p; A.t = (const float*)t;
+    A.W1 = (const float*)weights[0]; A.b1 = (const float*)weights[1];
+    A.stash = stash; A.ustash = ustash; A.row_scale = row_scale; A.p_pt = p_pt;
+    const size_t smem = 2 * (g.a_img + tc::image_bytes(tc::kH, g.NPu) + tc::image_bytes(tc::kRows, tc::kH));
+    cudaError_t e = cudaFuncSetAttribute(tc::point_layer1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int grid = (int)std::min<long long>(g.ntiles, (long long)device_sm_count() * 2);
+    tc::point_layer1_kernel<<<grid, 256, smem, st>>>(A);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (launches) *launches += 1;
+  }
+  PrExtra pr{};
+  pr.row_scale = row_scale;
+  pr.zstash = nullptr;
+  pr.store_h2 = 0;
+  return launch_fused_tc_impl(&g.dd, false, p_pt, t, weights, beta, eta, x, nullptr, nullptr, inner_ws, st, launches,
+                              stash, &pr);
 }
 
 }  // namespace nl
