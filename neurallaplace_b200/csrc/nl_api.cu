@@ -88,6 +88,7 @@ int nl_selected_impl(const nl_desc* d, int pass) {
 static size_t saved_bytes(const nl_desc* d) {
   if (check_fused(d)) return 0;
   if (pick_impl(d, 0) != 2 || pick_impl(d, 1) != 2) return 0;
+  if (d->t_mode == NL_T_PER_ROW) return nl::tc_pr_saved_bytes(d);
   return nl::tc_saved_bytes(d);
 }
 
@@ -112,7 +113,9 @@ static int reconstruct(const nl_desc* d, bool bwd, const void* p, const void* t,
     return NL_ERR_NULL;
   }
   const int pass = bwd ? 1 : 0;
-  const int impl = pick_impl(d, pass);
+  int impl = pick_impl(d, pass);
+  // per-row time grids: the tensor-core backward exists only in its saved form (nl_reconstruct_backward_saved)
+  if (impl == 2 && bwd && !saved && d->t_mode == NL_T_PER_ROW && d->impl != 2) impl = nl::simt_plan(d, pass).ok ? 1 : 0;
   if (impl == 0) return NL_ERR_UNSUPPORTED;
   if (saved) {
     const size_t sb = saved_bytes(d);

@@ -52,6 +52,7 @@ cudaError_t launch_fused_tc(const nl_desc* d, bool bwd, const void* p, const voi
 size_t tc_saved_bytes(const nl_desc* d);
 // per-row time grids on the tensor-core path (point_layer1_kernel + the forward with h1 streamed from the stash)
 TcPlan tc_pr_plan(const nl_desc* d, int pass);
+size_t tc_pr_saved_bytes(const nl_desc* d);
 cudaError_t launch_fused_tc_per_row(const nl_desc* d, bool bwd, const void* p, const void* t,
                                     const void* const* weights, const void* beta, const void* eta, void* x,
                                     const void* gx, void* const* grads, void* ws, cudaStream_t st, int* launches,
