@@ -2637,12 +2637,13 @@ struct PrExtra {
   const float* row_scale;
   unsigned char* zstash;
   int store_h2;
+  float* dp_part;  // out: the backward's per-tile dp partials [tile][128][K] == [point][K] (T = 1)
 };
 
 static cudaError_t launch_fused_tc_impl(const nl_desc* d, bool bwd, const void* p, const void* t,
                                         const void* const* weights, const void* beta, const void* eta, void* x,
                                         const void* gx, void* const* grads, void* ws, cudaStream_t st, int* launches,
-                                        void* saved, const PrExtra* pr);
+                                        void* saved, PrExtra* pr);
 
 cudaError_t launch_fused_tc(const nl_desc* d, bool bwd, const void* p, const void* t, const void* const* weights,
                             const void* beta, const void* eta, void* x, const void* gx, void* const* grads, void* ws,
@@ -2653,7 +2654,7 @@ cudaError_t launch_fused_tc(const nl_desc* d, bool bwd, const void* p, const voi
 static cudaError_t launch_fused_tc_impl(const nl_desc* d, bool bwd, const void* p, const void* t,
                                         const void* const* weights, const void* beta, const void* eta, void* x,
                                         const void* gx, void* const* grads, void* ws, cudaStream_t st, int* launches,
-                                        void* saved, const PrExtra* pr) {
+                                        void* saved, PrExtra* pr) {
   TcPlan pl = tc_plan(d, bwd ? 1 : 0);
   if (!pl.ok) return cudaErrorInvalidValue;
   TcGeom g = tc_geom(d, bwd, !bwd && saved != nullptr);
@@ -2751,8 +2752,10 @@ static cudaError_t launch_fused_tc_impl(const nl_desc* d, bool bwd, const void* 
     e = cudaMemsetAsync(A.slab, 0, (size_t)A.slab_len * 4 * pl.grid, st);
     if (e != cudaSuccess) return e;
     A.dp = (float*)grads[6];
-    e = cudaMemsetAsync(A.dp, 0, (size_t)d->B * d->K * 4, st);
-    if (e != cudaSuccess) return e;
+    if (!pr) {  // (per-row time grids: dp is written by dp_sum_t_kernel; here d->B counts points, not rows of dp)
+      e = cudaMemsetAsync(A.dp, 0, (size_t)d->B * d->K * 4, st);
+      if (e != cudaSuccess) return e;
+    }
     if (bg.ok) {
       A.g1buf = g1buf;
       A.dp_part = dp_part;
@@ -2782,7 +2785,8 @@ static cudaError_t launch_fused_tc_impl(const nl_desc* d, bool bwd, const void* 
       if (e != cudaSuccess) return e;
       if (launches) *launches += 1;
     }
-    if (bg.ok && d->T > 0) {
+    if (pr) pr->dp_part = dp_part;  // per-row time grids: one tile per 128 points, summed over time by the caller
+    if (bg.ok && d->T > 0 && !pr) {
       tc::dp_reduce_kernel<<<dim3((unsigned)A.nbt, tc::kDpSlices), 256, 0, st>>>(dp_part, d->B, d->T, d->K, A.nbt, A.dp);
       e = cudaGetLastError();
       if (e != cudaSuccess) return e;
@@ -2847,8 +2851,8 @@ static bool pr_bwd_ok(const PrGeom& g) {
   return bg.ok && bg.two;
 }
 static size_t pr_bwd_extra_bytes(const nl_desc* d, const PrGeom& g) {
-  return (size_t)g.ntiles * 2 * tc::kStashImg + tc_align((size_t)tc::kH * g.NPu * 4, 256) +
-         tc_align((size_t)g.N * d->K * 4, 256) + 512;
+  (void)d;
+  return (size_t)g.ntiles * 2 * tc::kStashImg + tc_align((size_t)tc::kH * g.NPu * 4, 256) + 512;
 }
 
 TcPlan tc_pr_plan(const nl_desc* d, int pass) {
@@ -2916,13 +2920,11 @@ cudaError_t launch_fused_tc_per_row(const nl_desc* d, bool bwd, const void* p, c
   w += (size_t)g.ntiles * 2 * tc::kStashImg;
   float* acc = (float*)w;
   w += tc_align((size_t)tc::kH * g.NPu * 4, 256);
-  float* dp_pt = (float*)w;
-  w += tc_align((size_t)g.N * d->K * 4, 256);
   cudaError_t e = cudaMemsetAsync(acc, 0, (size_t)tc::kH * g.NPu * 4, st);
   if (e != cudaSuccess) return e;
   void* inner_grads[7];
   for (int i = 0; i < 6; ++i) inner_grads[i] = grads[i];
-  inner_grads[6] = dp_pt;
+  inner_grads[6] = grads[6];  // (zeroed by the inner launcher; written by dp_sum_t_kernel below)
   pr.zstash = zstash;
   pr.store_h2 = 0;
   e = launch_fused_tc_impl(&g.dd, true, p_pt, t, weights, beta, eta, nullptr, gx, inner_grads, w, st, launches, stash,
@@ -2941,7 +2943,7 @@ cudaError_t launch_fused_tc_per_row(const nl_desc* d, bool bwd, const void* p, c
     tc::point_dw1_finish_kernel<<<tc::kH, 128, 0, st>>>(acc, g.NPu, 2 * d->n + d->K, (float*)grads[0], (float*)grads[1]);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    tc::dp_sum_t_kernel<<<d->B, 256, 0, st>>>(dp_pt, d->T, d->K, (float*)grads[6]);
+    tc::dp_sum_t_kernel<<<d->B, 256, 0, st>>>(pr.dp_part, d->T, d->K, (float*)grads[6]);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (launches) *launches += 3;
