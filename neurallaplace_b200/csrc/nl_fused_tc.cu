@@ -2187,7 +2187,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcAr
 //   point_dw1_kernel       [dW1s | dW1p | db1] = sum over tiles of Z1g^T . A  (streams both images, HBM-bound).
 // The reduction coefficients do not depend on the time point apart from the prefactor (Fourier: exp(i pi k t/T)
 // with T = 2t is i^k; Abate-Whitt: eta_k), so one coefficient table serves every tile.
-constexpr int kPrMaxHalf = 32;  // s points per warpgroup in point_layer1_kernel (n <= 62)
+constexpr int kPrMaxHalf = 16;  // s points per warpgroup in point_layer1_kernel (n <= 62, 4 warpgroups)
 
 __device__ __forceinline__ void store_elem(unsigned char* img_hi, unsigned char* img_lo, int rows_in_image, int r, int c,
                                            float v) {
@@ -2210,7 +2210,8 @@ struct PrArgs {
   float* p_pt;            // [N][K] p of the point's batch row
 };
 
-__global__ void __launch_bounds__(256, 2) point_layer1_kernel(PrArgs A) {
+constexpr int kPrThreads = 512;  // 4 warpgroups: 2 CTAs x 16 warps per SM hide the latency of the accurate atan2f / asinf
+__global__ void __launch_bounds__(kPrThreads, 2) point_layer1_kernel(PrArgs A) {
   extern __shared__ __align__(128) unsigned char smem_pr[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_slot;
@@ -2228,10 +2229,10 @@ __global__ void __launch_bounds__(256, 2) point_layer1_kernel(PrArgs A) {
   const size_t total = 2 * (a_img + w_img + h_img);
   const int ldw1 = 2 * n + K;
 
-  for (size_t i = tid; i < total / 16; i += 256) reinterpret_cast<uint4*>(smem_pr)[i] = make_uint4(0, 0, 0, 0);
+  for (size_t i = tid; i < total / 16; i += kPrThreads) reinterpret_cast<uint4*>(smem_pr)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
   // B operand: row c = [W1[c][0 .. 2n+K) | b1[c] | 0 ...]
-  for (int idx = tid; idx < kH * (NPu / 8); idx += 256) {
+  for (int idx = tid; idx < kH * (NPu / 8); idx += kPrThreads) {
     const int c = idx / (NPu / 8), c0 = (idx % (NPu / 8)) * 8;
     float v[8];
 #pragma unroll
@@ -2254,7 +2255,7 @@ __global__ void __launch_bounds__(256, 2) point_layer1_kernel(PrArgs A) {
   const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   const GemmOp g1 = make_gemm(smem_u32(A_hi), (uint32_t)a_img, kRows, 0, smem_u32(W_hi), (uint32_t)w_img, kH, 0, 128, kH,
                               NPu);
-  const int kh = (n + 1) / 2;  // s points per warpgroup
+  const int kh = (n + 3) / 4;  // s points per warpgroup
   uint32_t ph = 0;
   for (long long tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x) {
     const long long pt = tile * kRows + r;
@@ -2262,7 +2263,7 @@ __global__ void __launch_bounds__(256, 2) point_layer1_kernel(PrArgs A) {
     const long long b = valid ? pt / A.T : 0;
     const TimeCtx<float> c = make_time_ctx<float>(P, valid ? __ldg(A.t + pt) : 1.f, nullptr, 0);
     float f0[kPrMaxHalf], f1[kPrMaxHalf];
-#pragma unroll 1
+#pragma unroll 4  // (independent evaluations: the accurate atan2f / asinf are long dependent chains)
     for (int i = 0; i < kh; ++i) {
       const int k = wg * kh + i;
       float a = 0.f, bb = 0.f;
@@ -2302,16 +2303,15 @@ __global__ void __launch_bounds__(256, 2) point_layer1_kernel(PrArgs A) {
     mbar_wait(&bar, ph);
     ph ^= 1;
     tc_fence_after();
-    // h1 = tanh(z1) -> operand image (32 columns per thread)
-#pragma unroll
-    for (int i = 0; i < 32; i += 16) {
+    // h1 = tanh(z1) -> operand image (16 columns per thread)
+    {
       float v[16];
-      tmem_ld16(lane_addr + wg * 32 + i, v);
+      tmem_ld16(lane_addr + wg * 16, v);
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = valid ? fast::tanh_fast(v[j]) : 0.f;
-      store_chunk8(H_hi, H_lo, kRows, r, wg * 32 + i, &v[0]);
-      store_chunk8(H_hi, H_lo, kRows, r, wg * 32 + i + 8, &v[8]);
+      store_chunk8(H_hi, H_lo, kRows, r, wg * 16, &v[0]);
+      store_chunk8(H_hi, H_lo, kRows, r, wg * 16 + 8, &v[8]);
     }
     fence_async_smem();
     tc_fence_before();
@@ -2818,7 +2818,7 @@ static PrGeom pr_geom(const nl_desc* d) {
   if (N <= 0 || N >= (1LL << 31) - 256) return g;
   if (d->impl == 0 && N < 64 * 128) return g;  // tiny problems: SIMT kernels
   g.NPu = (2 * d->n + d->K + 1 + 15) / 16 * 16;
-  if (g.NPu > 128 || (d->n + 1) / 2 > tc::kPrMaxHalf) return g;
+  if (g.NPu > 128 || (d->n + 3) / 4 > tc::kPrMaxHalf) return g;
   g.dd = *d;
   g.dd.B = (int32_t)N;
   g.dd.T = 1;
@@ -2905,7 +2905,7 @@ cudaError_t launch_fused_tc_per_row(const nl_desc* d, bool bwd, const void* p, c
     cudaError_t e = cudaFuncSetAttribute(tc::point_layer1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int grid = (int)std::min<long long>(g.ntiles, (long long)device_sm_count() * 2);
-    tc::point_layer1_kernel<<<grid, 256, smem, st>>>(A);
+    tc::point_layer1_kernel<<<grid, tc::kPrThreads, smem, st>>>(A);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (launches) *launches += 1;
