@@ -115,7 +115,8 @@ static int reconstruct(const nl_desc* d, bool bwd, const void* p, const void* t,
   const int pass = bwd ? 1 : 0;
   int impl = pick_impl(d, pass);
   // per-row time grids: the tensor-core backward exists only in its saved form (nl_reconstruct_backward_saved)
-  if (impl == 2 && bwd && !saved && d->t_mode == NL_T_PER_ROW && d->impl != 2) impl = nl::simt_plan(d, pass).ok ? 1 : 0;
+  if (impl == 2 && bwd && !saved && d->t_mode == NL_T_PER_ROW)
+    impl = (d->impl != 2 && nl::simt_plan(d, pass).ok) ? 1 : 0;
   if (impl == 0) return NL_ERR_UNSUPPORTED;
   if (saved) {
     const size_t sb = saved_bytes(d);

@@ -1462,9 +1462,11 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
 
     constexpr int kGPre = 4;
     float pv_n[KP], g_n[kGPre];
+    float rs_n = 1.f;  // per-row time grids: prefactor of this row's point
     auto prefetch = [&](int ti, int bi) {
       const int bn = bi * kRows + r;
       const bool ok = bn < A.B;
+      if (A.row_scale) rs_n = ok ? __ldg(A.row_scale + bn) : 0.f;
 #pragma unroll
       for (int j = 0; j < KP; ++j) pv_n[j] = (ok && j < K) ? __ldg(A.p + (size_t)bn * K + j) : 0.f;
 #pragma unroll
@@ -1494,6 +1496,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
       for (int j = 0; j < KP; ++j) pv[j] = pv_n[j];
 #pragma unroll
       for (int dd = 0; dd < kGPre; ++dd) graw[dd] = g_n[dd];
+      const float rs = rs_n;
       if (tile + 1 < tile_hi) prefetch(t_cur, b_cur);
       const int hb = h2db ? (int)((tile - tile_lo) & 1) : 0;
       const unsigned char* H2_hi = H2_base + (size_t)hb * 2 * L.H2_img;
@@ -1513,6 +1516,10 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
       if (tid == 0) NL_TRACE(0);
 
       ++slot_tiles;
+      if (A.zstash) {  // per-row time grids: the bulk store that exported the previous Z1g image must have read it
+        if (warp == 0 && elect_one()) bulk_wait_read_all();
+        ep_sync();
+      }
       // bounded accumulation chains: dW3 of the previous tile has executed (waited for in its stage 4)
       const bool drain = tile > tile_lo && (tile - tile_lo) % kFlushTiles == 0;
       if (drain) drain_dw3();
@@ -1547,7 +1554,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
         } else if (valid) {
           gr = __ldg(A.gx + ((size_t)b * A.T + t_idx) * D + d);
         }
-        const float g = gr;
+        const float g = gr * rs;
         const float* cf = sCoef + kci * NP;
         const float* bb3 = sb3 + ch * NP;
         for (int c0 = wg * cw; c0 < min((wg + 1) * cw, ncols_real); c0 += 4) {
@@ -1655,6 +1662,12 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
       tc_fence_before();
       ep_sync();
       if (tid == 0) mbar_arrive(&rdy_z1);
+      if (A.zstash && warp == 0 && elect_one()) {  // per-row time grids: Z1g image -> HBM (point_dw1_kernel)
+        unsigned char* dst = A.zstash + (size_t)tile * 2 * kStashImg;
+        bulk_store(dst, Z1_hi, kStashImg);
+        bulk_store(dst + kStashImg, Z1_lo, kStashImg);
+        bulk_commit();
+      }
       if (wg == 0) {
         float* dst = A.dp_part + ((size_t)tile * kRows + r) * K;
         for (int q = 0; q < K; ++q) {
@@ -1674,6 +1687,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
       for (int i = 0; i < 12; ++i) atomicAdd((unsigned long long*)A.prof + i, (unsigned long long)prof_acc[i]);
 #endif
 
+    if (A.zstash && warp == 0 && elect_one()) bulk_wait_all();
     // ---- what is left in the TMEM-resident weight-gradient accumulators -> this CTA's slab
     flush_slot();
     wait_dw2();
@@ -2512,6 +2526,17 @@ static size_t tc_aux_bytes(const nl_desc* d, const TcGeom& g) {
          tc_align((size_t)d->T * 2 * d->n * 4, 256);
 }
 
+// forward with h1 streamed from the stash (per-row time grids): every W3 chunk resident and h2 in its own image,
+// whether or not two CTAs then share an SM
+static TcGeom tc_geom_pr_fwd(const nl_desc* d) {
+  TcGeom g = tc_geom(d, false, true);
+  g.h2sep = 1;
+  g.w3_slots = g.nch;
+  g.smem = tc::tc_smem(false, g.NP, g.nch, g.nkc, g.nch, d->n, true).total;
+  g.ok = g.smem <= (size_t)227 * 1024 - 1024;
+  return g;
+}
+
 // geometry of the "saved" backward (activation stash): everything resident
 struct BsGeom {
   bool ok, zsep, z1sep;
@@ -2657,7 +2682,7 @@ static cudaError_t launch_fused_tc_impl(const nl_desc* d, bool bwd, const void* 
                                         void* saved, PrExtra* pr) {
   TcPlan pl = tc_plan(d, bwd ? 1 : 0);
   if (!pl.ok) return cudaErrorInvalidValue;
-  TcGeom g = tc_geom(d, bwd, !bwd && saved != nullptr);
+  TcGeom g = (pr && !bwd) ? tc_geom_pr_fwd(d) : tc_geom(d, bwd, !bwd && saved != nullptr);
   if (!bwd && saved && !g.ok) {  // no room for the separate h2 image: run without the stash (never happens at H = 64)
     return cudaErrorInvalidValue;
   }
@@ -2810,7 +2835,7 @@ static PrGeom pr_geom(const nl_desc* d) {
   PrGeom g{};
   if (d->t_mode != NL_T_PER_ROW || d->dtype != NL_F32 || d->H != tc::kH) return g;
   if (d->family != NL_FOURIER && d->family != NL_AW) return g;
-  if (d->K < 1 || d->K > tc::kMaxK || d->D != 1 || d->n < 1) return g;
+  if (d->K < 1 || d->K > tc::kMaxK || d->D < 1 || d->n < 1) return g;
   // sphere features only: they are bounded by pi, so the bf16 hi/lo operand images of layer 1 and of the dW1 GEMM
   // keep 1e-5; the raw (Re s, Im s) features of use_sphere_projection=False reach 500 and measured 3e-4 on dW1
   if (d->head != NL_HEAD_SPHERE) return g;
@@ -2824,8 +2849,8 @@ static PrGeom pr_geom(const nl_desc* d) {
   g.dd.T = 1;
   g.dd.t_mode = NL_T_SHARED;
   g.dd.impl = 2;
-  const TcGeom tg = tc_geom(&g.dd, false, true);
-  if (!tg.ok || tg.nch != 1 || !tg.h2sep) return g;  // one resident W3 chunk, separate h2 image
+  const TcGeom tg = tc_geom_pr_fwd(&g.dd);
+  if (!tg.ok) return g;
   if (!tc_plan(&g.dd, 0).ok) return g;
   g.N = N;
   g.ntiles = (N + tc::kRows - 1) / tc::kRows;
@@ -2848,7 +2873,7 @@ static size_t pr_buffer_bytes(const PrGeom& g) {
 static bool pr_bwd_ok(const PrGeom& g) {
   if (!g.ok || !tc_plan(&g.dd, 1).ok) return false;
   const BsGeom bg = bs_geom(&g.dd, tc_geom(&g.dd, true));
-  return bg.ok && bg.two;
+  return bg.ok;  // (either saved backward: both take the per-row scale and export Z1g)
 }
 static size_t pr_bwd_extra_bytes(const nl_desc* d, const PrGeom& g) {
   (void)d;
