@@ -361,8 +361,11 @@ def run_b200(a):
                      "streaming": {"activation_stash_bytes": stash, "fwd_gbs": hbm_fwd, "bwd_gbs": hbm_bwd,
                                    "peak_gbs": peak_hbm, "fwd_frac": hbm_fwd / peak_hbm,
                                    "bwd_frac": hbm_bwd / peak_hbm},
-                     "note": "co-limited by the CUDA-core epilogue (MUFU / issue slots) and shared-memory bandwidth of "
-                             "the SS-mode MMAs, see DESIGN.md section 6 and profiles/"},
+                     "note": ("De Hoog: the step is dominated by the per-thread quotient-difference recurrence "
+                              "(dehoog_qd kernels: CUDA cores, IEEE divisions, 8 warps/SM), the tensor-core MLP "
+                              "kernels take ~3 ms of it; see DESIGN.md section 4.9") if a.alg == "dehoog" else
+                             ("co-limited by the CUDA-core epilogue (MUFU / issue slots) and shared-memory bandwidth "
+                              "of the SS-mode MMAs, see DESIGN.md section 6 and profiles/")},
     }
     if not a.no_cpu_baseline and world == 1:  # reported on rank 0 at N=1 only
       rate, ms, cores, sample = cpu_step_rate(a, 2, 1, a.cpu_sample_batch)

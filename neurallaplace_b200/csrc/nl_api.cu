@@ -34,7 +34,8 @@ int check_fused(const nl_desc* d) {
 
 // 1 = SIMT, 2 = tcgen05, 0 = neither covers the shape
 bool tc_any(const nl_desc* d, int pass) {
-  return nl::tc2_plan(d, pass).ok || nl::tc_plan(d, pass).ok || nl::tc_pr_plan(d, pass).ok;
+  return nl::tc2_plan(d, pass).ok || nl::tc_plan(d, pass).ok || nl::tc_pr_plan(d, pass).ok ||
+         nl::tc_dh_plan(d, pass).ok;
 }
 
 int pick_impl(const nl_desc* d, int pass) {
@@ -77,6 +78,8 @@ size_t nl_workspace_bytes(const nl_desc* d, int pass) {
   if (tp2.ok && tp2.ws_bytes > b) b = tp2.ws_bytes;
   nl::TcPlan tpr = nl::tc_pr_plan(d, pass);
   if (tpr.ok && tpr.ws_bytes > b) b = tpr.ws_bytes;
+  nl::TcPlan tdh = nl::tc_dh_plan(d, pass);
+  if (tdh.ok && tdh.ws_bytes > b) b = tdh.ws_bytes;
   return (a > b ? a : b) + 256;
 }
 
@@ -89,6 +92,7 @@ static size_t saved_bytes(const nl_desc* d) {
   if (check_fused(d)) return 0;
   if (pick_impl(d, 0) != 2 || pick_impl(d, 1) != 2) return 0;
   if (d->t_mode == NL_T_PER_ROW) return nl::tc_pr_saved_bytes(d);
+  if (d->family == NL_DEHOOG) return nl::tc_dh_saved_bytes(d);
   return nl::tc_saved_bytes(d);
 }
 
@@ -114,8 +118,9 @@ static int reconstruct(const nl_desc* d, bool bwd, const void* p, const void* t,
   }
   const int pass = bwd ? 1 : 0;
   int impl = pick_impl(d, pass);
-  // per-row time grids: the tensor-core backward exists only in its saved form (nl_reconstruct_backward_saved)
-  if (impl == 2 && bwd && !saved && d->t_mode == NL_T_PER_ROW)
+  // per-row time grids / De Hoog: the tensor-core backward exists only in its saved form
+  // (nl_reconstruct_backward_saved)
+  if (impl == 2 && bwd && !saved && (d->t_mode == NL_T_PER_ROW || d->family == NL_DEHOOG))
     impl = (d->impl != 2 && nl::simt_plan(d, pass).ok) ? 1 : 0;
   if (impl == 0) return NL_ERR_UNSUPPORTED;
   if (saved) {
@@ -129,6 +134,8 @@ static int reconstruct(const nl_desc* d, bool bwd, const void* p, const void* t,
   cudaError_t e;
   if (impl == 2 && d->t_mode == NL_T_PER_ROW) {
     e = nl::launch_fused_tc_per_row(d, bwd, p, t, weights, beta, eta, x, gx, grads, ws, st, &g_launches, saved);
+  } else if (impl == 2 && d->family == NL_DEHOOG) {
+    e = nl::launch_fused_tc_dehoog(d, bwd, p, t, weights, x, gx, grads, ws, st, &g_launches, saved);
   } else if (impl == 2) {
     // Two tensor-core variants exist (nl_fused_tc.cu: one stream per CTA, nl_fused_tc2.cu: two streams + a
     // dedicated MMA-issuer warp).  Measured on B200: backward -> one stream; forward -> one stream at 2 CTAs/SM

@@ -42,15 +42,16 @@ NL_HD Cx<R> cscale(Cx<R> a, R s) {
 // Smith's algorithm: robust against overflow of |b|^2 (DeHoog tables span many decades).
 template <typename R>
 NL_HD Cx<R> cdiv(Cx<R> a, Cx<R> b) {
-  if (fabs(b.re) >= fabs(b.im)) {
-    R rat = b.im / b.re;
-    R den = R(1) / (b.re + b.im * rat);
-    return {(a.re + a.im * rat) * den, (a.im - a.re * rat) * den};
-  } else {
-    R rat = b.re / b.im;
-    R den = R(1) / (b.re * rat + b.im);
-    return {(a.re * rat + a.im) * den, (a.im * rat - a.re) * den};
-  }
+  // branch-free (selects, two real divisions): with p the larger and s the smaller component of b,
+  //   |b.re| >= |b.im|: ((a.re + a.im rat) den, (a.im - a.re rat) den),  rat = b.im/b.re, den = 1/(b.re + b.im rat)
+  //   else            : ((a.re rat + a.im) den, (a.im rat - a.re) den),  rat = b.re/b.im, den = 1/(b.re rat + b.im)
+  const bool big = fabs(b.re) >= fabs(b.im);
+  const R p = big ? b.re : b.im, s = big ? b.im : b.re;
+  const R u = big ? a.re : a.im, v = big ? a.im : a.re;
+  const R rat = s / p;
+  const R den = R(1) / (p + s * rat);
+  const R x = v - u * rat;
+  return {(u + v * rat) * den, (big ? x : -x) * den};
 }
 template <typename R>
 NL_HD Cx<R> crecip(Cx<R> b) {

@@ -114,6 +114,12 @@ struct TcArgs {
   int h1_from_stash, store_h2;
   unsigned char* zstash;
   int h2sep;             // forward + stash: h2 has its own image (else it aliases h1 and two more barriers order the bulk stores)
+  // De Hoog (DH instantiations): the forward writes F = head(layer 3) instead of reducing it, the saved backward
+  // reads dL/dF instead of forming it from grad_x and the reduction coefficients; both [d][k][t][b] float2
+  // (the quotient-difference recurrence runs in between, nl_dehoog_qd.cu)
+  float2* fout;
+  const float2* dfin;
+  long long f_plane;     // T * B
   unsigned char* stash;  // optional [ntiles][h1_hi | h1_lo | h2_hi | h2_lo] operand images (16 KB each), see kStashTile
   long long* prof;  // optional: per-phase clock totals of thread 0 (NL_TC_PROFILE builds)
 };
@@ -342,7 +348,7 @@ __global__ void __launch_bounds__(256) dp_reduce_kernel(const float* __restrict_
 // stores of the stash against the rewrites (used when a separate h2 image would cost the 2-CTA co-residency).
 // PR = true (forward only): per-row time grids -- h1 is not computed here but streamed from the stash (written by
 // point_layer1_kernel), x is scaled by the per-point prefactor.
-template <bool BWD, int KP, bool GENERAL, bool ALIAS = false, bool PR = false>
+template <bool BWD, int KP, bool GENERAL, bool ALIAS = false, bool PR = false, bool DH = false>
 __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 : 2) fused_tc_kernel(TcArgs A) {
   constexpr int kEWG = BWD ? kEwgBwd : kEwgFwd;
   constexpr int kThreadsTc = 128 * kEWG;
@@ -842,7 +848,11 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
           const int c = c0 + 2 * i;
           const fast::Head h = fast::head_forward(P.head, v[2 * i] + bb3[c], v[2 * i + 1] + bb3[c + 1]);
           const float cr = cf[c], ci = cf[c + 1];
-          if (!BWD) {
+          if (!BWD && DH) {
+            const int kk = c >> 1, k = kci * A.kc + kk;
+            if (valid && kk < A.kc && k < n)
+              A.fout[(size_t)(d * n + k) * A.f_plane + ((size_t)t_idx * A.B + b)] = make_float2(h.fre, h.fim);
+          } else if (!BWD) {
             xsum = fmaf(h.fre, cr, xsum);
             xsum = fmaf(-h.fim, ci, xsum);
           } else {
@@ -862,7 +872,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
           umma_commit(&bar_main);
         }
         if (d_last) {
-          if (wg == 0 && valid) {
+          if (!DH && wg == 0 && valid) {
             float s = 0.f;
 #pragma unroll
             for (int w = 0; w < kEWG; ++w) s += sxacc[w * kRows + r];
@@ -1102,7 +1112,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 // of the stashed h1 / h2 images.  A tcgen05.mma dispatch blocks its issuing thread for ~50 clk (24 per
 // weight-gradient GEMM), so no epilogue warp ever issues one.  640 threads cap the kernel at 96 registers per
 // thread; the epilogue (16 columns per thread, h1 / h2 re-read from shared memory) needs 86.
-template <int KP>
+template <int KP, bool DH = false>
 __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArgs A, int zsep_i, int h2bufs, int z1sep_i) {
   constexpr int kEWG = kEwgBwd;
   constexpr int kEpi = 128 * kEWG;
@@ -1565,7 +1575,19 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
           for (int i = 0; i < 2; ++i) {
             const int c = c0 + 2 * i;
             const fast::Head h = fast::head_forward(P.head, v[2 * i] + bb3[c], v[2 * i + 1] + bb3[c + 1]);
-            fast::head_backward(P.head, h, g * cf[c], -g * cf[c + 1], &dv[2 * i], &dv[2 * i + 1]);
+            float gre, gim;
+            if (DH) {
+              const int kk = c >> 1, k = kci * A.kc + kk;
+              float2 df = make_float2(0.f, 0.f);
+              if (valid && kk < A.kc && k < A.n)
+                df = __ldg(A.dfin + (size_t)(d * A.n + k) * A.f_plane + ((size_t)t_idx * A.B + b));
+              gre = df.x;
+              gim = df.y;
+            } else {
+              gre = g * cf[c];
+              gim = -g * cf[c + 1];
+            }
+            fast::head_backward(P.head, h, gre, gim, &dv[2 * i], &dv[2 * i + 1]);
           }
           store_chunk4(dO_hi, dO_lo, kRows, r, c0, dv);
         }
@@ -1740,7 +1762,7 @@ __host__ __device__ inline Bs2Smem bs2_smem(int NP, int nkc, int K) {
   return L;
 }
 
-template <int KP>
+template <int KP, bool DH = false>
 __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcArgs A) {
   constexpr int kStreamThreads = 256;
   constexpr int kCols = 32;  // hidden columns per thread (two warpgroups per stream)
@@ -2082,7 +2104,18 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcAr
         for (int i = 0; i < 2; ++i) {
           const int c = c0 + 2 * i;
           const fast::Head h = fast::head_forward(A.P.head, v[2 * i] + sb3[c], v[2 * i + 1] + sb3[c + 1]);
-          fast::head_backward(A.P.head, h, g * sCoef[c], -g * sCoef[c + 1], &dv[2 * i], &dv[2 * i + 1]);
+          float gre, gim;
+          if (DH) {
+            const int k = c >> 1;
+            float2 df = make_float2(0.f, 0.f);
+            if (valid && k < A.n) df = __ldg(A.dfin + (size_t)k * A.f_plane + ((size_t)t_idx * A.B + b));
+            gre = df.x;
+            gim = df.y;
+          } else {
+            gre = g * sCoef[c];
+            gim = -g * sCoef[c + 1];
+          }
+          fast::head_backward(A.P.head, h, gre, gim, &dv[2 * i], &dv[2 * i + 1]);
         }
         store_chunk4(X_hi, X_lo, kRows, r, c0, dv);
       }
@@ -2619,17 +2652,22 @@ TcPlan tc_plan(const nl_desc* d, int pass) {
 cudaError_t launch_reduce_slabs_f32(const float* slab, long long slab_len, int nslabs, void* const* grads,
                                     const nl_desc* d, cudaStream_t st);
 
-template <bool BWD, int KP, bool GENERAL, bool ALIAS = false, bool PR = false>
+template <bool BWD, int KP, bool GENERAL, bool ALIAS = false, bool PR = false, bool DH = false>
 static cudaError_t launch_tc1_g(const tc::TcArgs& A, int grid, size_t smem, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(tc::fused_tc_kernel<BWD, KP, GENERAL, ALIAS, PR>,
+  cudaError_t e = cudaFuncSetAttribute(tc::fused_tc_kernel<BWD, KP, GENERAL, ALIAS, PR, DH>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  tc::fused_tc_kernel<BWD, KP, GENERAL, ALIAS, PR><<<grid, 128 * (BWD ? tc::kEwgBwd : tc::kEwgFwd), smem, st>>>(A);
+  tc::fused_tc_kernel<BWD, KP, GENERAL, ALIAS, PR, DH><<<grid, 128 * (BWD ? tc::kEwgBwd : tc::kEwgFwd), smem, st>>>(A);
   return cudaGetLastError();
 }
 template <bool BWD, int KP>
 static cudaError_t launch_tc1(const tc::TcArgs& A, int grid, size_t smem, cudaStream_t st) {
   const bool general = A.w3_slots < A.nch || (BWD && A.resident < A.nch);
+  if (!BWD && A.fout) {  // De Hoog: F is written out instead of reduced
+    if (A.stash && !A.h2sep) return launch_tc1_g<false, KP, false, true, false, true>(A, grid, smem, st);
+    return general ? launch_tc1_g<false, KP, true, false, false, true>(A, grid, smem, st)
+                   : launch_tc1_g<false, KP, false, false, false, true>(A, grid, smem, st);
+  }
   if (!BWD && A.h1_from_stash)  // per-row time grids: h1 streamed from the stash (separate h2 image, resident W3)
     return launch_tc1_g<false, KP, false, false, true>(A, grid, smem, st);
   if (!BWD && A.stash && !A.h2sep)  // (the stash needs every W3 chunk resident, so this is never the general kernel)
@@ -2639,6 +2677,13 @@ static cudaError_t launch_tc1(const tc::TcArgs& A, int grid, size_t smem, cudaSt
 
 template <int KP>
 static cudaError_t launch_bs2(const tc::TcArgs& A, int grid, size_t smem, cudaStream_t st) {
+  if (A.dfin) {
+    cudaError_t e = cudaFuncSetAttribute(tc::fused_tc_bwd_saved2_kernel<KP, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    tc::fused_tc_bwd_saved2_kernel<KP, true><<<grid, tc::kBsThreads, smem, st>>>(A);
+    return cudaGetLastError();
+  }
   cudaError_t e = cudaFuncSetAttribute(tc::fused_tc_bwd_saved2_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem);
   if (e != cudaSuccess) return e;
@@ -2649,6 +2694,13 @@ static cudaError_t launch_bs2(const tc::TcArgs& A, int grid, size_t smem, cudaSt
 template <int KP>
 static cudaError_t launch_bs(const tc::TcArgs& A, int grid, size_t smem, bool zsep, int h2bufs, bool z1sep,
                              cudaStream_t st) {
+  if (A.dfin) {
+    cudaError_t e = cudaFuncSetAttribute(tc::fused_tc_bwd_saved_kernel<KP, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    tc::fused_tc_bwd_saved_kernel<KP, true><<<grid, tc::kBsThreads, smem, st>>>(A, zsep ? 1 : 0, h2bufs, z1sep ? 1 : 0);
+    return cudaGetLastError();
+  }
   cudaError_t e = cudaFuncSetAttribute(tc::fused_tc_bwd_saved_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem);
   if (e != cudaSuccess) return e;
@@ -2664,11 +2716,16 @@ struct PrExtra {
   int store_h2;
   float* dp_part;  // out: the backward's per-tile dp partials [tile][128][K] == [point][K] (T = 1)
 };
+// De Hoog: F out of the forward / dL/dF into the saved backward, [d][k][t][b] complex (launch_fused_tc_dehoog)
+struct DhExtra {
+  float2* fout;
+  const float2* dfin;
+};
 
 static cudaError_t launch_fused_tc_impl(const nl_desc* d, bool bwd, const void* p, const void* t,
                                         const void* const* weights, const void* beta, const void* eta, void* x,
                                         const void* gx, void* const* grads, void* ws, cudaStream_t st, int* launches,
-                                        void* saved, PrExtra* pr);
+                                        void* saved, PrExtra* pr, DhExtra* dh = nullptr);
 
 cudaError_t launch_fused_tc(const nl_desc* d, bool bwd, const void* p, const void* t, const void* const* weights,
                             const void* beta, const void* eta, void* x, const void* gx, void* const* grads, void* ws,
@@ -2679,7 +2736,7 @@ cudaError_t launch_fused_tc(const nl_desc* d, bool bwd, const void* p, const voi
 static cudaError_t launch_fused_tc_impl(const nl_desc* d, bool bwd, const void* p, const void* t,
                                         const void* const* weights, const void* beta, const void* eta, void* x,
                                         const void* gx, void* const* grads, void* ws, cudaStream_t st, int* launches,
-                                        void* saved, PrExtra* pr) {
+                                        void* saved, PrExtra* pr, DhExtra* dh) {
   TcPlan pl = tc_plan(d, bwd ? 1 : 0);
   if (!pl.ok) return cudaErrorInvalidValue;
   TcGeom g = (pr && !bwd) ? tc_geom_pr_fwd(d) : tc_geom(d, bwd, !bwd && saved != nullptr);
@@ -2711,6 +2768,11 @@ static cudaError_t launch_fused_tc_impl(const nl_desc* d, bool bwd, const void* 
   A.x = (float*)x; A.gx = (const float*)gx;
   A.stash = (unsigned char*)saved;
   A.h2sep = g.h2sep;
+  if (dh) {
+    A.fout = dh->fout;
+    A.dfin = dh->dfin;
+    A.f_plane = (long long)d->T * d->B;
+  }
   if (pr) {
     A.row_scale = pr->row_scale;
     A.zstash = pr->zstash;
@@ -2974,6 +3036,84 @@ cudaError_t launch_fused_tc_per_row(const nl_desc* d, bool bwd, const void* p, c
     if (launches) *launches += 3;
   }
   return cudaSuccess;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// De Hoog on the tensor-core path.  The s points and the MLP are those of the Fourier family
+// (inverse_laplace.py:1146-1147), so the kernels run on a Fourier descriptor; only the last step differs:
+// the forward writes F[d][k][t][b] and dehoog_qd_kernel turns it into x, the backward first runs the
+// recurrence's reverse sweep (dL/dF from grad_x) and the saved backward kernel reads that instead of
+// grad_x * coefficients.  F lives behind the activation stash; without a stash the backward is the SIMT kernel.
+static bool dh_desc(const nl_desc* d, nl_desc* dd) {
+  // NL_B200_DEHOOG_TC=0 keeps De Hoog on the SIMT kernels (float32 FMA MLP: F to ~1e-7 instead of the ~1e-5 of the
+  // bf16x3 tensor-core GEMMs, which the ill-conditioned recurrence amplifies -- see DESIGN.md section 4.9)
+  static const bool off = [] { const char* v = getenv("NL_B200_DEHOOG_TC"); return v && atoi(v) == 0; }();
+  if (off) return false;
+  if (d->family != NL_DEHOOG || d->dtype != NL_F32 || d->t_mode != NL_T_SHARED) return false;
+  if (d->n < 3 || d->n % 2 == 0) return false;
+  *dd = *d;
+  dd->family = NL_FOURIER;
+  return true;
+}
+static size_t dh_f_bytes(const nl_desc* d) {
+  return tc_align((size_t)d->D * d->n * (size_t)d->T * d->B * sizeof(float2), 256);
+}
+
+TcPlan tc_dh_plan(const nl_desc* d, int pass) {
+  nl_desc dd;
+  if (!dh_desc(d, &dd)) return TcPlan{};
+  TcPlan pl = tc_plan(&dd, pass);
+  if (!pl.ok) return pl;
+  if (pass != 0 && tc_saved_bytes(&dd) == 0) return TcPlan{};
+  pl.ws_bytes = tc_align(pl.ws_bytes, 256) + dh_f_bytes(d) + dehoog_qd_scratch_bytes(d, pass != 0) + 1024;
+  return pl;
+}
+
+size_t tc_dh_saved_bytes(const nl_desc* d) {
+  nl_desc dd;
+  if (!dh_desc(d, &dd)) return 0;
+  const size_t inner = tc_saved_bytes(&dd);
+  if (inner == 0) return 0;
+  return tc_align(inner, 256) + dh_f_bytes(d) + 512;
+}
+
+cudaError_t launch_fused_tc_dehoog(const nl_desc* d, bool bwd, const void* p, const void* t,
+                                   const void* const* weights, void* x, const void* gx, void* const* grads, void* ws,
+                                   cudaStream_t st, int* launches, void* saved) {
+  nl_desc dd;
+  if (!dh_desc(d, &dd)) return cudaErrorInvalidValue;
+  const TcPlan inner = tc_plan(&dd, bwd ? 1 : 0);
+  if (!inner.ok) return cudaErrorInvalidValue;
+  unsigned char* w = (unsigned char*)tc_align((size_t)ws, 256);
+  unsigned char* extra = (unsigned char*)tc_align((size_t)w + inner.ws_bytes, 256);
+  float2* F;
+  if (saved) {
+    F = (float2*)tc_align((size_t)saved + tc_saved_bytes(&dd), 256);
+  } else {
+    F = (float2*)extra;
+    extra += dh_f_bytes(d);
+  }
+  cudaError_t e;
+  if (!bwd) {
+    DhExtra dh{F, nullptr};
+    e = launch_fused_tc_impl(&dd, false, p, t, weights, nullptr, nullptr, x, nullptr, nullptr, w, st, launches, saved,
+                             nullptr, &dh);
+    if (e != cudaSuccess) return e;
+    e = launch_dehoog_qd(d, false, t, F, nullptr, x, nullptr, extra, st);
+    if (e != cudaSuccess) return e;
+    if (launches) *launches += 1;
+    return cudaSuccess;
+  }
+  if (!saved) return cudaErrorInvalidValue;
+  float2* dF = (float2*)extra;
+  extra += dh_f_bytes(d);
+  e = launch_dehoog_qd(d, true, t, F, gx, nullptr, dF, extra, st);
+  if (e != cudaSuccess) return e;
+  if (launches) *launches += 1;
+  DhExtra dh{nullptr, dF};
+  return launch_fused_tc_impl(&dd, true, p, t, weights, nullptr, nullptr, nullptr, gx, grads, w, st, launches, saved,
+                              nullptr, &dh);
 }
 
 }  // namespace nl

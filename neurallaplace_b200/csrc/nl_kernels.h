@@ -64,6 +64,17 @@ cudaError_t launch_fused_tc2(const nl_desc* d, bool bwd, const void* p, const vo
                              const void* beta, const void* eta, void* x, const void* gx, void* const* grads, void* ws,
                              cudaStream_t st, int* launches);
 
+// ---- De Hoog on the tensor-core path: F / dF cross HBM as [d][k][t][b] complex planes, the quotient-difference
+// recurrence runs one thread per (b, t, d) in between (nl_dehoog_qd.cu) ----
+TcPlan tc_dh_plan(const nl_desc* d, int pass);
+size_t tc_dh_saved_bytes(const nl_desc* d);
+cudaError_t launch_fused_tc_dehoog(const nl_desc* d, bool bwd, const void* p, const void* t,
+                                   const void* const* weights, void* x, const void* gx, void* const* grads, void* ws,
+                                   cudaStream_t st, int* launches, void* saved);
+size_t dehoog_qd_scratch_bytes(const nl_desc* d, bool bwd);
+cudaError_t launch_dehoog_qd(const nl_desc* d, bool bwd, const void* t, const void* F, const void* gx, void* x,
+                             void* dF, void* scratch, cudaStream_t st);
+
 int device_sm_count();
 
 }  // namespace nl
