@@ -1,201 +1,212 @@
-// De Hoog quotient-difference recurrence between the tensor-core forward and backward kernels
-// (reference: torchlaplace/inverse_laplace.py:737-866; the recurrence itself is nl_dehoog.cuh).
+// De Hoog quotient-difference recurrence as its own kernels, between the kernels that evaluate the MLP
+// (reference: torchlaplace/inverse_laplace.py:737-866; the recurrence itself is nl_dehoog_sm.cuh / nl_dehoog.cuh).
 // One thread per (b, t, d) element, as BASELINE.json's north_star asks ("a per-thread recurrence that stays
-// parallel over batch and time").  F and dL/dF are [d][k][t][b] complex planes, so the 32 threads of a warp
-// (consecutive b) read and write 256 contiguous bytes per term.
+// parallel over batch and time"): the fused kernels run one CTA per SM with at most 128 rows per tile, which left
+// the recurrence on 2-4 warps per SM; here it runs at full occupancy.  F and dL/dF are [d][k][t][b] complex
+// planes, so the 32 threads of a warp (consecutive b) read and write contiguous bytes per term.
+//   forward : F -> x = pref * Re(A*/B*)
+//   backward: F, grad_x -> dL/dF as (g Re dw, -g Im dw), g = grad_x * pref: what head_backward takes
 #include <algorithm>
 #include <cstdlib>
 
 #include "nl_dehoog.cuh"
-#include "nl_dehoog_reg.cuh"
+#include "nl_dehoog_sm.cuh"
 #include "nl_kernels.h"
 
 namespace nl {
 
 namespace {
+
+template <typename R>
+struct QdArgs {
+  IltParams<R> P;
+  int B, T, D, per_row;
+  const R* t;
+  const Cx<R>* F;
+  const R* gx;
+  R* x;
+  Cx<R>* dF;
+  Cx<R>* scratch;    // per-thread table (strip variant) or the whole working set (generic variant)
+  int64_t stride;    // launched threads
+};
+
+template <typename R>
+struct QdItem {
+  int d, ti, b;
+  int64_t tb, xi;
+  TimeCtx<R> c;
+  Cx<R> z;
+};
+template <typename R>
+__device__ __forceinline__ QdItem<R> qd_item(const QdArgs<R>& A, int64_t item) {
+  QdItem<R> q;
+  const int64_t plane = (int64_t)A.T * A.B;
+  q.d = (int)(item / plane);
+  q.tb = item - (int64_t)q.d * plane;
+  q.ti = (int)(q.tb / A.B);
+  q.b = (int)(q.tb - (int64_t)q.ti * A.B);
+  const R tv = A.per_row ? A.t[(int64_t)q.b * A.T + q.ti] : A.t[q.ti];
+  q.c = make_time_ctx<R>(A.P, tv, nullptr, 0);
+  R sn, cs;
+  m_sincos((R(kPi) * q.c.t) / q.c.T, &sn, &cs);  // z = exp(i*pi*t/T), inverse_laplace.py:842
+  q.z = Cx<R>{cs, sn};
+  q.xi = ((int64_t)q.b * A.T + q.ti) * A.D + q.d;
+  return q;
+}
+
+// ---- generic variant: any number of terms, working set in global memory (nl_dehoog.cuh) ----
 constexpr int kQdThreads = 128;
-
-template <bool BWD>
-__global__ void __launch_bounds__(kQdThreads) dehoog_qd_kernel(IltParams<float> P, int B, int T, int D,
-                                                               const float* __restrict__ t,
-                                                               const Cx<float>* __restrict__ F,
-                                                               const float* __restrict__ gx, float* __restrict__ x,
-                                                               Cx<float>* __restrict__ dF, Cx<float>* scratch,
-                                                               int64_t stride) {
-  const int n = P.n, M = (n - 1) / 2;
-  const int64_t plane = (int64_t)T * B;
-  const int64_t items = plane * D;
+template <typename R, bool BWD>
+__global__ void __launch_bounds__(kQdThreads) dehoog_qd_kernel(QdArgs<R> A) {
+  const int n = A.P.n, M = (n - 1) / 2;
+  const int64_t plane = (int64_t)A.T * A.B;
+  const int64_t items = plane * A.D;
   const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   for (int64_t item = slot; item < items; item += (int64_t)gridDim.x * blockDim.x) {
-    const int d = (int)(item / plane);
-    const int64_t tb = item - (int64_t)d * plane;
-    const int ti = (int)(tb / B);
-    const int b = (int)(tb - (int64_t)ti * B);
-    const TimeCtx<float> c = make_time_ctx<float>(P, t[ti], nullptr, 0);
-    float sn, cs;
-    m_sincos((float(kPi) * c.t) / c.T, &sn, &cs);  // z = exp(i*pi*t/T), inverse_laplace.py:842
-    const Cx<float> z{cs, sn};
-    const Cx<float>* Fp = F + (int64_t)d * n * plane + tb;
+    const QdItem<R> q = qd_item(A, item);
+    const Cx<R>* Fp = A.F + (int64_t)q.d * n * plane + q.tb;
     auto a = [&](int k) { return Fp[(int64_t)k * plane]; };
-    Scratch<float> scr{scratch, stride, slot};
-    const int64_t xi = ((int64_t)b * T + ti) * D + d;
+    Scratch<R> scr{A.scratch, A.stride, slot};
     if (!BWD) {
-      const Cx<float> w = dehoog_forward<float>(M, z, a, scr);
-      x[xi] = c.pref * w.re;
+      const Cx<R> w = dehoog_forward<R>(M, q.z, a, scr);
+      A.x[q.xi] = q.c.pref * w.re;
     } else {
-      const float g = gx[xi] * c.pref;
-      Cx<float>* dFp = dF + (int64_t)d * n * plane + tb;
-      auto emit = [&](int k, Cx<float> dw) { dFp[(int64_t)k * plane] = Cx<float>{g * dw.re, -g * dw.im}; };
-      dehoog_forward_backward<float>(M, z, a, emit, scr);
+      const R g = A.gx[q.xi] * q.c.pref;
+      Cx<R>* dFp = A.dF + (int64_t)q.d * n * plane + q.tb;
+      auto emit = [&](int k, Cx<R> dw) { dFp[(int64_t)k * plane] = Cx<R>{g * dw.re, -g * dw.im}; };
+      dehoog_forward_backward<R>(M, q.z, a, emit, scr);
     }
   }
 }
 
-// ---- register-resident variant for 17 / 33 terms (nl_dehoog_reg.cuh) ----
-struct TabRef {
-  Cx<float>* base;
-  int64_t stride, slot;
-  __device__ __forceinline__ Cx<float>& operator()(int idx) const { return base[(int64_t)idx * stride + slot]; }
-};
-struct HistRef {
-  Cx<float>* base;
-  __device__ __forceinline__ Cx<float>& operator()(int idx) const { return base[idx * kQdThreads + threadIdx.x]; }
-};
-
-// per-thread ring in shared memory filled by cp.async (8 bytes per entry and thread; a thread only ever reads what
-// it copied itself, so cp.async.wait_group is the only synchronisation)
-struct StageRef {
-  Cx<float>* ring;          // [kDhStageEntries][kQdThreads]
-  const Cx<float>* tbase;   // this thread's table slot
-  int64_t stride;
-  __device__ __forceinline__ void issue(int k, int idx) const {
-    const unsigned dst = (unsigned)__cvta_generic_to_shared(ring + k * kQdThreads + threadIdx.x);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(tbase + (int64_t)idx * stride) : "memory");
-  }
-  __device__ __forceinline__ void commit() const { asm volatile("cp.async.commit_group;" ::: "memory"); }
-  template <int N>
-  __device__ __forceinline__ void wait() const {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-  }
-  __device__ __forceinline__ Cx<float> get(int k) const { return ring[k * kQdThreads + threadIdx.x]; }
-};
-
-template <int M, bool BWD>
-__global__ void __launch_bounds__(kQdThreads, BWD ? 2 : 3) dehoog_qd_reg_kernel(
-    IltParams<float> P, int B, int T, int D, const float* __restrict__ t, const Cx<float>* __restrict__ F,
-    const float* __restrict__ gx, float* __restrict__ x, Cx<float>* __restrict__ dF, Cx<float>* table,
-    int64_t stride) {
+// ---- shared-memory-strip variant (nl_dehoog_sm.cuh): working columns in shared memory, table in global ----
+template <typename R, bool BWD, int THREADS>
+__global__ void __launch_bounds__(THREADS) dehoog_qd_sm_kernel(QdArgs<R> A) {
   extern __shared__ __align__(16) unsigned char qd_smem[];
-  constexpr int n = 2 * M + 1;
-  const int64_t plane = (int64_t)T * B;
-  const int64_t items = plane * D;
+  Cx<R>* strip = reinterpret_cast<Cx<R>*>(qd_smem) + threadIdx.x;
+  const int n = A.P.n, M = (n - 1) / 2;
+  const int64_t plane = (int64_t)A.T * A.B;
+  const int64_t items = plane * A.D;
   const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  Cx<R>* tabp = A.scratch + slot;
+  const int64_t stride = A.stride;
+  auto col = [&](int i) -> Cx<R>& { return strip[i * THREADS]; };
+  auto tab = [&](int i) -> Cx<R>& { return tabp[(int64_t)i * stride]; };
+  auto pf = [&](int i) { asm volatile("prefetch.global.L2 [%0];" ::"l"(tabp + (int64_t)i * stride)); };
   for (int64_t item = slot; item < items; item += (int64_t)gridDim.x * blockDim.x) {
-    const int d = (int)(item / plane);
-    const int64_t tb = item - (int64_t)d * plane;
-    const int ti = (int)(tb / B);
-    const int b = (int)(tb - (int64_t)ti * B);
-    const TimeCtx<float> c = make_time_ctx<float>(P, t[ti], nullptr, 0);
-    float sn, cs;
-    m_sincos((float(kPi) * c.t) / c.T, &sn, &cs);
-    const Cx<float> z{cs, sn};
-    const Cx<float>* Fp = F + (int64_t)d * n * plane + tb;
+    const QdItem<R> q = qd_item(A, item);
+    const Cx<R>* Fp = A.F + (int64_t)q.d * n * plane + q.tb;
     auto a = [&](int k) { return Fp[(int64_t)k * plane]; };
-    const int64_t xi = ((int64_t)b * T + ti) * D + d;
+    auto pfa = [&](int k) { asm volatile("prefetch.global.L2 [%0];" ::"l"(Fp + (int64_t)k * plane)); };
     if (!BWD) {
-      const Cx<float> w = dehoog_reg_forward<float, M>(z, a);
-      x[xi] = c.pref * w.re;
+      auto emit = [&](int, Cx<R>) {};
+      const Cx<R> w = dehoog_sm<R, false>(M, q.z, a, emit, col, tab, pf, pfa);
+      A.x[q.xi] = q.c.pref * w.re;
     } else {
-      const float g = gx[xi] * c.pref;
-      Cx<float>* dFp = dF + (int64_t)d * n * plane + tb;
-      auto emit = [&](int k, Cx<float> dw) { dFp[(int64_t)k * plane] = Cx<float>{g * dw.re, -g * dw.im}; };
-      Cx<float>* sm = reinterpret_cast<Cx<float>*>(qd_smem);
-      dehoog_reg_forward_backward<float, M>(
-          z, a, emit, TabRef{table, stride, slot}, HistRef{sm},
-          StageRef{sm + DehoogRegLayout<M>::kHistEntries * kQdThreads, table + slot, stride});
+      const R g = A.gx[q.xi] * q.c.pref;
+      Cx<R>* dFp = A.dF + (int64_t)q.d * n * plane + q.tb;
+      auto emit = [&](int k, Cx<R> dw) { dFp[(int64_t)k * plane] = Cx<R>{g * dw.re, -g * dw.im}; };
+      dehoog_sm<R, true>(M, q.z, a, emit, col, tab, pf, pfa);
     }
   }
 }
 
-template <int M, bool BWD>
-size_t reg_smem() {
-  return BWD ? (size_t)(DehoogRegLayout<M>::kHistEntries + kDhStageEntries) * kQdThreads * sizeof(Cx<float>) : 0;
+// threads per CTA of the strip variant: the largest of 128 / 64 / 32 whose strips (2n complex per thread) let
+// three CTAs share an SM; 0 = use the generic variant
+int sm_threads(const nl_desc* d) {
+  static const bool off = [] { const char* v = getenv("NL_B200_DEHOOG_SM"); return v && atoi(v) == 0; }();
+  if (off) return 0;
+  const size_t per_thread = (size_t)dehoog_sm_col_entries(d->n) * (d->dtype == NL_F64 ? 16 : 8);
+  for (int th = 128; th >= 32; th /= 2)
+    if (per_thread * th <= 72 * 1024) return th;
+  return 0;
 }
-template <int M, bool BWD>
-int reg_blocks() {
-  static int per_sm = [] {
-    int v = 0;
-    cudaFuncSetAttribute(dehoog_qd_reg_kernel<M, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)reg_smem<M, BWD>());
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, dehoog_qd_reg_kernel<M, BWD>, kQdThreads, reg_smem<M, BWD>());
-    return v > 0 ? v : 1;
-  }();
-  return per_sm * device_sm_count();
+size_t sm_smem(const nl_desc* d) {
+  return (size_t)dehoog_sm_col_entries(d->n) * (d->dtype == NL_F64 ? 16 : 8) * sm_threads(d);
 }
-bool reg_variant(const nl_desc* d) {
-  static const bool off = [] { const char* v = getenv("NL_B200_DEHOOG_REG"); return v && atoi(v) == 0; }();
-  return !off && (d->n == 17 || d->n == 33);
+template <typename R, bool BWD, int THREADS>
+int sm_blocks(size_t smem) {
+  int v = 0;
+  cudaFuncSetAttribute(dehoog_qd_sm_kernel<R, BWD, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, dehoog_qd_sm_kernel<R, BWD, THREADS>, THREADS, smem);
+  return (v > 0 ? v : 1) * device_sm_count();
 }
-template <int M>
-cudaError_t launch_reg(const nl_desc* d, bool bwd, const IltParams<float>& P, const void* t, const void* F,
-                       const void* gx, void* x, void* dF, Cx<float>* scr, cudaStream_t st) {
+template <typename R>
+int64_t sm_cap(int th, bool bwd, size_t smem) {
+  if (th == 128) return bwd ? sm_blocks<R, true, 128>(smem) : sm_blocks<R, false, 128>(smem);
+  if (th == 64) return bwd ? sm_blocks<R, true, 64>(smem) : sm_blocks<R, false, 64>(smem);
+  return bwd ? sm_blocks<R, true, 32>(smem) : sm_blocks<R, false, 32>(smem);
+}
+// launched CTAs (persistent, grid-stride): the table is one slot per launched thread
+int64_t qd_grid(const nl_desc* d, bool bwd) {
   const int64_t items = (int64_t)d->B * d->T * d->D;
-  const int64_t need = (items + kQdThreads - 1) / kQdThreads;
-  if (bwd) {
-    const int64_t blocks = std::min<int64_t>(need, reg_blocks<M, true>());
-    dehoog_qd_reg_kernel<M, true><<<(unsigned)blocks, kQdThreads, reg_smem<M, true>(), st>>>(
-        P, d->B, d->T, d->D, (const float*)t, (const Cx<float>*)F, (const float*)gx, nullptr, (Cx<float>*)dF, scr,
-        blocks * kQdThreads);
+  const int th = sm_threads(d);
+  if (th == 0) {
+    const int64_t need = (items + kQdThreads - 1) / kQdThreads;
+    return std::min<int64_t>(need, (int64_t)device_sm_count() * 8);
+  }
+  const int64_t need = (items + th - 1) / th;
+  const int64_t cap = d->dtype == NL_F64 ? sm_cap<double>(th, bwd, sm_smem(d)) : sm_cap<float>(th, bwd, sm_smem(d));
+  return std::min<int64_t>(need, cap);
+}
+
+template <typename R, bool BWD, int THREADS>
+void sm_launch(const QdArgs<R>& A, int64_t blocks, size_t smem, cudaStream_t st) {
+  dehoog_qd_sm_kernel<R, BWD, THREADS><<<(unsigned)blocks, THREADS, smem, st>>>(A);
+}
+
+template <typename R>
+cudaError_t launch_t(const nl_desc* d, bool bwd, const void* t, const void* F, const void* gx, void* x, void* dF,
+                     void* scratch, cudaStream_t st) {
+  const int64_t blocks = qd_grid(d, bwd);
+  if (blocks == 0) return cudaSuccess;
+  QdArgs<R> A{};
+  A.P.family = NL_DEHOOG;
+  A.P.n = d->n;
+  A.P.head = d->head;
+  A.P.alpha = (R)d->alpha;
+  A.P.log_tol = (R)d->log_tol;
+  A.P.scale = (R)d->scale;
+  A.B = d->B; A.T = d->T; A.D = d->D;
+  A.per_row = d->t_mode == NL_T_PER_ROW ? 1 : 0;
+  A.t = (const R*)t; A.F = (const Cx<R>*)F; A.gx = (const R*)gx; A.x = (R*)x; A.dF = (Cx<R>*)dF;
+  A.scratch = (Cx<R>*)(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
+  const int th = sm_threads(d);
+  if (th == 0) {
+    A.stride = blocks * kQdThreads;
+    if (bwd) dehoog_qd_kernel<R, true><<<(unsigned)blocks, kQdThreads, 0, st>>>(A);
+    else dehoog_qd_kernel<R, false><<<(unsigned)blocks, kQdThreads, 0, st>>>(A);
+    return cudaGetLastError();
+  }
+  A.stride = blocks * th;
+  const size_t smem = sm_smem(d);
+  if (th == 128) {
+    if (bwd) sm_launch<R, true, 128>(A, blocks, smem, st);
+    else sm_launch<R, false, 128>(A, blocks, smem, st);
+  } else if (th == 64) {
+    if (bwd) sm_launch<R, true, 64>(A, blocks, smem, st);
+    else sm_launch<R, false, 64>(A, blocks, smem, st);
   } else {
-    const int64_t blocks = std::min<int64_t>(need, (int64_t)reg_blocks<M, false>() * 4);
-    dehoog_qd_reg_kernel<M, false><<<(unsigned)blocks, kQdThreads, 0, st>>>(
-        P, d->B, d->T, d->D, (const float*)t, (const Cx<float>*)F, nullptr, (float*)x, nullptr, nullptr, 0);
+    if (bwd) sm_launch<R, true, 32>(A, blocks, smem, st);
+    else sm_launch<R, false, 32>(A, blocks, smem, st);
   }
   return cudaGetLastError();
-}
-
-int64_t qd_blocks(const nl_desc* d) {
-  const int64_t items = (int64_t)d->B * d->T * d->D;
-  const int64_t need = (items + kQdThreads - 1) / kQdThreads;
-  return std::min<int64_t>(need, (int64_t)device_sm_count() * 8);
 }
 }  // namespace
 
 size_t dehoog_qd_scratch_bytes(const nl_desc* d, bool bwd) {
-  if (reg_variant(d)) {
-    if (!bwd) return 256;
-    const int blocks = d->n == 17 ? reg_blocks<8, true>() : reg_blocks<16, true>();
-    const size_t ent = d->n == 17 ? DehoogRegLayout<8>::kTabEntries : DehoogRegLayout<16>::kTabEntries;
-    return ent * (size_t)blocks * kQdThreads * sizeof(Cx<float>) + 256;
-  }
-  return (size_t)dehoog_scratch_entries(d->n, bwd) * (size_t)qd_blocks(d) * kQdThreads * sizeof(Cx<float>) + 256;
+  const size_t cs = d->dtype == NL_F64 ? 16 : 8;
+  const int th = sm_threads(d);
+  if (th == 0)
+    return (size_t)dehoog_scratch_entries(d->n, bwd) * (size_t)qd_grid(d, bwd) * kQdThreads * cs + 256;
+  if (!bwd) return 256;
+  return (size_t)dehoog_sm_tab_entries(d->n) * (size_t)qd_grid(d, true) * th * cs + 256;
 }
 
 cudaError_t launch_dehoog_qd(const nl_desc* d, bool bwd, const void* t, const void* F, const void* gx, void* x,
                              void* dF, void* scratch, cudaStream_t st) {
-  const int64_t blocks = qd_blocks(d);
-  if (blocks == 0) return cudaSuccess;
-  IltParams<float> P{};
-  P.family = NL_DEHOOG;
-  P.n = d->n;
-  P.head = d->head;
-  P.alpha = (float)d->alpha;
-  P.log_tol = (float)d->log_tol;
-  P.scale = (float)d->scale;
-  Cx<float>* scr = (Cx<float>*)(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
-  if (reg_variant(d))
-    return d->n == 17 ? launch_reg<8>(d, bwd, P, t, F, gx, x, dF, scr, st)
-                      : launch_reg<16>(d, bwd, P, t, F, gx, x, dF, scr, st);
-  const int64_t stride = blocks * kQdThreads;
-  if (bwd)
-    dehoog_qd_kernel<true><<<(unsigned)blocks, kQdThreads, 0, st>>>(P, d->B, d->T, d->D, (const float*)t,
-                                                                   (const Cx<float>*)F, (const float*)gx, nullptr,
-                                                                   (Cx<float>*)dF, scr, stride);
-  else
-    dehoog_qd_kernel<false><<<(unsigned)blocks, kQdThreads, 0, st>>>(P, d->B, d->T, d->D, (const float*)t,
-                                                                    (const Cx<float>*)F, nullptr, (float*)x, nullptr,
-                                                                    scr, stride);
-  return cudaGetLastError();
+  return d->dtype == NL_F64 ? launch_t<double>(d, bwd, t, F, gx, x, dF, scratch, st)
+                            : launch_t<float>(d, bwd, t, F, gx, x, dF, scratch, st);
 }
 
 }  // namespace nl

@@ -40,8 +40,10 @@ struct FusedArgs {
   R* slab;
   int64_t slab_len;
   R* dp;
-  Cx<R>* scratch;
-  int64_t scratch_stride;
+  // De Hoog: the recurrence runs in its own kernels (nl_dehoog_qd.cu); the forward instantiation writes
+  // F[d][k][t][b] here, the backward one reads dL/dF (already scaled by grad_x * pref, imaginary part negated)
+  Cx<R>* fplane;
+  const Cx<R>* dfplane;
 };
 
 struct SmemLayout {
@@ -353,51 +355,23 @@ __global__ void __launch_bounds__(kThreads, 1) fused_simt_kernel(FusedArgs<R> A)
           }
         }
       } else {
-        // De Hoog: F -> scratch, one thread per row runs the recurrence, then (bwd) dF -> dO.
-        const int M = (n - 1) / 2;
-        const int ent = dehoog_scratch_entries(n, BWD);
+        // De Hoog: the quotient-difference recurrence is not run here (one CTA per SM and <= 128 rows per tile
+        // would leave it on a few warps): forward = F out to its [d][k][t][b] plane, backward = dL/dF in.
+        const int64_t plane = (int64_t)A.T * A.B;
         for (int k = warp; k < n; k += kWarps) {
 #pragma unroll
           for (int i = 0; i < RP; ++i) {
             const int r = lane + 32 * i;
             if (r < rows) {
               HeadOut<R> h = head_forward<R>(P.head, sO[r * ldo + k], sO[r * ldo + n + k]);
-              Scratch<R> scr{A.scratch, A.scratch_stride, (int64_t)blockIdx.x * RMAX + r};
-              scr[ent + k] = Cx<R>{h.fre, h.fim};
-            }
-          }
-        }
-        __syncthreads();
-        if (tid < rows) {
-          const int r = tid;
-          Scratch<R> scr{A.scratch, A.scratch_stride, (int64_t)blockIdx.x * RMAX + r};
-          SlotCtx<R> sc = sCtx[row_slot(r)];
-          Cx<R> z{sc.zc, sc.zs};
-          auto a = [&](int k) { return scr[ent + k]; };
-          if (!BWD) {
-            Cx<R> w = dehoog_forward<R>(M, z, a, scr);
-            sX[r] = w.re;
-          } else {
-            auto emit = [&](int k, Cx<R> dw) { scr[ent + n + k] = dw; };
-            if (row_valid(r)) {
-              dehoog_forward_backward<R>(M, z, a, emit, scr);
-            } else {
-              for (int k = 0; k < n; ++k) scr[ent + n + k] = Cx<R>{R(0), R(0)};
-            }
-          }
-        }
-        if (BWD) {
-          __syncthreads();
-          for (int k = warp; k < n; k += kWarps) {
-#pragma unroll
-            for (int i = 0; i < RP; ++i) {
-              const int r = lane + 32 * i;
-              if (r < rows) {
-                HeadOut<R> h = head_forward<R>(P.head, sO[r * ldo + k], sO[r * ldo + n + k]);
-                Scratch<R> scr{A.scratch, A.scratch_stride, (int64_t)blockIdx.x * RMAX + r};
-                Cx<R> dw = scr[ent + n + k];
-                R g = sGp[r], goa, gob;
-                head_backward<R>(P.head, h, g * dw.re, -g * dw.im, &goa, &gob);
+              const int64_t idx = ((int64_t)d * n + k) * plane + (int64_t)row_t(r) * A.B + row_b(r);
+              if (!BWD) {
+                if (row_valid(r)) A.fplane[idx] = Cx<R>{h.fre, h.fim};
+              } else {
+                Cx<R> df{R(0), R(0)};
+                if (row_valid(r)) df = A.dfplane[idx];
+                R goa, gob;
+                head_backward<R>(P.head, h, df.re, df.im, &goa, &gob);
                 sO[r * ldo + k] = goa;
                 sO[r * ldo + n + k] = gob;
               }
@@ -408,8 +382,10 @@ __global__ void __launch_bounds__(kThreads, 1) fused_simt_kernel(FusedArgs<R> A)
       __syncthreads();
 
       if (!BWD) {
-        for (int r = tid; r < rows; r += kThreads) {
-          if (row_valid(r)) A.x[((int64_t)row_b(r) * A.T + row_t(r)) * D + d] = sCtx[row_slot(r)].pref * sX[r];
+        if (!dehoog) {  // (De Hoog: x is written by dehoog_qd_kernel)
+          for (int r = tid; r < rows; r += kThreads) {
+            if (row_valid(r)) A.x[((int64_t)row_b(r) * A.T + row_t(r)) * D + d] = sCtx[row_slot(r)].pref * sX[r];
+          }
         }
       } else {
         // dH2 += dO . W3[rows of d]   ;   dW3 / db3 slabs
@@ -544,8 +520,9 @@ SimtPlan simt_plan(const nl_desc* d, int pass) {
                 (size_t)2 * d->D * d->n;
   size_t ws = 0;
   if (bwd) ws += align_up(pl.slab_len * rs * pl.grid, 256);
-  if (d->family == NL_DEHOOG)
-    ws += align_up((size_t)(dehoog_scratch_entries(d->n, bwd) + 2 * d->n) * (size_t)pl.grid * rmax * 2 * rs, 256);
+  if (d->family == NL_DEHOOG)  // F plane (+ dL/dF plane) + what the recurrence kernels need
+    ws += (bwd ? 2 : 1) * align_up((size_t)d->D * d->n * (size_t)d->T * d->B * 2 * rs, 256) +
+          align_up(dehoog_qd_scratch_bytes(d, bwd), 256);
   pl.ws_bytes = ws + 256;
   pl.ok = 1;
   return pl;
@@ -605,7 +582,6 @@ cudaError_t launch_fused_simt(const nl_desc* d, bool bwd, const void* p, const v
   unsigned char* w = (unsigned char*)ws;
   w = (unsigned char*)align_up((size_t)w, 256);
   cudaError_t e;
-  const int rmax = 32 * pl.rp;
   if (bwd) {
     A.slab = (R*)w;
     A.slab_len = (int64_t)pl.slab_len;
@@ -617,14 +593,44 @@ cudaError_t launch_fused_simt(const nl_desc* d, bool bwd, const void* p, const v
     e = cudaMemsetAsync(A.dp, 0, (size_t)d->B * d->K * sizeof(R), st);
     if (e != cudaSuccess) return e;
   }
+  auto run = [&](const FusedArgs<R>& args, bool backward) {
+    return pl.rp == 2 ? launch_rp<R, 2>(args, backward, pl.grid, pl.smem, st)
+                      : launch_rp<R, 1>(args, backward, pl.grid, pl.smem, st);
+  };
   if (d->family == NL_DEHOOG) {
-    A.scratch = (Cx<R>*)w;
-    A.scratch_stride = (int64_t)pl.grid * rmax;
+    // forward: MLP -> F plane, recurrence -> x.   backward: MLP -> F plane (recomputed), recurrence forward +
+    // reverse sweep -> dL/dF plane, then the backward kernel proper with dL/dF in place of grad_x * coefficients.
+    const size_t fbytes = align_up((size_t)d->D * d->n * (size_t)d->T * d->B * 2 * sizeof(R), 256);
+    Cx<R>* F = (Cx<R>*)w;
+    w += fbytes;
+    Cx<R>* dF = nullptr;
+    if (bwd) {
+      dF = (Cx<R>*)w;
+      w += fbytes;
+    }
+    FusedArgs<R> Af = A;
+    Af.fplane = F;
+    if (bwd) {  // the forward instantiation has no slab / dp
+      Af.slab = nullptr;
+      Af.dp = nullptr;
+      const SimtPlan plf = simt_plan(d, 0);  // (the forward plan may pick a different tile geometry)
+      if (!plf.ok) return cudaErrorInvalidValue;
+      Af.BB = plf.BB; Af.TT = plf.TT;
+      Af.nbt = (d->B + plf.BB - 1) / plf.BB;
+      Af.ntt = (d->T + plf.TT - 1) / plf.TT;
+      e = plf.rp == 2 ? launch_rp<R, 2>(Af, false, plf.grid, plf.smem, st)
+                      : launch_rp<R, 1>(Af, false, plf.grid, plf.smem, st);
+    } else {
+      e = run(Af, false);
+    }
+    if (e != cudaSuccess) return e;
+    e = launch_dehoog_qd(d, bwd, t, F, gx, x, dF, w, st);
+    if (e != cudaSuccess) return e;
+    if (launches) *launches += 2;
+    if (!bwd) return cudaSuccess;
+    A.dfplane = dF;
   }
-  if (pl.rp == 2)
-    e = launch_rp<R, 2>(A, bwd, pl.grid, pl.smem, st);
-  else
-    e = launch_rp<R, 1>(A, bwd, pl.grid, pl.smem, st);
+  e = run(A, bwd);
   if (e != cudaSuccess) return e;
   if (launches) *launches += 1;
   if (bwd) {

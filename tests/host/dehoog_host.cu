@@ -4,39 +4,9 @@
 #include <vector>
 
 #include "../../neurallaplace_b200/csrc/nl_dehoog.cuh"
-#include "../../neurallaplace_b200/csrc/nl_dehoog_reg.cuh"
+#include "../../neurallaplace_b200/csrc/nl_dehoog_sm.cuh"
 
 using namespace nl;
-
-struct HostStage {
-  std::vector<Cx<double>>* t;
-  Cx<double> ring[kDhStageEntries];
-  void issue(int k, int idx) { ring[k] = (*t)[idx]; }
-  void commit() {}
-  template <int N>
-  void wait() {}
-  Cx<double> get(int k) const { return ring[k]; }
-};
-
-// register-resident variant (compile-time M) used by the tensor-core De Hoog path
-template <int M>
-static void run_reg(double zr, double zi, const double* a, double* w_out, double* dw_out, double* w_fwd_only) {
-  std::vector<Cx<double>> tabv(DehoogRegLayout<M>::kTabEntries), histv(DehoogRegLayout<M>::kHistEntries);
-  auto acc = [&](int k) { return Cx<double>{a[2 * k], a[2 * k + 1]}; };
-  auto emit = [&](int k, Cx<double> g) {
-    dw_out[2 * k] = g.re;
-    dw_out[2 * k + 1] = g.im;
-  };
-  auto tab = [&](int i) -> Cx<double>& { return tabv[i]; };
-  auto hist = [&](int i) -> Cx<double>& { return histv[i]; };
-  HostStage stage{&tabv};
-  Cx<double> w = dehoog_reg_forward_backward<double, M>(Cx<double>{zr, zi}, acc, emit, tab, hist, stage);
-  w_out[0] = w.re;
-  w_out[1] = w.im;
-  Cx<double> w2 = dehoog_reg_forward<double, M>(Cx<double>{zr, zi}, acc);
-  w_fwd_only[0] = w2.re;
-  w_fwd_only[1] = w2.im;
-}
 
 extern "C" {
 
@@ -72,11 +42,25 @@ int nlh_dehoog_f32(int n, float zr, float zi, const float* a, float* w_out) {
   return 0;
 }
 
-int nlh_dehoog_reg(int n, double zr, double zi, const double* a, double* w_out, double* dw_out, double* w_fwd_only) {
-  if (n == 5) run_reg<2>(zr, zi, a, w_out, dw_out, w_fwd_only);
-  else if (n == 17) run_reg<8>(zr, zi, a, w_out, dw_out, w_fwd_only);
-  else if (n == 33) run_reg<16>(zr, zi, a, w_out, dw_out, w_fwd_only);
-  else return 1;
+// shared-memory-strip variant (runtime M, rolled loops): the one the tensor-core De Hoog path launches
+int nlh_dehoog_sm(int n, double zr, double zi, const double* a, double* w_out, double* dw_out, double* w_fwd_only) {
+  const int M = (n - 1) / 2;
+  std::vector<Cx<double>> colv(dehoog_sm_col_entries(n)), tabv(dehoog_sm_tab_entries(n));
+  auto acc = [&](int k) { return Cx<double>{a[2 * k], a[2 * k + 1]}; };
+  auto emit = [&](int k, Cx<double> g) {
+    dw_out[2 * k] = g.re;
+    dw_out[2 * k + 1] = g.im;
+  };
+  auto col = [&](int i) -> Cx<double>& { return colv.at(i); };
+  auto tab = [&](int i) -> Cx<double>& { return tabv.at(i); };
+  auto pf = [&](int i) { (void)tabv.at(i); };
+  auto pf0 = [&](int) {};
+  Cx<double> w = dehoog_sm<double, true>(M, Cx<double>{zr, zi}, acc, emit, col, tab, pf, pf0);
+  w_out[0] = w.re;
+  w_out[1] = w.im;
+  Cx<double> w2 = dehoog_sm<double, false>(M, Cx<double>{zr, zi}, acc, emit, col, tab, pf, pf0);
+  w_fwd_only[0] = w2.re;
+  w_fwd_only[1] = w2.im;
   return 0;
 }
 

@@ -22,7 +22,7 @@ DP = ctypes.POINTER(ctypes.c_double)
 def hostlib():
   src = os.path.join(HOST_DIR, "dehoog_host.cu")
   hdrs = [os.path.join(hp.ROOT, "neurallaplace_b200", "csrc", h)
-          for h in ("nl_common.cuh", "nl_dehoog.cuh", "nl_dehoog_reg.cuh")]
+          for h in ("nl_common.cuh", "nl_dehoog.cuh", "nl_dehoog_sm.cuh")]
   if not os.path.exists(SO) or any(os.path.getmtime(f) > os.path.getmtime(SO) for f in [src] + hdrs):
     subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "--extended-lambda",
                            "--expt-relaxed-constexpr", "-diag-suppress", "20013,20015", "-o", SO, src])
@@ -57,14 +57,14 @@ def test_dehoog_forward_and_reverse_sweep(hostlib, terms):
     g = fp.grad[row]
     assert np.linalg.norm(pref * dw[0::2] - g.real.numpy()) <= tol * 100 * np.linalg.norm(g.real.numpy())
     assert np.linalg.norm(-pref * dw[1::2] - g.imag.numpy()) <= tol * 100 * np.linalg.norm(g.imag.numpy())
-    if terms in (5, 17, 33):
-      # the register-resident variant (compile-time M, in-place adjoint columns) performs the same operations in
-      # the same order: identical results, bit for bit
-      wr, dwr, w2r = np.zeros(2), np.zeros(2 * terms), np.zeros(2)
-      assert hostlib.nlh_dehoog_reg(terms, ctypes.c_double(math.cos(ang)), ctypes.c_double(math.sin(ang)), _p(a),
-                                    _p(wr), _p(dwr), _p(w2r)) == 0
-      assert wr[0] == w[0] and wr[1] == w[1] and w2r[0] == w[0] and w2r[1] == w[1]
-      assert np.array_equal(dwr, dw), np.abs(dwr - dw).max()
+    # the shared-memory-strip variant the GPU launches (rolled loops, in-place adjoint columns, divisions in
+    # batches of four) performs the same operations in the same order: identical results, bit for bit
+    ws, dws, w2s = np.zeros(2), np.zeros(2 * terms), np.zeros(2)
+    assert hostlib.nlh_dehoog_sm(terms, ctypes.c_double(math.cos(ang)), ctypes.c_double(math.sin(ang)), _p(a),
+                                 _p(ws), _p(dws), _p(w2s)) == 0
+    assert ws[0] == w[0] and ws[1] == w[1] and w2s[0] == w[0] and w2s[1] == w[1]
+    assert np.array_equal(dws, dw), np.abs(dws - dw).max()
+
 
 
 def test_head_chain_rule(hostlib):
