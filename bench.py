@@ -334,6 +334,17 @@ def run_b200(a):
     elt = 8 if a.dtype == "f64" else 4
     hbm_fwd = (elt * a.dobs * pts_rank + stash) / (fwd_ms * 1e-3) / 1e9
     hbm_bwd = (elt * a.dobs * pts_rank + stash) / (bwd_ms * 1e-3) / 1e9
+    # transcendental (MUFU) share, SURVEY section 8(d): the tcgen05 kernels spend 2 MUFU ops per hidden tanh
+    # (ex2 + rcp) and 7 per head pair (two tanh sharing one rcp, sin, cos, and sin / cos / rcp for the tangent);
+    # the saved backward re-evaluates the heads only.  Peak = SMs x 16 MUFU lanes x SM clock.
+    mufu = None
+    if impl_f == 2 and a.tmode == "shared" and a.alg != "dehoog":
+      clk = sampler.summary().get("sm_mhz") or 1965
+      mufu_peak = 148 * 16 * clk * 1e6
+      mf, mb = 4 * 64 + 7 * a.dobs * n, 7 * a.dobs * n
+      mufu = {"fwd_ops_per_point": mf, "bwd_ops_per_point": mb, "peak_ops_per_s": mufu_peak,
+              "fwd_frac": mf * pts_rank / (fwd_ms * 1e-3) / mufu_peak,
+              "bwd_frac": mb * pts_rank / (bwd_ms * 1e-3) / mufu_peak}
     traffic = None
     try:
       tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
@@ -361,6 +372,7 @@ def run_b200(a):
                      "streaming": {"activation_stash_bytes": stash, "fwd_gbs": hbm_fwd, "bwd_gbs": hbm_bwd,
                                    "peak_gbs": peak_hbm, "fwd_frac": hbm_fwd / peak_hbm,
                                    "bwd_frac": hbm_bwd / peak_hbm},
+                     "mufu": mufu,
                      "note": ("De Hoog: the step is dominated by the per-thread quotient-difference recurrence "
                               "(dehoog_qd kernels: CUDA cores, IEEE divisions, 8 warps/SM), the tensor-core MLP "
                               "kernels take ~3 ms of it; see DESIGN.md section 4.9") if a.alg == "dehoog" else

@@ -110,5 +110,47 @@ __device__ __forceinline__ void head_backward(int head, const Head& h, float gre
   *gob = gr * fmaf(h.r, h.r, 1.f) * 0.5f * h.db;
 }
 
+// atan(t) for t in [0, 1]: t * P(t^2), degree-8 least-squares fit on Chebyshev nodes; max abs error 9e-8 in float.
+__device__ __forceinline__ float atan01(float t) {
+  const float z = t * t;
+  float p = 2.9327620e-3f;
+  p = fmaf(p, z, -1.6413191e-2f);
+  p = fmaf(p, z, 4.3278243e-2f);
+  p = fmaf(p, z, -7.5569004e-2f);
+  p = fmaf(p, z, 1.0667487e-1f);
+  p = fmaf(p, z, -1.4211106e-1f);
+  p = fmaf(p, z, 1.9993694e-1f);
+  p = fmaf(p, z, -3.3333138e-1f);
+  p = fmaf(p, z, 1.0f);
+  return p * t;
+}
+
+// Riemann-sphere features of s = re + i im (transformations.py:56-89): theta = atan2(im, re),
+// phi = asin((|s|^2 - 1) / (|s|^2 + 1)) = 2 atan(|s|) - pi/2.  Used where the features feed a bf16x3 operand
+// image (per-row time grids, point_layer1_kernel): the image keeps 16 mantissa bits, the ~2e-7 absolute error of
+// this version is far below that, and it costs ~50 instructions per s point against ~110 for atan2f + asinf
+// with their IEEE divisions.  (The asin form loses accuracy as |s| grows -- the float32 reference is ~1e-5 off
+// at |s| ~ 500 -- the atan form does not.)
+__device__ __forceinline__ void sphere_features(float re, float im, float* theta, float* phi) {
+  constexpr float kHalfPi = 1.57079632679489662f, kPiF = 3.14159265358979324f;
+  const float a2 = fmaf(im, im, re * re);
+  float ri;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(ri) : "f"(a2));
+  ri = ri * fmaf(-0.5f * a2 * ri, ri, 1.5f);  // one Newton step: 1 / |s|
+  const float r = a2 * ri;                    // |s|
+  const bool big = r > 1.f;
+  const float pr = atan01(big ? ri : r);
+  float ph = big ? fmaf(-2.f, pr, kHalfPi) : fmaf(2.f, pr, -kHalfPi);
+  if (!(a2 < 3.0e38f)) ph = kHalfPi;   // |s|^2 overflowed: the reference's isinf branch (ratio = 1)
+  if (a2 == 0.f) ph = -kHalfPi;
+  const float ax = fabsf(re), ay = fabsf(im);
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  float pt = atan01(mx > 0.f ? __fdividef(mn, mx) : 0.f);
+  if (ay > ax) pt = kHalfPi - pt;
+  if (re < 0.f) pt = kPiF - pt;
+  *theta = copysignf(pt, im);
+  *phi = ph;
+}
+
 }  // namespace fast
 }  // namespace nl

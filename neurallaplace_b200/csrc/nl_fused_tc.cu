@@ -2310,11 +2310,14 @@ __global__ void __launch_bounds__(kPrThreads, 2) point_layer1_kernel(PrArgs A) {
     const long long b = valid ? pt / A.T : 0;
     const TimeCtx<float> c = make_time_ctx<float>(P, valid ? __ldg(A.t + pt) : 1.f, nullptr, 0);
     float f0[kPrMaxHalf], f1[kPrMaxHalf];
-#pragma unroll 4  // (independent evaluations: the accurate atan2f / asinf are long dependent chains)
+#pragma unroll 4  // (independent evaluations overlap)
     for (int i = 0; i < kh; ++i) {
       const int k = wg * kh + i;
       float a = 0.f, bb = 0.f;
-      if (valid && k < n) s_features(P, s_point(P, c, k), &a, &bb);
+      if (valid && k < n) {
+        const Cx<float> sp = s_point(P, c, k);
+        fast::sphere_features(sp.re, sp.im, &a, &bb);  // (sphere head only: pr_geom)
+      }
       f0[i] = a;
       f1[i] = bb;
     }
