@@ -157,6 +157,21 @@ int nl_complex_to_sphere(int dtype, int64_t count, const void* s_re, const void*
 int nl_sphere_to_complex(int dtype, int64_t count, const void* theta, const void* phi, void* s_re,
                          void* s_im, void* cuda_stream);
 
+/* ---- training-step tail ------------------------------------
+ * Global-norm gradient clip + Adam update over ONE flat buffer of `count` parameters, two launches:
+ * replaces torch.nn.utils.clip_grad_norm_(params, max_norm) followed by torch.optim.Adam.step()
+ * (examples/simple_demo.py:349-350, experiments/utils.py:70-71; Adam without amsgrad / weight decay).
+ *   params, grads, exp_avg, exp_avg_sq: `count` values each; params / exp_avg / exp_avg_sq are updated in
+ *   place; grads are read, and overwritten with the clipped gradients when write_clipped_grads != 0
+ *   (clip_grad_norm_ scales them in place).  step = 1, 2, ... (bias correction).  max_norm <= 0: no clip.
+ *   scratch: nl_clip_adam_scratch_bytes() bytes; the gradient norm before clipping is left in the double at
+ *   byte offset 8192 of it.                                                                          */
+size_t nl_clip_adam_scratch_bytes(void);
+int nl_clip_adam_step(int dtype, int64_t count, void* params, void* grads, void* exp_avg,
+                      void* exp_avg_sq, double lr, double beta1, double beta2, double eps, int64_t step,
+                      double max_norm, int write_clipped_grads, void* scratch, size_t scratch_bytes,
+                      void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

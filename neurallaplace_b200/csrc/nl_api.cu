@@ -257,4 +257,20 @@ int nl_sphere_to_complex(int dtype, int64_t count, const void* theta, const void
   return sphere(1, dtype, count, theta, phi, s_re, s_im, stream);
 }
 
+size_t nl_clip_adam_scratch_bytes(void) { return nl::clip_adam_scratch_bytes(); }
+
+int nl_clip_adam_step(int dtype, int64_t count, void* params, void* grads, void* exp_avg, void* exp_avg_sq, double lr,
+                      double beta1, double beta2, double eps, int64_t step, double max_norm, int write_clipped_grads,
+                      void* scratch, size_t scratch_bytes, void* stream) {
+  if (dtype != NL_F32 && dtype != NL_F64) return NL_ERR_ENUM;
+  if (count < 0 || step < 1) return NL_ERR_SHAPE;
+  if (count == 0) return NL_OK;
+  if (!params || !grads || !exp_avg || !exp_avg_sq || !scratch) return NL_ERR_NULL;
+  if (scratch_bytes < nl::clip_adam_scratch_bytes()) return NL_ERR_WORKSPACE;
+  g_launches = max_norm > 0.0 ? 2 : 1;
+  cudaError_t e = nl::launch_clip_adam(dtype, count, params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step,
+                                       max_norm, write_clipped_grads, scratch, (cudaStream_t)stream);
+  return e == cudaSuccess ? NL_OK : cuda_fail(e);
+}
+
 }  // extern "C"

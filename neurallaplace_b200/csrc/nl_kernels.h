@@ -75,6 +75,12 @@ size_t dehoog_qd_scratch_bytes(const nl_desc* d, bool bwd);
 cudaError_t launch_dehoog_qd(const nl_desc* d, bool bwd, const void* t, const void* F, const void* gx, void* x,
                              void* dF, void* scratch, cudaStream_t st);
 
+// ---- training-step tail over one flat buffer: global-norm clip + Adam (nl_optim.cu) ----
+size_t clip_adam_scratch_bytes();
+cudaError_t launch_clip_adam(int dtype, int64_t count, void* p, void* g, void* m, void* v, double lr, double beta1,
+                             double beta2, double eps, int64_t step, double max_norm, int write_grad, void* scratch,
+                             cudaStream_t st);
+
 int device_sm_count();
 
 }  // namespace nl

@@ -6,7 +6,7 @@ cd "$(dirname "$0")/.."
 SRC=neurallaplace_b200/csrc
 mkdir -p /tmp/nlprof
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --extended-lambda -DNL_TC_PROFILE ${NL_EXTRA:-}"
-for f in nl_api nl_elementwise nl_fused_simt nl_fused_tc nl_fused_tc2 nl_tc_selftest nl_dehoog_qd; do
+for f in nl_api nl_elementwise nl_fused_simt nl_fused_tc nl_fused_tc2 nl_tc_selftest nl_dehoog_qd nl_optim; do
   nvcc $FLAGS -c $SRC/$f.cu -o /tmp/nlprof/$f.o 2>/dev/null &
 done; wait
 nvcc -shared -o /tmp/nlprof/libnl_b200.so /tmp/nlprof/*.o -lcudart
