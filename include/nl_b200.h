@@ -151,6 +151,14 @@ int nl_line_integrate_backward(const nl_desc* desc, int f_layout, const void* fa
                                const void* grad_x, void* grad_fa, void* grad_fb,
                                void* cuda_stream);
 
+/* Optional scratch for nl_line_integrate_* (they have no workspace argument).  Only the De Hoog family needs any
+ * (F / dL/dF planes + the recurrence's table): nl_line_integrate_scratch_bytes says how much (0 otherwise).
+ * nl_set_scratch registers a caller-owned device buffer for the calling host thread (NULL clears it); the
+ * next line-integrate call uses it when it is large enough, else the library allocates stream-ordered
+ * (cudaMallocAsync), which costs tens of milliseconds per call at the north-star size.                     */
+size_t nl_line_integrate_scratch_bytes(const nl_desc* desc, int pass);
+void nl_set_scratch(void* device_ptr, size_t bytes);
+
 /* ---- sphere maps (transformations.py:28-151), elementwise over `count` values -------- */
 int nl_complex_to_sphere(int dtype, int64_t count, const void* s_re, const void* s_im, void* theta,
                          void* phi, void* cuda_stream);

@@ -40,6 +40,8 @@ EXPORTS = (
     "nl_line_integrate_backward",
     "nl_complex_to_sphere",
     "nl_sphere_to_complex",
+    "nl_line_integrate_scratch_bytes",
+    "nl_set_scratch",
     "nl_clip_adam_scratch_bytes",
     "nl_clip_adam_step",
 )
@@ -117,6 +119,10 @@ def load():
     lib.nl_complex_to_sphere.argtypes = [i32, i64, vp, vp, vp, vp, vp]
     lib.nl_sphere_to_complex.restype = i32
     lib.nl_sphere_to_complex.argtypes = [i32, i64, vp, vp, vp, vp, vp]
+    lib.nl_line_integrate_scratch_bytes.restype = sz
+    lib.nl_line_integrate_scratch_bytes.argtypes = [dp, i32]
+    lib.nl_set_scratch.restype = None
+    lib.nl_set_scratch.argtypes = [vp, sz]
     f64 = ctypes.c_double
     lib.nl_clip_adam_scratch_bytes.restype = sz
     lib.nl_clip_adam_step.restype = i32

@@ -152,6 +152,17 @@ def query_points(consts, t_flat, head, want_s, want_feat, Tper=None):
   return (torch.view_as_complex(s) if want_s else None), feat
 
 
+def _line_scratch(lib, d, which, device):
+  """De Hoog's line integral needs scratch (planes + recurrence table): hand it a buffer from torch's caching
+  allocator instead of letting the library allocate stream-ordered on every call."""
+  need = int(lib.nl_line_integrate_scratch_bytes(ctypes.byref(d), which))
+  if need == 0:
+    return None
+  buf = torch.empty(need, dtype=torch.uint8, device=device)
+  lib.nl_set_scratch(_lib.ptr(buf), need)
+  return buf
+
+
 class LineIntegrateFn(torch.autograd.Function):
   """x[B,T,D] from F[B,T,D,n] given as (theta, phi) / (re, im) planes or an interleaved complex."""
 
@@ -173,8 +184,11 @@ class LineIntegrateFn(torch.autograd.Function):
     tc = t.contiguous()
     Tc = Tper.contiguous() if Tper is not None else None
     x = torch.empty((B, T, D), dtype=dtype, device=dev)
+    scratch = _line_scratch(lib, d, 0, dev)
     st = lib.nl_line_integrate_forward(ctypes.byref(d), layout, _lib.ptr(fac), _lib.ptr(fbc), _lib.ptr(tc),
                                        _lib.ptr(Tc), _lib.ptr(eta), _lib.ptr(x), _lib.stream_ptr())
+    lib.nl_set_scratch(None, 0)
+    del scratch
     _lib.check(st)
     ctx.save_for_backward(fac, fbc, tc, Tc, eta)
     ctx.meta = (consts, layout, t_mode, d)
@@ -188,9 +202,12 @@ class LineIntegrateFn(torch.autograd.Function):
     ga = torch.empty_like(fac)
     gb = torch.empty_like(fbc) if fbc is not None else None
     gxc = gx.contiguous()
+    scratch = _line_scratch(lib, d, 1, gxc.device)
     st = lib.nl_line_integrate_backward(ctypes.byref(d), layout, _lib.ptr(fac), _lib.ptr(fbc), _lib.ptr(tc),
                                         _lib.ptr(Tc), _lib.ptr(eta), _lib.ptr(gxc), _lib.ptr(ga), _lib.ptr(gb),
                                         _lib.stream_ptr())
+    lib.nl_set_scratch(None, 0)
+    del scratch
     _lib.check(st)
     return ga, gb, None, None, None, None, None, None
 

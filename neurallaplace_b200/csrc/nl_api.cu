@@ -257,6 +257,13 @@ int nl_sphere_to_complex(int dtype, int64_t count, const void* theta, const void
   return sphere(1, dtype, count, theta, phi, s_re, s_im, stream);
 }
 
+size_t nl_line_integrate_scratch_bytes(const nl_desc* d, int pass) {
+  if (check_desc(d) || d->B < 0 || d->T < 0 || d->D < 1 || d->n < 1) return 0;
+  if ((int64_t)d->B * d->T == 0) return 0;
+  return nl::line_integrate_scratch_bytes(d, pass != 0);
+}
+void nl_set_scratch(void* ptr, size_t bytes) { nl::set_thread_scratch(ptr, bytes); }
+
 size_t nl_clip_adam_scratch_bytes(void) { return nl::clip_adam_scratch_bytes(); }
 
 int nl_clip_adam_step(int dtype, int64_t count, void* params, void* grads, void* exp_avg, void* exp_avg_sq, double lr,

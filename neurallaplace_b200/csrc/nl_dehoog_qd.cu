@@ -22,6 +22,7 @@ struct QdArgs {
   IltParams<R> P;
   int B, T, D, per_row;
   const R* t;
+  const R* Tper;     // optional per-time-point contour scale (line_integrate_all_multi), indexed like t
   const Cx<R>* F;
   const R* gx;
   R* x;
@@ -45,8 +46,8 @@ __device__ __forceinline__ QdItem<R> qd_item(const QdArgs<R>& A, int64_t item) {
   q.tb = item - (int64_t)q.d * plane;
   q.ti = (int)(q.tb / A.B);
   q.b = (int)(q.tb - (int64_t)q.ti * A.B);
-  const R tv = A.per_row ? A.t[(int64_t)q.b * A.T + q.ti] : A.t[q.ti];
-  q.c = make_time_ctx<R>(A.P, tv, nullptr, 0);
+  const int64_t tidx = A.per_row ? (int64_t)q.b * A.T + q.ti : q.ti;
+  q.c = make_time_ctx<R>(A.P, A.t[tidx], A.Tper, tidx);
   R sn, cs;
   m_sincos((R(kPi) * q.c.t) / q.c.T, &sn, &cs);  // z = exp(i*pi*t/T), inverse_laplace.py:842
   q.z = Cx<R>{cs, sn};
@@ -156,8 +157,8 @@ void sm_launch(const QdArgs<R>& A, int64_t blocks, size_t smem, cudaStream_t st)
 }
 
 template <typename R>
-cudaError_t launch_t(const nl_desc* d, bool bwd, const void* t, const void* F, const void* gx, void* x, void* dF,
-                     void* scratch, cudaStream_t st) {
+cudaError_t launch_t(const nl_desc* d, bool bwd, const void* t, const void* Tper, const void* F, const void* gx,
+                     void* x, void* dF, void* scratch, cudaStream_t st) {
   const int64_t blocks = qd_grid(d, bwd);
   if (blocks == 0) return cudaSuccess;
   QdArgs<R> A{};
@@ -169,7 +170,7 @@ cudaError_t launch_t(const nl_desc* d, bool bwd, const void* t, const void* F, c
   A.P.scale = (R)d->scale;
   A.B = d->B; A.T = d->T; A.D = d->D;
   A.per_row = d->t_mode == NL_T_PER_ROW ? 1 : 0;
-  A.t = (const R*)t; A.F = (const Cx<R>*)F; A.gx = (const R*)gx; A.x = (R*)x; A.dF = (Cx<R>*)dF;
+  A.t = (const R*)t; A.Tper = (const R*)Tper; A.F = (const Cx<R>*)F; A.gx = (const R*)gx; A.x = (R*)x; A.dF = (Cx<R>*)dF;
   A.scratch = (Cx<R>*)(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
   const int th = sm_threads(d);
   if (th == 0) {
@@ -204,9 +205,9 @@ size_t dehoog_qd_scratch_bytes(const nl_desc* d, bool bwd) {
 }
 
 cudaError_t launch_dehoog_qd(const nl_desc* d, bool bwd, const void* t, const void* F, const void* gx, void* x,
-                             void* dF, void* scratch, cudaStream_t st) {
-  return d->dtype == NL_F64 ? launch_t<double>(d, bwd, t, F, gx, x, dF, scratch, st)
-                            : launch_t<float>(d, bwd, t, F, gx, x, dF, scratch, st);
+                             void* dF, void* scratch, cudaStream_t st, const void* Tper) {
+  return d->dtype == NL_F64 ? launch_t<double>(d, bwd, t, Tper, F, gx, x, dF, scratch, st)
+                            : launch_t<float>(d, bwd, t, Tper, F, gx, x, dF, scratch, st);
 }
 
 }  // namespace nl

@@ -2,6 +2,8 @@
 // line-integrate reductions (forward + backward) on explicit F tensors.  These serve the
 // class-level ILT API and arbitrary user laplace_rep_func modules; the fused kernels in
 // nl_fused_simt.cu / nl_fused_tc.cu are the hot path.
+#include <algorithm>
+
 #include "nl_dehoog.cuh"
 #include "nl_kernels.h"
 
@@ -102,18 +104,18 @@ __global__ void line_integrate_kernel(IltParams<R> P, int B, int T, int D, int t
                                       const R* __restrict__ fa, const R* __restrict__ fb,
                                       const R* __restrict__ t, const R* __restrict__ Tper,
                                       const R* __restrict__ gx, R* __restrict__ x, R* __restrict__ ga,
-                                      R* __restrict__ gb, Cx<R>* scratch, int64_t scratch_stride) {
+                                      R* __restrict__ gb) {
   const int n = P.n;
   const int64_t items = (int64_t)B * T * D;
   FView<R> F{fa, fb, layout, NL_HEAD_SPHERE};
-  // grid-stride so the DeHoog scratch (one slot per launched thread) stays bounded
+  // (De Hoog does not come here: launch_line_integrate hands it to the recurrence kernels of nl_dehoog_qd.cu)
   for (int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; item < items;
        item += (int64_t)gridDim.x * blockDim.x) {
     int64_t row = item / D;
     int64_t tidx = (t_mode == NL_T_PER_ROW) ? row : (row % T);
     TimeCtx<R> c = make_time_ctx(P, t[tidx], Tper, tidx);
     const int64_t off0 = item * n;
-    if (P.family != NL_DEHOOG) {
+    {
       R acc = R(0);
       R g = BWD ? gx[item] * c.pref : R(0);
       for (int k = 0; k < n; ++k) {
@@ -126,27 +128,32 @@ __global__ void line_integrate_kernel(IltParams<R> P, int B, int T, int D, int t
         }
       }
       if (!BWD) x[item] = c.pref * acc;
+    }
+  }
+}
+
+// De Hoog: the recurrence runs in the full-occupancy kernels of nl_dehoog_qd.cu, which work on [d][k][t][b]
+// complex planes.  to_planes: F in the caller's layout -> plane; from_planes: dL/dF plane (already g Re dw, -g Im dw)
+// -> gradient in the caller's layout (chain rule of the sphere angles included).  One thread per (d, k, t, b),
+// b fastest: plane accesses coalesced, caller-layout accesses strided by D*n.
+template <typename R, bool BACK>
+__global__ void dehoog_planes_kernel(int B, int T, int D, int n, int layout, const R* __restrict__ fa,
+                                     const R* __restrict__ fb, Cx<R>* __restrict__ plane_f,
+                                     const Cx<R>* __restrict__ plane_df, R* __restrict__ ga, R* __restrict__ gb) {
+  const int64_t tb_count = (int64_t)T * B;
+  const int64_t total = tb_count * D * n;
+  FView<R> F{fa, fb, layout, NL_HEAD_SPHERE};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t dk = i / tb_count, tb = i - dk * tb_count;
+    const int d = (int)(dk / n), k = (int)(dk - (int64_t)d * n);
+    const int ti = (int)(tb / B), b = (int)(tb - (int64_t)ti * B);
+    const int64_t off = (((int64_t)b * T + ti) * D + d) * n + k;
+    const HeadOut<R> h = F.load(off);
+    if (!BACK) {
+      plane_f[i] = Cx<R>{h.fre, h.fim};
     } else {
-      const int M = (n - 1) / 2;
-      Scratch<R> scr{scratch, scratch_stride, (int64_t)blockIdx.x * blockDim.x + threadIdx.x};
-      R sn, cs;
-      m_sincos((R(kPi) * c.t) / c.T, &sn, &cs);  // z = exp(i*pi*t/T), inverse_laplace.py:842
-      Cx<R> z{cs, sn};
-      auto a = [&](int k) {
-        HeadOut<R> h = F.load(off0 + k);
-        return Cx<R>{h.fre, h.fim};
-      };
-      if (!BWD) {
-        Cx<R> w = dehoog_forward<R>(M, z, a, scr);
-        x[item] = c.pref * w.re;
-      } else {
-        R g = gx[item] * c.pref;
-        auto emit = [&](int k, Cx<R> dw) {
-          HeadOut<R> h = F.load(off0 + k);
-          store_grad(layout, ga, gb, off0 + k, h, g * dw.re, -g * dw.im);
-        };
-        dehoog_forward_backward<R>(M, z, a, emit, scr);
-      }
+      const Cx<R> df = plane_df[i];
+      store_grad(layout, ga, gb, off, h, df.re, df.im);
     }
   }
 }
@@ -154,6 +161,22 @@ __global__ void line_integrate_kernel(IltParams<R> P, int B, int T, int D, int t
 // ---------------------------------------------------------------------------------------
 // host-side launchers
 // ---------------------------------------------------------------------------------------
+// Optional caller-owned scratch for the entry points that have no workspace argument (nl_set_scratch): without
+// it the De Hoog line integral allocates stream-ordered, and growing the driver's pool by gigabytes per call
+// costs tens of milliseconds.
+static thread_local void* g_scratch = nullptr;
+static thread_local size_t g_scratch_bytes = 0;
+void set_thread_scratch(void* ptr, size_t bytes) {
+  g_scratch = ptr;
+  g_scratch_bytes = ptr ? bytes : 0;
+}
+size_t line_integrate_scratch_bytes(const nl_desc* d, bool bwd) {
+  if (d->family != NL_DEHOOG) return 0;
+  const size_t rs = d->dtype == NL_F64 ? 16 : 8;
+  const size_t plane_bytes = ((size_t)d->B * d->T * d->D * d->n * rs + 255) / 256 * 256;
+  return plane_bytes * (bwd ? 2 : 1) + dehoog_qd_scratch_bytes(d, bwd) + 512;
+}
+
 template <typename R>
 static IltParams<R> make_params(const nl_desc* d, const void* beta, const void* eta) {
   IltParams<R> P;
@@ -202,31 +225,46 @@ cudaError_t launch_line_integrate(const nl_desc* d, int layout, bool bwd, const 
   if (items == 0) return cudaSuccess;
   int threads = 128;
   int64_t blocks = (items + threads - 1) / threads;
-  Cx<R>* scratch = nullptr;
-  int64_t stride = 0;
   if (d->family == NL_DEHOOG) {
-    // bounded grid; scratch allocated stream-ordered (the split path is not the hot path)
-    int64_t max_blocks = 148 * 8;
-    if (blocks > max_blocks) blocks = max_blocks;
-    stride = blocks * threads;
-    size_t bytes = (size_t)dehoog_scratch_entries(d->n, bwd) * stride * sizeof(Cx<R>);
-    cudaError_t e = cudaMallocAsync((void**)&scratch, bytes, st);
-    if (e != cudaSuccess) return e;
+    // planes + recurrence scratch: the caller's (nl_set_scratch) or allocated stream-ordered -- the one place
+    // the library allocates
+    const size_t plane_bytes = ((size_t)items * d->n * sizeof(Cx<R>) + 255) / 256 * 256;
+    const size_t need = line_integrate_scratch_bytes(d, bwd);
+    unsigned char* buf = nullptr;
+    const bool own = !(g_scratch && g_scratch_bytes >= need);
+    cudaError_t e = cudaSuccess;
+    if (own) {
+      e = cudaMallocAsync((void**)&buf, need, st);
+      if (e != cudaSuccess) return e;
+    } else {
+      buf = (unsigned char*)(((uintptr_t)g_scratch + 255) & ~(uintptr_t)255);
+    }
+    Cx<R>* pf = (Cx<R>*)buf;
+    Cx<R>* pdf = bwd ? (Cx<R>*)(buf + plane_bytes) : nullptr;
+    void* scr = buf + plane_bytes * (bwd ? 2 : 1);
+    const int64_t total = items * d->n;
+    const int cb = (int)std::min<int64_t>((total + 255) / 256, (int64_t)device_sm_count() * 16);
+    dehoog_planes_kernel<R, false><<<cb, 256, 0, st>>>(d->B, d->T, d->D, d->n, layout, (const R*)fa, (const R*)fb, pf,
+                                                      nullptr, nullptr, nullptr);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = launch_dehoog_qd(d, bwd, t, pf, gx, x, pdf, scr, st, Tper);
+    if (e == cudaSuccess && bwd) {
+      dehoog_planes_kernel<R, true><<<cb, 256, 0, st>>>(d->B, d->T, d->D, d->n, layout, (const R*)fa, (const R*)fb,
+                                                       nullptr, pdf, (R*)ga, (R*)gb);
+      e = cudaGetLastError();
+    }
+    const cudaError_t e2 = own ? cudaFreeAsync(buf, st) : cudaSuccess;
+    return e != cudaSuccess ? e : e2;
   }
   if (bwd)
     line_integrate_kernel<R, true><<<(unsigned)blocks, threads, 0, st>>>(
         P, d->B, d->T, d->D, d->t_mode, layout, (const R*)fa, (const R*)fb, (const R*)t, (const R*)Tper,
-        (const R*)gx, nullptr, (R*)ga, (R*)gb, scratch, stride);
+        (const R*)gx, nullptr, (R*)ga, (R*)gb);
   else
     line_integrate_kernel<R, false><<<(unsigned)blocks, threads, 0, st>>>(
         P, d->B, d->T, d->D, d->t_mode, layout, (const R*)fa, (const R*)fb, (const R*)t, (const R*)Tper, nullptr,
-        (R*)x, nullptr, nullptr, scratch, stride);
-  cudaError_t e = cudaGetLastError();
-  if (scratch) {
-    cudaError_t e2 = cudaFreeAsync(scratch, st);
-    if (e == cudaSuccess) e = e2;
-  }
-  return e;
+        (R*)x, nullptr, nullptr);
+  return cudaGetLastError();
 }
 
 template cudaError_t launch_query_points<float>(const nl_desc*, int64_t, const void*, const void*, const void*,

@@ -18,6 +18,9 @@ cudaError_t launch_line_integrate(const nl_desc* d, int layout, bool bwd, const 
                                   const void* t, const void* Tper, const void* eta, const void* gx, void* x,
                                   void* ga, void* gb, cudaStream_t st);
 
+void set_thread_scratch(void* ptr, size_t bytes);
+size_t line_integrate_scratch_bytes(const nl_desc* d, bool bwd);
+
 // ---- fused SIMT path (any dtype / family / t_mode; nl_fused_simt.cu) ----
 struct SimtPlan {
   int ok;            // 0 => shape not supported by the fused SIMT kernels
@@ -73,7 +76,7 @@ cudaError_t launch_fused_tc_dehoog(const nl_desc* d, bool bwd, const void* p, co
                                    cudaStream_t st, int* launches, void* saved);
 size_t dehoog_qd_scratch_bytes(const nl_desc* d, bool bwd);
 cudaError_t launch_dehoog_qd(const nl_desc* d, bool bwd, const void* t, const void* F, const void* gx, void* x,
-                             void* dF, void* scratch, cudaStream_t st);
+                             void* dF, void* scratch, cudaStream_t st, const void* Tper = nullptr);
 
 // ---- training-step tail over one flat buffer: global-norm clip + Adam (nl_optim.cu) ----
 size_t clip_adam_scratch_bytes();
