@@ -51,6 +51,34 @@ def test_workspace_and_impl_queries():
   assert lib.nl_reconstruct_forward(ctypes.byref(d), None, None, None, None, None, None, None, 0, None) == -1
 
 
+def test_dehoog_and_optimizer_queries():
+  """Host-side contract of the entry points added for De Hoog and the training-step tail (no compute calls)."""
+  lib = _lib.load()
+  d = _lib.NlDesc()
+  d.B, d.T, d.K, d.H, d.D, d.n = 4096, 1024, 2, 64, 1, 33
+  d.family = _lib.NL_FOURIER if hasattr(_lib, "NL_FOURIER") else 0
+  assert lib.nl_line_integrate_scratch_bytes(ctypes.byref(d), 0) == 0  # only De Hoog needs scratch
+  d.family = 2  # NL_DEHOOG
+  planes = 4096 * 1024 * 33 * 8
+  fwd = lib.nl_line_integrate_scratch_bytes(ctypes.byref(d), 0)
+  bwd = lib.nl_line_integrate_scratch_bytes(ctypes.byref(d), 1)
+  assert planes <= fwd < 2 * planes and bwd > 2 * planes  # F plane; F + dL/dF planes + the recurrence's table
+  # De Hoog on the tensor-core path keeps F behind the activation stash; float64 and per-row grids do not use it
+  assert lib.nl_selected_impl(ctypes.byref(d), 0) == 2 and lib.nl_selected_impl(ctypes.byref(d), 1) == 2
+  assert lib.nl_saved_bytes(ctypes.byref(d)) > 4096 * 1024 * (512 + 33 * 8)
+  d.dtype = 1
+  assert lib.nl_selected_impl(ctypes.byref(d), 1) == 1 and lib.nl_saved_bytes(ctypes.byref(d)) == 0
+  d.dtype = 0
+  d.n = 34  # De Hoog needs an odd number of terms
+  assert lib.nl_selected_impl(ctypes.byref(d), 0) == 0
+  lib.nl_set_scratch(None, 0)
+  assert lib.nl_clip_adam_scratch_bytes() >= 8200
+  assert lib.nl_clip_adam_step(5, 10, None, None, None, None, 1e-3, 0.9, 0.999, 1e-8, 1, 1.0, 1, None, 0, None) == -6
+  assert lib.nl_clip_adam_step(0, 10, None, None, None, None, 1e-3, 0.9, 0.999, 1e-8, 0, 1.0, 1, None, 0, None) == -2
+  assert lib.nl_clip_adam_step(0, 10, None, None, None, None, 1e-3, 0.9, 0.999, 1e-8, 1, 1.0, 1, None, 0, None) == -1
+  assert lib.nl_clip_adam_step(0, 0, None, None, None, None, 1e-3, 0.9, 0.999, 1e-8, 1, 1.0, 1, None, 0, None) == 0
+
+
 def test_check_inputs_error_contract():
   f = LaplaceRepresentationFunc(33, 1, 2)
   p, t = torch.zeros(2, 2), torch.ones(3)
