@@ -89,11 +89,13 @@ __global__ void __launch_bounds__(THREADS) dehoog_qd_sm_kernel(QdArgs<R> A) {
   const int64_t plane = (int64_t)A.T * A.B;
   const int64_t items = plane * A.D;
   const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  Cx<R>* tabp = A.scratch + slot;
-  const int64_t stride = A.stride;
+  char* tabp = reinterpret_cast<char*>(A.scratch + slot);
+  // byte stride between table entries of one thread: < 2^32 (at most a few hundred thousand resident threads), so
+  // an entry address is ONE 32x32->64 multiply-add
+  const uint32_t sb = (uint32_t)(A.stride * (int64_t)sizeof(Cx<R>));
   auto col = [&](int i) -> Cx<R>& { return strip[i * THREADS]; };
-  auto tab = [&](int i) -> Cx<R>& { return tabp[(int64_t)i * stride]; };
-  auto pf = [&](int i) { asm volatile("prefetch.global.L2 [%0];" ::"l"(tabp + (int64_t)i * stride)); };
+  auto tab = [&](int i) -> Cx<R>& { return *reinterpret_cast<Cx<R>*>(tabp + (uint64_t)(uint32_t)i * sb); };
+  auto pf = [&](int i) { asm volatile("prefetch.global.L2 [%0];" ::"l"(tabp + (uint64_t)(uint32_t)i * sb)); };
   for (int64_t item = slot; item < items; item += (int64_t)gridDim.x * blockDim.x) {
     const QdItem<R> q = qd_item(A, item);
     const Cx<R>* Fp = A.F + (int64_t)q.d * n * plane + q.tb;

@@ -2051,6 +2051,18 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcAr
     const int ncols_real = min(NP, (2 * A.kc + 3) & ~3);
     const int cw = (((ncols_real + 1) / 2) + 3) & ~3;
     (void)kGPre;
+    // De Hoog: the dL/dF entries this thread reads in the head stage of the NEXT tile, pulled into L2 one tile ahead
+    auto prefetch_df = [&](int ti, int bi) {
+      const int bn = bi * kRows + r;
+      if (bn < A.B) {
+        const float2* base = A.dfin + ((size_t)ti * A.B + bn);
+        for (int c0 = wg * cw; c0 < min((wg + 1) * cw, ncols_real); c0 += 2) {
+          const int k = c0 >> 1;
+          if (k < A.n) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)k * A.f_plane));
+        }
+      }
+    };
+    if (DH && tile_lo < tile_hi) prefetch_df(t_cur, b_cur);
 
     for (long long tile = tile_lo; tile < tile_hi; ++tile) {
       const int t_idx = t_cur;
@@ -2064,7 +2076,10 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcAr
 #pragma unroll
       for (int j = 0; j < KP; ++j) pv[j] = pv_n[j];
       const float g = g_n;
-      if (tile + 1 < tile_hi) prefetch(t_cur, b_cur);
+      if (tile + 1 < tile_hi) {
+        prefetch(t_cur, b_cur);
+        if (DH) prefetch_df(t_cur, b_cur);
+      }
 
       if (t_idx == cur_t && slot_tiles % kFlushTiles == 0) flush_slot();  // bounded D1 chain within a long slot
       if (t_idx != cur_t) {
