@@ -653,7 +653,7 @@ TcPlan tc2_plan(const nl_desc* d, int pass) {
   if (d->family != NL_FOURIER && d->family != NL_AW) return pl;
   if (d->K < 1 || d->K > 7 || d->n < 1 || d->D < 1) return pl;
   if ((long long)d->B * d->T <= 0) return pl;
-  if (d->impl == 0 && d->B < 64) return pl;
+  if (d->impl == 0 && d->B < 16) return pl;
   const Tc2Geom g = tc2_geom(d);
   if (g.nch > 32) return pl;
   const tc2::Tmem tm = tc2::tmem_plan(bwd, g.NP, g.nch);

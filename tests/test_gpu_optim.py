@@ -63,7 +63,7 @@ def test_flat_clip_adam_trains_the_reconstruction():
     loss = ((laplace_reconstruct(f, p, t, recon_dim=1) - target)**2).mean()
     loss.backward()
     opt.step()
-    losses.append(float(loss))
+    losses.append(float(loss.detach()))
   assert losses[-1] < 0.7 * losses[0], losses
   base = opt.flat_param.data_ptr()
   assert all(base <= q.data_ptr() < base + opt.flat_param.numel() * 4 for q in f.parameters())
