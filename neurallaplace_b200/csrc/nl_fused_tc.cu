@@ -2319,11 +2319,23 @@ __global__ void __launch_bounds__(kPrThreads, 2) point_layer1_kernel(PrArgs A) {
                               NPu);
   const int kh = (n + 3) / 4;  // s points per warpgroup
   uint32_t ph = 0;
+  // the time of a point is needed at once (every feature depends on it): loaded one tile ahead
+  auto load_t = [&](long long tl) {
+    const long long q = tl * kRows + r;
+    return (tl < A.ntiles && q < A.N) ? __ldg(A.t + q) : 1.f;
+  };
+  float t_next = load_t(blockIdx.x);
   for (long long tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x) {
     const long long pt = tile * kRows + r;
     const bool valid = pt < A.N;
     const long long b = valid ? pt / A.T : 0;
-    const TimeCtx<float> c = make_time_ctx<float>(P, valid ? __ldg(A.t + pt) : 1.f, nullptr, 0);
+    const float t_cur = t_next;
+    t_next = load_t(tile + gridDim.x);
+    // (p is only stored, after the features: its load overlaps them)
+    float pv[kMaxK];
+#pragma unroll
+    for (int j = 0; j < kMaxK; ++j) pv[j] = (wg == 1 && valid && j < K) ? __ldg(A.p + (size_t)b * K + j) : 0.f;
+    const TimeCtx<float> c = make_time_ctx<float>(P, t_cur, nullptr, 0);
     float f0[kPrMaxHalf], f1[kPrMaxHalf];
 #pragma unroll 4  // (independent evaluations overlap)
     for (int i = 0; i < kh; ++i) {
@@ -2348,10 +2360,12 @@ __global__ void __launch_bounds__(kPrThreads, 2) point_layer1_kernel(PrArgs A) {
       }
     }
     if (wg == 1) {
-      for (int j = 0; j < K; ++j) {
-        const float pj = valid ? __ldg(A.p + (size_t)b * K + j) : 0.f;
-        store_elem(A_hi, A_lo, kRows, r, 2 * n + j, pj);
-        if (valid) A.p_pt[(size_t)pt * K + j] = pj;
+#pragma unroll
+      for (int j = 0; j < kMaxK; ++j) {
+        if (j < K) {
+          store_elem(A_hi, A_lo, kRows, r, 2 * n + j, pv[j]);
+          if (valid) A.p_pt[(size_t)pt * K + j] = pv[j];
+        }
       }
       store_elem(A_hi, A_lo, kRows, r, 2 * n + K, valid ? 1.f : 0.f);
     } else if (valid) {
