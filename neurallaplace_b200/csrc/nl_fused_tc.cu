@@ -839,7 +839,24 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
       if (d_first) xsum = 0.f;
       const float* cf = sCoef + kci * NP;
       const float* bb3 = (!GENERAL || b3_in_smem) ? sb3 + ch * NP : A.b3pack + ch * NP;
-      for (int c0 = wg * cw; c0 < min((wg + 1) * cw, ncols_real); c0 += 4) {
+      int c_lo = wg * cw;
+      const int c_hi = min((wg + 1) * cw, ncols_real);
+      if (!BWD && !DH) {  // forward: eight columns (four head pairs) per TMEM load while they last (measured:
+        // 0.865 -> 0.839 ms against four columns per load; sixteen per load is slower, 0.888 ms)
+        for (; c_lo + 8 <= c_hi; c_lo += 8) {
+          float v[8];
+          tmem_ld8(lane_addr + TM.O + c_lo, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int c = c_lo + 2 * i;
+            const fast::Head h = fast::head_forward(P.head, v[2 * i] + bb3[c], v[2 * i + 1] + bb3[c + 1]);
+            xsum = fmaf(h.fre, cf[c], xsum);
+            xsum = fmaf(-h.fim, cf[c + 1], xsum);
+          }
+        }
+      }
+      for (int c0 = c_lo; c0 < c_hi; c0 += 4) {
         float v[4], dv[4];
         tmem_ld4(lane_addr + TM.O + c0, v);
         tmem_ld_wait();
