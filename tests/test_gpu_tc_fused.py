@@ -110,3 +110,27 @@ def test_tc_dehoog_against_oracle(terms, B, T, D, K, sphere, monkeypatch):
     e, eo, es = hp.rel(a, b64), hp.rel(b32, b64), hp.rel(bs, b64)
     print(f"    grad{i}: tc {e:.2e} simt {es:.2e} oracle32 {eo:.2e}")
     assert e <= 10 * max(eo, es) + floor, (i, e, eo, es)
+
+
+def test_tc_dehoog_without_stash_falls_back_for_backward(monkeypatch):
+  """NL_B200_STASH=0: the forward still runs on the tensor cores (F plane in the workspace), the backward has no
+  saved F / activations and runs on the SIMT kernels + the recurrence kernels; same bar as above."""
+  if not torch.cuda.is_available():
+    pytest.skip("no CUDA device")
+  dev = torch.device("cuda", 0)
+  monkeypatch.setenv("NL_B200_STASH", "0")
+  from oracle import nl_oracle as orc
+  terms, B, T, D, K = 33, 96, 6, 1, 2
+  n = orc.IltConsts("dehoog", terms).n
+  g = torch.Generator().manual_seed(11)
+  weights = orc.make_canonical_weights(n, D, K, seed=7)
+  p = torch.randn(B, K, generator=g)
+  t = torch.linspace(0.5, 10.0, T)
+  gout = torch.randn(B, T, D, generator=g)
+  x32, g32 = hp.oracle_run(weights, p, t, D, "dehoog", True, terms, None, gout)
+  x64, g64 = hp.oracle_run([w.double() for w in weights], p.double(), t.double(), D, "dehoog", True, terms, None,
+                           gout.double())
+  x, grads = _run_product(weights, p, t, D, "dehoog", True, terms, None, gout, dev)
+  assert hp.rel(x, x64) <= 10 * hp.rel(x32, x64) + 1e-5
+  for a, b32, b64 in zip(grads, g32, g64):
+    assert hp.rel(a, b64) <= 10 * hp.rel(b32, b64) + 1e-4
