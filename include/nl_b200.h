@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define NL_B200_ABI_VERSION 2
+#define NL_B200_ABI_VERSION 3
 
 typedef enum nl_status {
   NL_OK = 0,
@@ -151,13 +151,30 @@ int nl_line_integrate_backward(const nl_desc* desc, int f_layout, const void* fa
                                const void* grad_x, void* grad_fa, void* grad_fb,
                                void* cuda_stream);
 
-/* Optional scratch for nl_line_integrate_* (they have no workspace argument).  Only the De Hoog family needs any
+/* Scratch for nl_line_integrate_* (they have no workspace argument).  Only the De Hoog family needs any
  * (F / dL/dF planes + the recurrence's table): nl_line_integrate_scratch_bytes says how much (0 otherwise).
- * nl_set_scratch registers a caller-owned device buffer for the calling host thread (NULL clears it); the
- * next line-integrate call uses it when it is large enough, else the library allocates stream-ordered
- * (cudaMallocAsync), which costs tens of milliseconds per call at the north-star size.                     */
+ * nl_set_scratch registers a caller-owned device buffer for the calling host thread (NULL clears it); a
+ * De Hoog line-integrate call without a large enough registered buffer returns NL_ERR_WORKSPACE (the library
+ * never allocates).                                                                                        */
 size_t nl_line_integrate_scratch_bytes(const nl_desc* desc, int pass);
 void nl_set_scratch(void* device_ptr, size_t bytes);
+
+/* ---- fixed-contour De Hoog ----------------------------------
+ * Replaces DeHoog.fixed_line_integrate (inverse_laplace.py:587-701): ONE contour F[rows][n] complex (the
+ * Laplace representation at the s points of DeHoog.compute_fixed_s(time_max), l.567-585), evaluated at every
+ * t[T]:  x[row][i] = exp(gamma t_i) / contour_T * Re(A / B)(z_i),  z_i = exp(i pi t_i / contour_T).
+ * The quotient-difference table is built once per row, only the Pade recurrence runs per time point.
+ *   contour_T = scale * time_max and gamma = alpha - log(tol) / (scale * contour_T), both ALREADY rounded
+ *   to float32 as the reference computes them there (l.640-642), passed as doubles.
+ *   backward writes grad_F[rows][n] (complex interleaved: d/dRe, d/dIm) of sum(grad_x * x), grad_x[rows][T].
+ *   scratch: nl_dehoog_fixed_scratch_bytes(dtype, rows, n, T, pass) bytes, caller-owned (pass 0 fwd, 1 bwd). */
+size_t nl_dehoog_fixed_scratch_bytes(int dtype, int64_t rows, int n, int64_t T, int pass);
+int nl_dehoog_fixed_forward(int dtype, int64_t rows, int n, int64_t T, const void* F, const void* t,
+                            double contour_T, double gamma, void* x, void* scratch, size_t scratch_bytes,
+                            void* cuda_stream);
+int nl_dehoog_fixed_backward(int dtype, int64_t rows, int n, int64_t T, const void* F, const void* t,
+                             double contour_T, double gamma, const void* grad_x, void* grad_F, void* scratch,
+                             size_t scratch_bytes, void* cuda_stream);
 
 /* ---- sphere maps (transformations.py:28-151), elementwise over `count` values -------- */
 int nl_complex_to_sphere(int dtype, int64_t count, const void* s_re, const void* s_im, void* theta,

@@ -50,6 +50,17 @@ class Consts:
     return self._dev[key]
 
 
+class FixedContour:
+  """Fourier-type contour with a given abscissa (DeHoog.compute_fixed_s): what `_ops._desc` reads."""
+
+  def __init__(self, base, gamma):
+    self.n, self.family, self.scale = base.n, base.family, base.scale
+    self.alpha, self.log_tol = float(gamma), 0.0
+
+  def tables_on(self, device):
+    return None, None
+
+
 def _f32(x):
   return torch.tensor([x], dtype=torch.float32)
 

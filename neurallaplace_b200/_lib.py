@@ -42,6 +42,9 @@ EXPORTS = (
     "nl_sphere_to_complex",
     "nl_line_integrate_scratch_bytes",
     "nl_set_scratch",
+    "nl_dehoog_fixed_scratch_bytes",
+    "nl_dehoog_fixed_forward",
+    "nl_dehoog_fixed_backward",
     "nl_clip_adam_scratch_bytes",
     "nl_clip_adam_step",
 )
@@ -124,6 +127,12 @@ def load():
     lib.nl_set_scratch.restype = None
     lib.nl_set_scratch.argtypes = [vp, sz]
     f64 = ctypes.c_double
+    lib.nl_dehoog_fixed_scratch_bytes.restype = sz
+    lib.nl_dehoog_fixed_scratch_bytes.argtypes = [i32, i64, i32, i64, i32]
+    lib.nl_dehoog_fixed_forward.restype = i32
+    lib.nl_dehoog_fixed_forward.argtypes = [i32, i64, i32, i64, vp, vp, f64, f64, vp, vp, sz, vp]
+    lib.nl_dehoog_fixed_backward.restype = i32
+    lib.nl_dehoog_fixed_backward.argtypes = [i32, i64, i32, i64, vp, vp, f64, f64, vp, vp, vp, sz, vp]
     lib.nl_clip_adam_scratch_bytes.restype = sz
     lib.nl_clip_adam_step.restype = i32
     lib.nl_clip_adam_step.argtypes = [i32, i64, vp, vp, vp, vp, f64, f64, f64, f64, i64, f64, i32, vp, sz, vp]
@@ -159,8 +168,16 @@ def ptr(t):
   return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
 
-def stream_ptr():
-  return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+def stream_ptr(device=None):
+  """Current torch stream of ``device`` (default: the current device) as the ABI's ``void* cuda_stream``."""
+  return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def on(device):
+  """Context that makes ``device`` the current CUDA device for a C-ABI call: the library launches on the
+  current device (kernel attributes, SM count, launches), so every call site enters this with the device of
+  its tensors and passes ``stream_ptr(device)``."""
+  return torch.cuda.device(device)
 
 
 def ptr_array(tensors):

@@ -9,6 +9,7 @@ import ctypes
 import os
 
 import torch
+from torch.autograd.function import once_differentiable
 
 from . import _lib
 from ._lib import NlDesc
@@ -36,7 +37,8 @@ def _desc(consts, dtype, B=0, T=0, K=1, H=1, D=1, t_mode=0, head=0, impl=0, n=No
 
 
 def _workspace(lib, d, which, device):
-  nbytes = lib.nl_workspace_bytes(ctypes.byref(d), which)
+  with _lib.on(device):
+    nbytes = lib.nl_workspace_bytes(ctypes.byref(d), which)
   return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device), nbytes
 
 
@@ -47,7 +49,7 @@ class ReconstructFn(torch.autograd.Function):
   """x = laplace_reconstruct(canonical MLP, p, t) as ONE fused forward and ONE fused backward."""
 
   @staticmethod
-  def forward(ctx, p, t, W1, b1, W2, b2, W3, b3, consts, D, t_mode, head, impl):
+  def forward(ctx, p, t, W1, b1, W2, b2, W3, b3, consts, D, t_mode, head, impl, stash=True):
     lib = _lib.load()
     dev = p.device
     B, K = p.shape
@@ -61,19 +63,26 @@ class ReconstructFn(torch.autograd.Function):
     pc, tc = p.contiguous(), t.contiguous()
     # Training: keep the two hidden activations for backward (the analogue of autograd's saved tensors,
     # 512 B per (b,t) point) so that backward does not recompute layers 1-2.  NL_B200_STASH=0 disables it.
+    # ``stash`` is decided by the caller (grad mode on AND something requires grad): ctx.needs_input_grad stays
+    # True under torch.no_grad() and would make inference pay for the stash.  Above NL_B200_STASH_MAX_GB
+    # (default: 60 % of the free device memory) or when the allocation fails, backward recomputes instead.
     saved, saved_bytes = None, 0
-    if any(ctx.needs_input_grad) and os.environ.get("NL_B200_STASH", "1") != "0":
+    if stash and any(ctx.needs_input_grad) and os.environ.get("NL_B200_STASH", "1") != "0":
       saved_bytes = int(lib.nl_saved_bytes(ctypes.byref(d)))
-      if saved_bytes:
-        saved = torch.empty(saved_bytes, dtype=torch.uint8, device=dev)
-    if saved is not None:
-      st = lib.nl_reconstruct_forward_save(ctypes.byref(d), _lib.ptr(pc), _lib.ptr(tc), _lib.ptr_array(weights),
-                                           _lib.ptr(beta), _lib.ptr(eta), _lib.ptr(x), _lib.ptr(saved), saved_bytes,
-                                           _lib.ptr(ws), nbytes, _lib.stream_ptr())
-    else:
-      st = lib.nl_reconstruct_forward(ctypes.byref(d), _lib.ptr(pc), _lib.ptr(tc), _lib.ptr_array(weights),
-                                      _lib.ptr(beta), _lib.ptr(eta), _lib.ptr(x), _lib.ptr(ws), nbytes,
-                                      _lib.stream_ptr())
+      if saved_bytes and saved_bytes <= _stash_budget(dev):
+        try:
+          saved = torch.empty(saved_bytes, dtype=torch.uint8, device=dev)
+        except torch.OutOfMemoryError:
+          saved = None
+    with _lib.on(dev):
+      if saved is not None:
+        st = lib.nl_reconstruct_forward_save(ctypes.byref(d), _lib.ptr(pc), _lib.ptr(tc), _lib.ptr_array(weights),
+                                             _lib.ptr(beta), _lib.ptr(eta), _lib.ptr(x), _lib.ptr(saved),
+                                             saved_bytes, _lib.ptr(ws), nbytes, _lib.stream_ptr(dev))
+      else:
+        st = lib.nl_reconstruct_forward(ctypes.byref(d), _lib.ptr(pc), _lib.ptr(tc), _lib.ptr_array(weights),
+                                        _lib.ptr(beta), _lib.ptr(eta), _lib.ptr(x), _lib.ptr(ws), nbytes,
+                                        _lib.stream_ptr(dev))
     _lib.check(st)
     _stats["launches"] += lib.nl_last_launch_count()
     ctx.save_for_backward(pc, tc, *weights)
@@ -82,6 +91,7 @@ class ReconstructFn(torch.autograd.Function):
     return x
 
   @staticmethod
+  @once_differentiable
   def backward(ctx, gx):
     lib = _lib.load()
     pc, tc, *weights = ctx.saved_tensors
@@ -96,19 +106,31 @@ class ReconstructFn(torch.autograd.Function):
     grads = [torch.empty_like(w) for w in weights] + [torch.empty_like(pc)]
     gxc = gx.contiguous()
     saved = ctx.saved_act
-    if saved is not None:
-      st = lib.nl_reconstruct_backward_saved(ctypes.byref(d), _lib.ptr(pc), _lib.ptr(tc), _lib.ptr_array(weights),
-                                             _lib.ptr(beta), _lib.ptr(eta), _lib.ptr(gxc), _lib.ptr(saved),
-                                             saved.numel(), _lib.ptr_array(grads), _lib.ptr(ws), nbytes,
-                                             _lib.stream_ptr())
-    else:
-      st = lib.nl_reconstruct_backward(ctypes.byref(d), _lib.ptr(pc), _lib.ptr(tc), _lib.ptr_array(weights),
-                                       _lib.ptr(beta), _lib.ptr(eta), _lib.ptr(gxc), _lib.ptr_array(grads),
-                                       _lib.ptr(ws), nbytes, _lib.stream_ptr())
+    with _lib.on(dev):
+      if saved is not None:
+        st = lib.nl_reconstruct_backward_saved(ctypes.byref(d), _lib.ptr(pc), _lib.ptr(tc), _lib.ptr_array(weights),
+                                               _lib.ptr(beta), _lib.ptr(eta), _lib.ptr(gxc), _lib.ptr(saved),
+                                               saved.numel(), _lib.ptr_array(grads), _lib.ptr(ws), nbytes,
+                                               _lib.stream_ptr(dev))
+      else:
+        st = lib.nl_reconstruct_backward(ctypes.byref(d), _lib.ptr(pc), _lib.ptr(tc), _lib.ptr_array(weights),
+                                         _lib.ptr(beta), _lib.ptr(eta), _lib.ptr(gxc), _lib.ptr_array(grads),
+                                         _lib.ptr(ws), nbytes, _lib.stream_ptr(dev))
     _lib.check(st)
     _stats["launches"] += lib.nl_last_launch_count()
     gW1, gb1, gW2, gb2, gW3, gb3, gp = grads
-    return gp, None, gW1, gb1, gW2, gb2, gW3, gb3, None, None, None, None, None
+    return gp, None, gW1, gb1, gW2, gb2, gW3, gb3, None, None, None, None, None, None
+
+
+def _stash_budget(dev):
+  """Largest activation stash (bytes) the training forward may allocate on ``dev``."""
+  cap = os.environ.get("NL_B200_STASH_MAX_GB")
+  if cap is not None:
+    return int(float(cap) * (1 << 30))
+  free, _total = torch.cuda.mem_get_info(dev)
+  # memory torch has cached but not in use is reusable too
+  free += torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
+  return int(0.6 * free)
 
 
 def fused_supported(consts, dtype, B, T, K, H, D, t_mode, head, impl=0):
@@ -146,16 +168,18 @@ def query_points(consts, t_flat, head, want_s, want_feat, Tper=None):
   feat = torch.empty((rows, 2 * consts.n), dtype=dtype, device=dev) if want_feat else None
   tc = t_flat.contiguous()
   Tc = Tper.contiguous() if Tper is not None else None
-  st = lib.nl_query_points(ctypes.byref(d), rows, _lib.ptr(tc), _lib.ptr(Tc), _lib.ptr(beta), _lib.ptr(s),
-                           _lib.ptr(feat), _lib.stream_ptr())
+  with _lib.on(dev):
+    st = lib.nl_query_points(ctypes.byref(d), rows, _lib.ptr(tc), _lib.ptr(Tc), _lib.ptr(beta), _lib.ptr(s),
+                             _lib.ptr(feat), _lib.stream_ptr(dev))
   _lib.check(st)
   return (torch.view_as_complex(s) if want_s else None), feat
 
 
 def _line_scratch(lib, d, which, device):
-  """De Hoog's line integral needs scratch (planes + recurrence table): hand it a buffer from torch's caching
-  allocator instead of letting the library allocate stream-ordered on every call."""
-  need = int(lib.nl_line_integrate_scratch_bytes(ctypes.byref(d), which))
+  """De Hoog's line integral needs scratch (planes + recurrence table): the library never allocates, so it gets a
+  buffer from torch's caching allocator, registered for this host thread for the duration of the call."""
+  with _lib.on(device):
+    need = int(lib.nl_line_integrate_scratch_bytes(ctypes.byref(d), which))
   if need == 0:
     return None
   buf = torch.empty(need, dtype=torch.uint8, device=device)
@@ -185,8 +209,9 @@ class LineIntegrateFn(torch.autograd.Function):
     Tc = Tper.contiguous() if Tper is not None else None
     x = torch.empty((B, T, D), dtype=dtype, device=dev)
     scratch = _line_scratch(lib, d, 0, dev)
-    st = lib.nl_line_integrate_forward(ctypes.byref(d), layout, _lib.ptr(fac), _lib.ptr(fbc), _lib.ptr(tc),
-                                       _lib.ptr(Tc), _lib.ptr(eta), _lib.ptr(x), _lib.stream_ptr())
+    with _lib.on(dev):
+      st = lib.nl_line_integrate_forward(ctypes.byref(d), layout, _lib.ptr(fac), _lib.ptr(fbc), _lib.ptr(tc),
+                                         _lib.ptr(Tc), _lib.ptr(eta), _lib.ptr(x), _lib.stream_ptr(dev))
     lib.nl_set_scratch(None, 0)
     del scratch
     _lib.check(st)
@@ -195,6 +220,7 @@ class LineIntegrateFn(torch.autograd.Function):
     return x
 
   @staticmethod
+  @once_differentiable
   def backward(ctx, gx):
     lib = _lib.load()
     fac, fbc, tc, Tc, eta = ctx.saved_tensors
@@ -202,10 +228,12 @@ class LineIntegrateFn(torch.autograd.Function):
     ga = torch.empty_like(fac)
     gb = torch.empty_like(fbc) if fbc is not None else None
     gxc = gx.contiguous()
-    scratch = _line_scratch(lib, d, 1, gxc.device)
-    st = lib.nl_line_integrate_backward(ctypes.byref(d), layout, _lib.ptr(fac), _lib.ptr(fbc), _lib.ptr(tc),
-                                        _lib.ptr(Tc), _lib.ptr(eta), _lib.ptr(gxc), _lib.ptr(ga), _lib.ptr(gb),
-                                        _lib.stream_ptr())
+    dev = fac.device
+    scratch = _line_scratch(lib, d, 1, dev)
+    with _lib.on(dev):
+      st = lib.nl_line_integrate_backward(ctypes.byref(d), layout, _lib.ptr(fac), _lib.ptr(fbc), _lib.ptr(tc),
+                                          _lib.ptr(Tc), _lib.ptr(eta), _lib.ptr(gxc), _lib.ptr(ga), _lib.ptr(gb),
+                                          _lib.stream_ptr(dev))
     lib.nl_set_scratch(None, 0)
     del scratch
     _lib.check(st)
@@ -216,13 +244,62 @@ def line_integrate(consts, fa, fb, t, Tper, layout, t_mode, eta_override=None):
   return LineIntegrateFn.apply(fa, fb, t, Tper, consts, layout, t_mode, eta_override)
 
 
+class DehoogFixedFn(torch.autograd.Function):
+  """x[rows, T] for ONE De Hoog contour per row: F[rows, n, 2] (interleaved complex), t[T]
+  (DeHoog.fixed_line_integrate, inverse_laplace.py:587-701; nl_dehoog_fixed_forward/backward)."""
+
+  @staticmethod
+  def forward(ctx, F, t, contour_T, gamma):
+    lib = _lib.load()
+    dev, dtype = F.device, F.dtype
+    rows, n, _two = F.shape
+    Tn = t.numel()
+    Fc, tc = F.contiguous(), t.contiguous()
+    x = torch.empty((rows, Tn), dtype=dtype, device=dev)
+    code = _lib.dtype_code(dtype)
+    with _lib.on(dev):
+      need = int(lib.nl_dehoog_fixed_scratch_bytes(code, rows, n, Tn, 0))
+      scratch = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
+      st = lib.nl_dehoog_fixed_forward(code, rows, n, Tn, _lib.ptr(Fc), _lib.ptr(tc), contour_T, gamma, _lib.ptr(x),
+                                       _lib.ptr(scratch), need, _lib.stream_ptr(dev))
+    _lib.check(st)
+    ctx.save_for_backward(Fc, tc)
+    ctx.meta = (contour_T, gamma)
+    return x
+
+  @staticmethod
+  @once_differentiable
+  def backward(ctx, gx):
+    lib = _lib.load()
+    Fc, tc = ctx.saved_tensors
+    contour_T, gamma = ctx.meta
+    dev = Fc.device
+    rows, n, _two = Fc.shape
+    Tn = tc.numel()
+    gF = torch.empty_like(Fc)
+    gxc = gx.contiguous()
+    code = _lib.dtype_code(Fc.dtype)
+    with _lib.on(dev):
+      need = int(lib.nl_dehoog_fixed_scratch_bytes(code, rows, n, Tn, 1))
+      scratch = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
+      st = lib.nl_dehoog_fixed_backward(code, rows, n, Tn, _lib.ptr(Fc), _lib.ptr(tc), contour_T, gamma,
+                                        _lib.ptr(gxc), _lib.ptr(gF), _lib.ptr(scratch), need, _lib.stream_ptr(dev))
+    _lib.check(st)
+    return gF, None, None, None
+
+
+def dehoog_fixed(F, t, contour_T, gamma):
+  return DehoogFixedFn.apply(F, t, float(contour_T), float(gamma))
+
+
 def sphere_map(which, a, b):
   """which=0: (s_re, s_im) -> (theta, phi);  which=1: (theta, phi) -> (s_re, s_im).  Flat, no grad."""
   lib = _lib.load()
   ac, bc = a.contiguous(), b.contiguous()
   o0, o1 = torch.empty_like(ac), torch.empty_like(bc)
   fn = lib.nl_complex_to_sphere if which == 0 else lib.nl_sphere_to_complex
-  st = fn(_lib.dtype_code(ac.dtype), ac.numel(), _lib.ptr(ac), _lib.ptr(bc), _lib.ptr(o0), _lib.ptr(o1),
-          _lib.stream_ptr())
+  with _lib.on(ac.device):
+    st = fn(_lib.dtype_code(ac.dtype), ac.numel(), _lib.ptr(ac), _lib.ptr(bc), _lib.ptr(o0), _lib.ptr(o1),
+            _lib.stream_ptr(ac.device))
   _lib.check(st)
   return o0, o1

@@ -67,9 +67,17 @@ def _head_kind(f, layers):
   with both canonical heads -- a module with the same attributes but a different forward is
   therefore never silently replaced by the fused kernel.
   """
-  kind = getattr(type(f), "_nl_head", None)
-  if kind in ("sphere", "raw"):
-    return kind
+  # The declaration of the shipped classes is honoured only for the shipped forward itself: a subclass that
+  # overrides forward, an instance whose phi_scale was changed (the kernel hard-codes pi) or a module with
+  # forward hooks goes through the probe / the split path like any user module.
+  from . import rep_func
+  if f._forward_hooks or f._forward_pre_hooks or getattr(f, "_forward_hooks_with_kwargs", None):
+    return None
+  shipped = {rep_func.LaplaceRepresentationFunc.forward: "sphere", rep_func.SurfaceModel.forward: "raw"}
+  kind = shipped.get(type(f).forward)
+  if kind is not None and kind == type(f).__dict__.get("_nl_head", getattr(type(f), "_nl_head", None)):
+    if kind == "raw" or getattr(f, "phi_scale", None) == torch.pi:
+      return kind
   try:
     return _canonical_cache[f]
   except (KeyError, TypeError):
@@ -180,7 +188,10 @@ def laplace_reconstruct(
       ws = [w if w.device == dev else w.to(dev) for w in (l1.weight, l1.bias, l2.weight, l2.bias, l3.weight, l3.bias)]
       if hasattr(laplace_rep_func, "nfe"):
         laplace_rep_func.nfe += 1
-      x = _ops.ReconstructFn.apply(pd, td, *ws, consts, recon_dim, t_mode, head, 0)
+      # keep the activation stash only when a backward can follow (needs_input_grad alone stays
+      # True under torch.no_grad())
+      stash = torch.is_grad_enabled() and (pd.requires_grad or any(w.requires_grad for w in ws))
+      x = _ops.ReconstructFn.apply(pd, td, *ws, consts, recon_dim, t_mode, head, 0, stash)
       return x if home == dev else x.to(home)
 
   # ---- split path: kernel A -> user module -> kernel B

@@ -57,7 +57,7 @@ const char* nl_strerror(int status) {
     case NL_ERR_NULL: return "required pointer is NULL";
     case NL_ERR_SHAPE: return "invalid dimension";
     case NL_ERR_UNSUPPORTED: return "shape not covered by the fused kernels (use the split path)";
-    case NL_ERR_WORKSPACE: return "workspace too small";
+    case NL_ERR_WORKSPACE: return "workspace / scratch missing or too small";
     case NL_ERR_CUDA: return "CUDA runtime error";
     case NL_ERR_ENUM: return "invalid enum value in nl_desc";
     default: return "unknown nl_status";
@@ -220,6 +220,8 @@ static int line_integrate(const nl_desc* d, int layout, bool bwd, const void* fa
   if (!fa || !t || (planar && !fb)) return NL_ERR_NULL;
   if (d->family == NL_AW && !eta) return NL_ERR_NULL;
   if (bwd ? (!gx || !ga || (planar && !gb)) : !x) return NL_ERR_NULL;
+  // De Hoog needs caller-owned scratch (nl_set_scratch): the library never allocates
+  if (nl::thread_scratch_bytes() < nl::line_integrate_scratch_bytes(d, bwd)) return NL_ERR_WORKSPACE;
   cudaError_t e =
       d->dtype == NL_F64
           ? nl::launch_line_integrate<double>(d, layout, bwd, fa, fb, t, Tper, eta, gx, x, ga, gb, (cudaStream_t)stream)
@@ -263,6 +265,40 @@ size_t nl_line_integrate_scratch_bytes(const nl_desc* d, int pass) {
   return nl::line_integrate_scratch_bytes(d, pass != 0);
 }
 void nl_set_scratch(void* ptr, size_t bytes) { nl::set_thread_scratch(ptr, bytes); }
+
+static int dehoog_fixed(int dtype, int64_t rows, int n, int64_t T, bool bwd, const void* F, const void* t,
+                        double contour_T, double gamma, const void* gx, void* x, void* dF, void* scratch,
+                        size_t scratch_bytes, void* stream) {
+  if (dtype != NL_F32 && dtype != NL_F64) return NL_ERR_ENUM;
+  if (rows < 0 || T < 0 || n < 3 || n % 2 == 0) return NL_ERR_SHAPE;
+  if (!(contour_T > 0.0)) return NL_ERR_SHAPE;
+  if (rows == 0 || T == 0) return NL_OK;
+  if (!F || !t || !scratch || (bwd ? (!gx || !dF) : !x)) return NL_ERR_NULL;
+  if (scratch_bytes < nl::dehoog_fixed_scratch_bytes(dtype, rows, n, T, bwd)) return NL_ERR_WORKSPACE;
+  g_launches = bwd ? 3 : 2;
+  cudaError_t e = nl::launch_dehoog_fixed(dtype, rows, n, T, bwd, F, t, contour_T, gamma, gx, x, dF, scratch,
+                                          (cudaStream_t)stream);
+  return e == cudaSuccess ? NL_OK : cuda_fail(e);
+}
+
+size_t nl_dehoog_fixed_scratch_bytes(int dtype, int64_t rows, int n, int64_t T, int pass) {
+  if ((dtype != NL_F32 && dtype != NL_F64) || rows <= 0 || T <= 0 || n < 3 || n % 2 == 0) return 0;
+  return nl::dehoog_fixed_scratch_bytes(dtype, rows, n, T, pass != 0);
+}
+
+int nl_dehoog_fixed_forward(int dtype, int64_t rows, int n, int64_t T, const void* F, const void* t,
+                            double contour_T, double gamma, void* x, void* scratch, size_t scratch_bytes,
+                            void* stream) {
+  return dehoog_fixed(dtype, rows, n, T, false, F, t, contour_T, gamma, nullptr, x, nullptr, scratch, scratch_bytes,
+                      stream);
+}
+
+int nl_dehoog_fixed_backward(int dtype, int64_t rows, int n, int64_t T, const void* F, const void* t,
+                             double contour_T, double gamma, const void* grad_x, void* grad_F, void* scratch,
+                             size_t scratch_bytes, void* stream) {
+  return dehoog_fixed(dtype, rows, n, T, true, F, t, contour_T, gamma, grad_x, nullptr, grad_F, scratch,
+                      scratch_bytes, stream);
+}
 
 size_t nl_clip_adam_scratch_bytes(void) { return nl::clip_adam_scratch_bytes(); }
 

@@ -22,6 +22,8 @@ struct Scratch {
   int64_t stride;
   int64_t slot;
   NL_HD Cx<R>& operator[](int idx) const { return base[(int64_t)idx * stride + slot]; }
+  // the same slot, `off` entries further on
+  NL_HD Scratch<R> at(int off) const { return Scratch<R>{base + (int64_t)off * stride, stride, slot}; }
 };
 
 // number of complex scratch entries per slot
@@ -31,10 +33,18 @@ __host__ __device__ inline int dehoog_scratch_entries(int n, bool backward) {
   return backward ? (2 * M + 1 + 8) * LD : 3 * LD;
 }
 
-// Accessor for a[k]: value k of the Laplace-domain samples F_k of this element.
-// Forward only (two in-place columns).  Returns w = A*/B*.
+// The recurrence comes in parts so that the fixed-contour variant (DeHoog.fixed_line_integrate,
+// inverse_laplace.py:587-701: ONE quotient-difference table per contour, the Pade recurrence per time point)
+// runs exactly the same arithmetic as the per-element kernels:
+//   dehoog_qd_coeffs   : a_k -> d_0..d_2M, two in-place columns                  (forward only)
+//   dehoog_pade        : d, z -> w = A*/B*                                          (forward only)
+//   dehoog_qd_store    : a_k -> every q^r / e^r column + d                          (kept for the reverse sweep)
+//   dehoog_pade_fwd_bwd: d, z -> w and dw/dd_i                                      (A_i, B_i history kept)
+//   dehoog_qd_reverse  : dw/dd_i -> dw/da_k through the stored columns
+
+// a[k]: value k of the Laplace-domain samples F_k.  Writes d_0..d_2M to scr[2 LD + i]; scr needs 3 LD entries.
 template <typename R, typename AFn>
-__host__ __device__ Cx<R> dehoog_forward(int M, Cx<R> z, AFn a, Scratch<R> scr) {
+__host__ __device__ void dehoog_qd_coeffs(int M, AFn a, Scratch<R> scr) {
   const int LD = 2 * M + 2;
   const int Q = 0, E = LD, Dd = 2 * LD;  // q[2M], e[2M+1], d[2M+1]
   const Cx<R> half_a0 = cscale(a(0), R(0.5));
@@ -51,15 +61,21 @@ __host__ __device__ Cx<R> dehoog_forward(int M, Cx<R> z, AFn a, Scratch<R> scr) 
       for (int i = 0; i < mr; ++i) scr[Q + i] = cdiv(cmul(scr[Q + i + 1], scr[E + i + 1]), scr[E + i]);
     }
   }
-  Cx<R> Am1 = {R(0), R(0)}, A = scr[Dd + 0], Bm1 = {R(1), R(0)}, B = {R(1), R(0)};
+}
+
+// Pade recurrence with the improved remainder for one z; d(i) returns d_i.
+template <typename R, typename DFn>
+__host__ __device__ Cx<R> dehoog_pade(int M, Cx<R> z, DFn d) {
+  Cx<R> Am1 = {R(0), R(0)}, A = d(0), Bm1 = {R(1), R(0)}, B = {R(1), R(0)};
   for (int i = 1; i < 2 * M; ++i) {
     // reference order: (d_i * A_{i-2}) * z
-    Cx<R> An = cadd(A, cmul(cmul(scr[Dd + i], Am1), z));
-    Cx<R> Bn = cadd(B, cmul(cmul(scr[Dd + i], Bm1), z));
+    const Cx<R> di = d(i);
+    Cx<R> An = cadd(A, cmul(cmul(di, Am1), z));
+    Cx<R> Bn = cadd(B, cmul(cmul(di, Bm1), z));
     Am1 = A; A = An; Bm1 = B; B = Bn;
   }
   const Cx<R> one = {R(1), R(0)};
-  Cx<R> d2m1 = scr[Dd + 2 * M - 1], d2m = scr[Dd + 2 * M];
+  Cx<R> d2m1 = d(2 * M - 1), d2m = d(2 * M);
   Cx<R> h = cscale(cadd(one, cmul(csub(d2m1, d2m), z)), R(0.5));
   Cx<R> U = cadd(one, cdiv(cmul(d2m, z), cmul(h, h)));
   Cx<R> rem = cmul(cneg(h), csub(one, csqrt(U)));
@@ -68,42 +84,57 @@ __host__ __device__ Cx<R> dehoog_forward(int M, Cx<R> z, AFn a, Scratch<R> scr) 
   return cdiv(As, Bs);
 }
 
-// Forward with the full table kept, then the reverse sweep.  On return ab(k) has been called
-// once per k with dw/da_k (holomorphic derivative); returns w.
-template <typename R, typename AFn, typename GFn>
-__host__ __device__ Cx<R> dehoog_forward_backward(int M, Cx<R> z, AFn a, GFn emit_grad, Scratch<R> scr) {
+// Forward only (two in-place columns).  Returns w = A*/B*.
+template <typename R, typename AFn>
+__host__ __device__ Cx<R> dehoog_forward(int M, Cx<R> z, AFn a, Scratch<R> scr) {
+  dehoog_qd_coeffs<R>(M, a, scr);
+  const Scratch<R> dd = scr.at(2 * (2 * M + 2));
+  return dehoog_pade<R>(M, z, [&](int i) { return dd[i]; });
+}
+
+// Quotient-difference table with every column kept.  tab layout (units of LD = 2M+2):
+//   q^r r=0..M-1 | e^r r=0..M | d        ((2M+2) LD entries)
+template <typename R, typename AFn>
+__host__ __device__ void dehoog_qd_store(int M, AFn a, Scratch<R> tab) {
   const int LD = 2 * M + 2;
-  // layout (in units of LD): q^r r=0..M-1 | e^r r=0..M | d | dbar | A | B | qbA | qbB | ebA | ebB
-  const int Q = 0, E = M * LD, Dd = (2 * M + 1) * LD, Db = Dd + LD, AA = Db + LD, BB = AA + LD;
-  const int QB0 = BB + LD, QB1 = QB0 + LD, EB0 = QB1 + LD, EB1 = EB0 + LD;
-  const Cx<R> zero = {R(0), R(0)}, one = {R(1), R(0)};
+  const int Q = 0, E = M * LD, Dd = (2 * M + 1) * LD;
+  const Cx<R> zero = {R(0), R(0)};
   const Cx<R> half_a0 = cscale(a(0), R(0.5));
-  // ---- forward, storing every column
-  scr[Dd + 0] = half_a0;
-  for (int i = 0; i < 2 * M; ++i) scr[Q + i] = (i == 0) ? cdiv(a(1), half_a0) : cdiv(a(i + 1), a(i));
-  for (int i = 0; i < LD; ++i) scr[E + i] = zero;  // e^0 == 0
+  tab[Dd + 0] = half_a0;
+  for (int i = 0; i < 2 * M; ++i) tab[Q + i] = (i == 0) ? cdiv(a(1), half_a0) : cdiv(a(i + 1), a(i));
+  for (int i = 0; i < LD; ++i) tab[E + i] = zero;  // e^0 == 0
   for (int r = 1; r <= M; ++r) {
     const int mr = 2 * (M - r) + 1;
     const int qp = Q + (r - 1) * LD, ep = E + (r - 1) * LD, ec = E + r * LD, qc = Q + r * LD;
-    for (int i = 0; i < mr; ++i) scr[ec + i] = cadd(csub(scr[qp + i + 1], scr[qp + i]), scr[ep + i + 1]);
-    scr[ec + mr] = zero;
-    scr[Dd + 2 * r - 1] = cneg(scr[qp + 0]);
-    scr[Dd + 2 * r] = cneg(scr[ec + 0]);
+    for (int i = 0; i < mr; ++i) tab[ec + i] = cadd(csub(tab[qp + i + 1], tab[qp + i]), tab[ep + i + 1]);
+    tab[ec + mr] = zero;
+    tab[Dd + 2 * r - 1] = cneg(tab[qp + 0]);
+    tab[Dd + 2 * r] = cneg(tab[ec + 0]);
     if (r < M) {
-      for (int i = 0; i < mr; ++i) scr[qc + i] = cdiv(cmul(scr[qp + i + 1], scr[ec + i + 1]), scr[ec + i]);
+      for (int i = 0; i < mr; ++i) tab[qc + i] = cdiv(cmul(tab[qp + i + 1], tab[ec + i + 1]), tab[ec + i]);
     }
   }
-  Cx<R> Am1 = zero, A = scr[Dd + 0], Bm1 = one, B = one;
-  scr[AA + 0] = A;
-  scr[BB + 0] = B;
+}
+
+// Pade recurrence for one z with the A_i / B_i history kept (hist: A at [0, LD), B at [LD, 2 LD)), then its
+// reverse sweep: dbar[i] = dw/dd_i, i = 0..2M (OVERWRITTEN).  d(i) returns d_i.  Returns w.
+template <typename R, typename DFn>
+__host__ __device__ Cx<R> dehoog_pade_fwd_bwd(int M, Cx<R> z, DFn d, Scratch<R> dbar, Scratch<R> hist) {
+  const int LD = 2 * M + 2;
+  const int AA = 0, BB = LD;
+  const Cx<R> zero = {R(0), R(0)}, one = {R(1), R(0)};
+  Cx<R> Am1 = zero, A = d(0), Bm1 = one, B = one;
+  hist[AA + 0] = A;
+  hist[BB + 0] = B;
   for (int i = 1; i < 2 * M; ++i) {
-    Cx<R> An = cadd(A, cmul(cmul(scr[Dd + i], Am1), z));
-    Cx<R> Bn = cadd(B, cmul(cmul(scr[Dd + i], Bm1), z));
+    const Cx<R> di = d(i);
+    Cx<R> An = cadd(A, cmul(cmul(di, Am1), z));
+    Cx<R> Bn = cadd(B, cmul(cmul(di, Bm1), z));
     Am1 = A; A = An; Bm1 = B; B = Bn;
-    scr[AA + i] = A;
-    scr[BB + i] = B;
+    hist[AA + i] = A;
+    hist[BB + i] = B;
   }
-  Cx<R> d2m1 = scr[Dd + 2 * M - 1], d2m = scr[Dd + 2 * M];
+  Cx<R> d2m1 = d(2 * M - 1), d2m = d(2 * M);
   Cx<R> h = cscale(cadd(one, cmul(csub(d2m1, d2m), z)), R(0.5));
   Cx<R> h2 = cmul(h, h);
   Cx<R> U = cadd(one, cdiv(cmul(d2m, z), h2));
@@ -114,7 +145,7 @@ __host__ __device__ Cx<R> dehoog_forward_backward(int M, Cx<R> z, AFn a, GFn emi
   Cx<R> w = cdiv(As, Bs);
 
   // ---- reverse: Pade part
-  for (int i = 0; i <= 2 * M; ++i) scr[Db + i] = zero;
+  for (int i = 0; i <= 2 * M; ++i) dbar[i] = zero;
   Cx<R> Asb = crecip(Bs);
   Cx<R> Bsb = cneg(cdiv(w, Bs));
   // A* = A_{2M-1} + rem*A_{2M-2}
@@ -130,15 +161,15 @@ __host__ __device__ Cx<R> dehoog_forward_backward(int M, Cx<R> z, AFn a, GFn emi
   hb = csub(hb, cmul(Ub, cdiv(cscale(cmul(d2m, z), R(2)), cmul(h2, h))));
   // h = (1 + (d_{2M-1} - d_{2M}) z)/2
   Cx<R> hz = cscale(cmul(hb, z), R(0.5));
-  scr[Db + 2 * M - 1] = hz;
-  scr[Db + 2 * M] = csub(d2mb, hz);
+  dbar[2 * M - 1] = hz;
+  dbar[2 * M] = csub(d2mb, hz);
   for (int i = 2 * M - 1; i >= 1; --i) {
     // A_i = A_{i-1} + d_i z A_{i-2}
-    Cx<R> Ai2 = (i >= 2) ? scr[AA + i - 2] : zero;
-    Cx<R> Bi2 = (i >= 2) ? scr[BB + i - 2] : one;
-    Cx<R> di = scr[Dd + i];
+    Cx<R> Ai2 = (i >= 2) ? hist[AA + i - 2] : zero;
+    Cx<R> Bi2 = (i >= 2) ? hist[BB + i - 2] : one;
+    Cx<R> di = d(i);
     Cx<R> g = cmul(cadd(cmul(ab1, Ai2), cmul(bb1, Bi2)), z);
-    scr[Db + i] = cadd(scr[Db + i], g);
+    dbar[i] = cadd(dbar[i], g);
     Cx<R> diz = cmul(di, z);
     Cx<R> na = cmul(ab1, diz), nb = cmul(bb1, diz);
     ab0 = cadd(ab0, ab1);
@@ -146,57 +177,81 @@ __host__ __device__ Cx<R> dehoog_forward_backward(int M, Cx<R> z, AFn a, GFn emi
     ab1 = ab0; ab0 = na;
     bb1 = bb0; bb0 = nb;
   }
-  scr[Db + 0] = cadd(scr[Db + 0], ab1);  // A_0 = d_0 ; B_0 = 1 is a constant
+  dbar[0] = cadd(dbar[0], ab1);  // A_0 = d_0 ; B_0 = 1 is a constant
+  return w;
+}
 
-  // ---- reverse: QD table, columns r = M .. 1 with ping-pong adjoint columns
+// Reverse sweep through the stored quotient-difference table (tab: dehoog_qd_store layout): dbar[i] = dw/dd_i
+// in, emit_grad(k, dw/da_k) out, k = 0..2M.  adj: 4 LD entries of ping-pong adjoint columns.
+template <typename R, typename AFn, typename GFn>
+__host__ __device__ void dehoog_qd_reverse(int M, AFn a, GFn emit_grad, Scratch<R> tab, Scratch<R> dbar,
+                                           Scratch<R> adj) {
+  const int LD = 2 * M + 2;
+  const int Q = 0, E = M * LD;
+  const int QB0 = 0, QB1 = LD, EB0 = 2 * LD, EB1 = 3 * LD;
+  const Cx<R> zero = {R(0), R(0)};
+  const Cx<R> half_a0 = cscale(a(0), R(0.5));
   int qb_cur = QB0, qb_prev = QB1, eb_cur = EB0, eb_prev = EB1;
   for (int i = 0; i < LD; ++i) {
-    scr[qb_cur + i] = zero;  // adjoint of q^M (does not exist) -- unused
-    scr[eb_cur + i] = zero;
+    adj[qb_cur + i] = zero;  // adjoint of q^M (does not exist) -- unused
+    adj[eb_cur + i] = zero;
   }
-  scr[eb_cur + 0] = cneg(scr[Db + 2 * M]);  // d_{2M} = -e^M_0
+  adj[eb_cur + 0] = cneg(dbar[2 * M]);  // d_{2M} = -e^M_0
   for (int r = M; r >= 1; --r) {
     const int mr = 2 * (M - r) + 1;
     const int qp = Q + (r - 1) * LD, ec = E + r * LD, qc = Q + r * LD;
     for (int i = 0; i < LD; ++i) {
-      scr[qb_prev + i] = zero;
-      scr[eb_prev + i] = zero;
+      adj[qb_prev + i] = zero;
+      adj[eb_prev + i] = zero;
     }
-    scr[qb_prev + 0] = cneg(scr[Db + 2 * r - 1]);               // d_{2r-1} = -q^{r-1}_0
-    if (r > 1) scr[eb_prev + 0] = cneg(scr[Db + 2 * (r - 1)]);  // d_{2(r-1)} = -e^{r-1}_0
+    adj[qb_prev + 0] = cneg(dbar[2 * r - 1]);               // d_{2r-1} = -q^{r-1}_0
+    if (r > 1) adj[eb_prev + 0] = cneg(dbar[2 * (r - 1)]);  // d_{2(r-1)} = -e^{r-1}_0
     if (r < M) {
       // q^r_i = q^{r-1}_{i+1} * e^r_{i+1} / e^r_i
       for (int i = 0; i < mr; ++i) {
-        Cx<R> g = scr[qb_cur + i];
-        Cx<R> ei = scr[ec + i], ei1 = scr[ec + i + 1], qpi1 = scr[qp + i + 1];
+        Cx<R> g = adj[qb_cur + i];
+        Cx<R> ei = tab[ec + i], ei1 = tab[ec + i + 1], qpi1 = tab[qp + i + 1];
         Cx<R> gi = cdiv(g, ei);
-        scr[qb_prev + i + 1] = cadd(scr[qb_prev + i + 1], cmul(gi, ei1));
-        if (i + 1 < mr) scr[eb_cur + i + 1] = cadd(scr[eb_cur + i + 1], cmul(gi, qpi1));
-        scr[eb_cur + i] = csub(scr[eb_cur + i], cmul(gi, scr[qc + i]));
+        adj[qb_prev + i + 1] = cadd(adj[qb_prev + i + 1], cmul(gi, ei1));
+        if (i + 1 < mr) adj[eb_cur + i + 1] = cadd(adj[eb_cur + i + 1], cmul(gi, qpi1));
+        adj[eb_cur + i] = csub(adj[eb_cur + i], cmul(gi, tab[qc + i]));
       }
     }
     // e^r_i = q^{r-1}_{i+1} - q^{r-1}_i + e^{r-1}_{i+1}
     for (int i = 0; i < mr; ++i) {
-      Cx<R> g = scr[eb_cur + i];
-      scr[qb_prev + i + 1] = cadd(scr[qb_prev + i + 1], g);
-      scr[qb_prev + i] = csub(scr[qb_prev + i], g);
-      if (r > 1) scr[eb_prev + i + 1] = cadd(scr[eb_prev + i + 1], g);
+      Cx<R> g = adj[eb_cur + i];
+      adj[qb_prev + i + 1] = cadd(adj[qb_prev + i + 1], g);
+      adj[qb_prev + i] = csub(adj[qb_prev + i], g);
+      if (r > 1) adj[eb_prev + i + 1] = cadd(adj[eb_prev + i + 1], g);
     }
     int tq = qb_cur; qb_cur = qb_prev; qb_prev = tq;
     int te = eb_cur; eb_cur = eb_prev; eb_prev = te;
   }
   // ---- q^0_i = a_{i+1}/a_i (i>=1), q^0_0 = a_1/(a_0/2) ; d_0 = a_0/2
-  Cx<R> carry = cscale(scr[Db + 0], R(0.5));  // running adjoint of a_i, starts with a_0
+  Cx<R> carry = cscale(dbar[0], R(0.5));  // running adjoint of a_i, starts with a_0
   for (int i = 0; i < 2 * M; ++i) {
-    Cx<R> g = scr[qb_cur + i];
+    Cx<R> g = adj[qb_cur + i];
     Cx<R> den = (i == 0) ? half_a0 : a(i);
     Cx<R> gi = cdiv(g, den);
-    Cx<R> back = cmul(gi, scr[Q + i]);  // d q/d den = -q/den
+    Cx<R> back = cmul(gi, tab[Q + i]);  // d q/d den = -q/den
     if (i == 0) back = cscale(back, R(0.5));
     emit_grad(i, csub(carry, back));
     carry = gi;
   }
   emit_grad(2 * M, carry);
+}
+
+// Forward with the full table kept, then the reverse sweep.  On return emit_grad(k, .) has been called
+// once per k with dw/da_k (holomorphic derivative); returns w.
+template <typename R, typename AFn, typename GFn>
+__host__ __device__ Cx<R> dehoog_forward_backward(int M, Cx<R> z, AFn a, GFn emit_grad, Scratch<R> scr) {
+  const int LD = 2 * M + 2;
+  // layout (in units of LD): q^r r=0..M-1 | e^r r=0..M | d | dbar | A | B | qbA | qbB | ebA | ebB
+  const int Dd = (2 * M + 1) * LD, Db = Dd + LD, AA = Db + LD, QB0 = AA + 2 * LD;
+  dehoog_qd_store<R>(M, a, scr);
+  const Scratch<R> dd = scr.at(Dd);
+  const Cx<R> w = dehoog_pade_fwd_bwd<R>(M, z, [&](int i) { return dd[i]; }, scr.at(Db), scr.at(AA));
+  dehoog_qd_reverse<R>(M, a, emit_grad, scr, scr.at(Db), scr.at(QB0));
   return w;
 }
 

@@ -161,15 +161,15 @@ __global__ void dehoog_planes_kernel(int B, int T, int D, int n, int layout, con
 // ---------------------------------------------------------------------------------------
 // host-side launchers
 // ---------------------------------------------------------------------------------------
-// Optional caller-owned scratch for the entry points that have no workspace argument (nl_set_scratch): without
-// it the De Hoog line integral allocates stream-ordered, and growing the driver's pool by gigabytes per call
-// costs tens of milliseconds.
+// Caller-owned scratch for the entry points that have no workspace argument (nl_set_scratch); the De Hoog line
+// integral needs it (planes + recurrence table) and fails with NL_ERR_WORKSPACE without it.
 static thread_local void* g_scratch = nullptr;
 static thread_local size_t g_scratch_bytes = 0;
 void set_thread_scratch(void* ptr, size_t bytes) {
   g_scratch = ptr;
   g_scratch_bytes = ptr ? bytes : 0;
 }
+size_t thread_scratch_bytes() { return g_scratch_bytes; }
 size_t line_integrate_scratch_bytes(const nl_desc* d, bool bwd) {
   if (d->family != NL_DEHOOG) return 0;
   const size_t rs = d->dtype == NL_F64 ? 16 : 8;
@@ -226,19 +226,12 @@ cudaError_t launch_line_integrate(const nl_desc* d, int layout, bool bwd, const 
   int threads = 128;
   int64_t blocks = (items + threads - 1) / threads;
   if (d->family == NL_DEHOOG) {
-    // planes + recurrence scratch: the caller's (nl_set_scratch) or allocated stream-ordered -- the one place
-    // the library allocates
+    // planes + recurrence scratch come from the caller (nl_set_scratch): the library never allocates
     const size_t plane_bytes = ((size_t)items * d->n * sizeof(Cx<R>) + 255) / 256 * 256;
     const size_t need = line_integrate_scratch_bytes(d, bwd);
-    unsigned char* buf = nullptr;
-    const bool own = !(g_scratch && g_scratch_bytes >= need);
+    if (!(g_scratch && g_scratch_bytes >= need)) return cudaErrorInvalidValue;  // nl_api.cu checks first
+    unsigned char* buf = (unsigned char*)(((uintptr_t)g_scratch + 255) & ~(uintptr_t)255);
     cudaError_t e = cudaSuccess;
-    if (own) {
-      e = cudaMallocAsync((void**)&buf, need, st);
-      if (e != cudaSuccess) return e;
-    } else {
-      buf = (unsigned char*)(((uintptr_t)g_scratch + 255) & ~(uintptr_t)255);
-    }
     Cx<R>* pf = (Cx<R>*)buf;
     Cx<R>* pdf = bwd ? (Cx<R>*)(buf + plane_bytes) : nullptr;
     void* scr = buf + plane_bytes * (bwd ? 2 : 1);
@@ -253,8 +246,7 @@ cudaError_t launch_line_integrate(const nl_desc* d, int layout, bool bwd, const 
                                                        nullptr, pdf, (R*)ga, (R*)gb);
       e = cudaGetLastError();
     }
-    const cudaError_t e2 = own ? cudaFreeAsync(buf, st) : cudaSuccess;
-    return e != cudaSuccess ? e : e2;
+    return e;
   }
   if (bwd)
     line_integrate_kernel<R, true><<<(unsigned)blocks, threads, 0, st>>>(

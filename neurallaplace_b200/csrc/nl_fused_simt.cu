@@ -478,13 +478,16 @@ __global__ void reduce_slabs_kernel(const R* __restrict__ slab, int64_t slab_len
 
 // ---------------------------------------------------------------------------------------
 int device_sm_count() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  // per device: a process may drive several GPUs (the caller makes the tensors' device current)
+  static int sms[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (sms[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    sms[dev] = v;
   }
-  return sms;
+  return sms[dev];
 }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

@@ -19,6 +19,7 @@ cudaError_t launch_line_integrate(const nl_desc* d, int layout, bool bwd, const 
                                   void* ga, void* gb, cudaStream_t st);
 
 void set_thread_scratch(void* ptr, size_t bytes);
+size_t thread_scratch_bytes();
 size_t line_integrate_scratch_bytes(const nl_desc* d, bool bwd);
 
 // ---- fused SIMT path (any dtype / family / t_mode; nl_fused_simt.cu) ----
@@ -77,6 +78,13 @@ cudaError_t launch_fused_tc_dehoog(const nl_desc* d, bool bwd, const void* p, co
 size_t dehoog_qd_scratch_bytes(const nl_desc* d, bool bwd);
 cudaError_t launch_dehoog_qd(const nl_desc* d, bool bwd, const void* t, const void* F, const void* gx, void* x,
                              void* dF, void* scratch, cudaStream_t st, const void* Tper = nullptr);
+
+// ---- fixed-contour De Hoog: one quotient-difference table per contour row, Pade recurrence per time point
+// (nl_dehoog_fixed.cu) ----
+size_t dehoog_fixed_scratch_bytes(int dtype, int64_t rows, int n, int64_t T, bool bwd);
+cudaError_t launch_dehoog_fixed(int dtype, int64_t rows, int n, int64_t T, bool bwd, const void* F, const void* t,
+                                double contour_T, double gamma, const void* gx, void* x, void* dF, void* scratch,
+                                cudaStream_t st);
 
 // ---- training-step tail over one flat buffer: global-norm clip + Adam (nl_optim.cu) ----
 size_t clip_adam_scratch_bytes();

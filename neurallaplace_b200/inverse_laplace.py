@@ -36,14 +36,17 @@ def _real(v):
   return v.real if v.is_complex() else v
 
 
-def _stage(x, dtype):
-  """-> contiguous CUDA tensor of ``dtype`` (+ the device to return results on)."""
+def _stage(x, dtype, device=None):
+  """-> contiguous CUDA tensor of ``dtype`` on ``device`` (default: where it is, or the current CUDA device for
+  host tensors) + the device to return results on."""
   _lib.require_cuda()
   if not isinstance(x, torch.Tensor):
     x = torch.as_tensor(x)
   home = x.device
   x = _real(x).to(dtype)
-  if not x.is_cuda:
+  if device is not None:
+    x = x.to(device)
+  elif not x.is_cuda:
     x = x.cuda()
   return x.contiguous(), home
 
@@ -67,7 +70,7 @@ class InverseLaplaceTransformAlgorithmBase(nn.Module):
   def _query(self, ti, Tper=None):
     t, home = _stage(ti, self.torch_float_datatype)
     flat = t.reshape(-1)
-    Tp = None if Tper is None else _stage(Tper, self.torch_float_datatype)[0].reshape(-1)
+    Tp = None if Tper is None else _stage(Tper, self.torch_float_datatype, flat.device)[0].reshape(-1)
     s, _ = _ops.query_points(self._c, flat, _lib.NL_HEAD_RAW, True, False, Tp)
     return s, flat, home
 
@@ -80,8 +83,10 @@ class InverseLaplaceTransformAlgorithmBase(nn.Module):
       f = f.cuda()
     n = f.shape[-1]
     lead = f.shape[:-1]
-    t, _ = _stage(ti, self.torch_float_datatype)
-    Tp = None if Tper is None else _stage(Tper, self.torch_float_datatype)[0]
+    t, _ = _stage(ti, self.torch_float_datatype, f.device)
+    Tp = None if Tper is None else _stage(Tper, self.torch_float_datatype, f.device)[0]
+    if eta_override is not None:
+      eta_override = eta_override.to(f.device)
     if batch_time:
       B, T, D = lead
       t_mode = _lib.NL_T_PER_ROW
@@ -143,8 +148,9 @@ class _ContourBase(InverseLaplaceTransformAlgorithmBase):
     if time_max is None:
       return None
     t = _real(torch.as_tensor(ti))
-    tm = float(time_max)
-    # T = scale * tmax with the float32 scale, in the working dtype
+    # `torch.Tensor([time_max])` (inverse_laplace.py:1136, 719): time_max is rounded to float32 on both dtype
+    # paths; T = scale * tmax with the float32 scale, in the working dtype
+    tm = float(torch.tensor(float(time_max), dtype=torch.float32))
     return torch.full(t.reshape(-1).shape, tm, dtype=self.torch_float_datatype) * float(self._c.scale)
 
   def compute_s(self, ti, time_max=None, Ti=None):
@@ -171,7 +177,8 @@ class _ContourBase(InverseLaplaceTransformAlgorithmBase):
     return self._integrate(fp, ti, T, True)
 
   def forward(self, fs, ti, time_max=None, Ti=None):
-    """inverse_laplace.py:1269-1306 / 897-1042."""
+    """inverse_laplace.py:1269-1306 / 897-1042.  (The reference evaluates ``fs`` on the full ``[T, n]`` grid of
+    s points also when ``time_max`` makes every row the same contour; so does this, ``fs`` is the caller's.)"""
     s, T = self.compute_s(ti, time_max, Ti)
     return self.line_integrate(fs(s), ti, T)
 
@@ -197,18 +204,47 @@ class DeHoog(_ContourBase):
                torch_float_datatype=TORCH_FLOAT_DATATYPE, torch_complex_datatype=TORCH_COMPLEX_DATATYPE):
     super().__init__(ilt_reconstruction_terms, alpha, tol, scale, torch_float_datatype, torch_complex_datatype)
 
+  def _fixed_contour(self, time_max):
+    """(T, gamma) of the single contour for ``time_max`` as the reference computes them: float32 on both dtype
+    paths (``torch.Tensor([...])``, inverse_laplace.py:579-582, 640-642)."""
+    c = self._c
+    tmax = torch.tensor([float(time_max)], dtype=torch.float32)
+    scale = torch.tensor([c.scale], dtype=torch.float32)
+    T = (scale * tmax).to(torch.float32)
+    gamma = torch.tensor([c.alpha], dtype=torch.float32) - torch.log(torch.tensor([c.tol], dtype=torch.float32)) / (
+        scale * T)
+    return float(T), float(gamma)
+
   def compute_fixed_s(self, time_max):
-    """s[n] for the single time point ``time_max`` (inverse_laplace.py:567-585)."""
-    tm = torch.as_tensor(time_max, dtype=self.torch_float_datatype).reshape(1)
-    s, _, home = self._query(tm)
+    """s[n] for the single time point ``time_max`` (inverse_laplace.py:567-585): gamma + i pi k / T with the
+    float32 (T, gamma) of that contour, evaluated by ``nl_query_points``."""
+    T, gamma = self._fixed_contour(time_max)
+    home = time_max.device if isinstance(time_max, torch.Tensor) else torch.device("cpu")
+    _lib.require_cuda()
+    dev = home if home.type == "cuda" else torch.device("cuda", torch.cuda.current_device())
+    one = torch.ones(1, dtype=self.torch_float_datatype, device=dev)
+    # the kernel forms gamma = alpha - log_tol / (scale * T): alpha := gamma, log_tol := 0 pins it
+    s, _ = _ops.query_points(_consts.FixedContour(self._c, gamma), one, _lib.NL_HEAD_RAW, True, False, one * T)
     return s.reshape(-1).to(home)
 
   def fixed_line_integrate(self, fp, ti, time_max):
-    """One contour (fp [n]) evaluated at every ti (inverse_laplace.py:587-701)."""
-    t = _real(torch.as_tensor(ti)).reshape(-1)
-    Tper = torch.full(t.shape, float(time_max), dtype=self.torch_float_datatype) * float(self._c.scale)
-    f = fp.reshape(1, -1).expand(t.numel(), fp.numel())
-    return self._integrate(f, t, Tper, False)
+    """One contour ``fp [n]`` (or ``[rows, n]``) evaluated at every ``ti`` (inverse_laplace.py:587-701): the
+    quotient-difference table is built once per contour, the Pade recurrence runs per time point
+    (``nl_dehoog_fixed_forward/backward``).  Returns ``[T]`` (or ``[rows, T]``)."""
+    _lib.require_cuda()
+    T, gamma = self._fixed_contour(time_max)
+    home = fp.device
+    f = fp.to(self.torch_complex_datatype)
+    if not f.is_cuda:
+      f = f.cuda()
+    t, _ = _stage(ti, self.torch_float_datatype, f.device)
+    t = t.reshape(-1)
+    single = f.dim() == 1
+    F = torch.view_as_real(f.reshape(-1, f.shape[-1]).contiguous())
+    if F.shape[1] != self.nt:
+      raise ValueError(f"fp has {F.shape[1]} terms, the contour has {self.nt}")
+    x = _ops.dehoog_fixed(F, t, T, gamma)
+    return (x.reshape(-1) if single else x).to(home)
 
 
 # ------------------------------------------------------------------------------------------
@@ -318,7 +354,7 @@ class FixedTablot(_AbateWhittBase):
     if time_max is None:
       return self._integrate(fp, ti, None, False)
     eta, div = self._tmax_tables(ti, time_max)
-    return self._integrate(fp, ti, div, False, eta_override=eta.cuda())
+    return self._integrate(fp, ti, div, False, eta_override=eta)
 
   def line_integrate_multi(self, fp, ti, time_max=None):
     return self.line_integrate(fp, ti, time_max)

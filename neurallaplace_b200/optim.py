@@ -90,9 +90,11 @@ class FlatClipAdam:
         self.flat_grad.div_(dist.get_world_size(self.group))
     self.step_count += 1
     lib = _lib.load()
-    st = lib.nl_clip_adam_step(_lib.dtype_code(self.flat_param.dtype), self.flat_param.numel(),
-                               _lib.ptr(self.flat_param), _lib.ptr(self.flat_grad), _lib.ptr(self.exp_avg),
-                               _lib.ptr(self.exp_avg_sq), self.lr, self.betas[0], self.betas[1], self.eps,
-                               self.step_count, float(self.max_norm) if self.max_norm else 0.0, 1,
-                               _lib.ptr(self._scratch), self._scratch.numel(), _lib.stream_ptr())
+    dev = self.flat_param.device
+    with _lib.on(dev):
+      st = lib.nl_clip_adam_step(_lib.dtype_code(self.flat_param.dtype), self.flat_param.numel(),
+                                 _lib.ptr(self.flat_param), _lib.ptr(self.flat_grad), _lib.ptr(self.exp_avg),
+                                 _lib.ptr(self.exp_avg_sq), self.lr, self.betas[0], self.betas[1], self.eps,
+                                 self.step_count, float(self.max_norm) if self.max_norm else 0.0, 1,
+                                 _lib.ptr(self._scratch), self._scratch.numel(), _lib.stream_ptr(dev))
     _lib.check(st)

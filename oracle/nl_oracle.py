@@ -363,6 +363,96 @@ def line_integrate_batched(c: IltConsts, fp, ti, T, per_row):
 
 
 # --------------------------------------------------------------------------------------
+# time_max / fixed-contour variants: ONE contour for every time point
+# --------------------------------------------------------------------------------------
+def compute_s_time_max(c: IltConsts, ti, time_max):
+  """``compute_s(ti, time_max=...)``: Fourier inverse_laplace.py:1135-1147, DeHoog 718-735, FixedTablot
+  328-339.  ``torch.Tensor([time_max])`` rounds ``time_max`` to float32 on both dtype paths."""
+  t = _to_complex(ti)
+  if c.alg in ("fourier", "dehoog"):
+    tmax = torch.Tensor([time_max]) * torch.ones_like(t)
+    T = (tmax * c.scale).to(c.cdtype)
+    gamma = c.alpha - torch.log(c.tol) / (c.scale * T)
+    si = torch.matmul(1 / T.view(-1, 1), 1j * torch.pi * c.k.view(1, -1))
+    return gamma.view(-1, 1) + si, T
+  if c.alg == "fixed_tablot":
+    ttm = _to_complex(torch.ones(t.shape, dtype=c.dtype)) * time_max
+    s = torch.matmul(1 / ttm.view(-1, 1), c.sdt.view(1, -1))
+    s0 = c.rdt / ttm
+    return torch.hstack((s0.view(-1, 1), s)), c.rdt / time_max
+  raise ValueError(c.alg)
+
+
+def fixed_tablot_line_integrate_time_max(c: IltConsts, fp, ti, time_max):
+  """FixedTablot.line_integrate / line_integrate_multi with ``time_max`` (inverse_laplace.py:361-368, 393-400).
+  fp [T, n] or [T, D, n]."""
+  t = _to_complex(ti)
+  th = c.theta
+  shape = (1.0 + 1j * th * (1.0 + (1 / torch.tan(th)**2)) - 1j * (1 / torch.tan(th)))
+  if fp.dim() == 2:
+    f0 = torch.exp((c.rdt * t) / time_max) * fp[:, 0] / 2.0
+    pans = torch.exp((c.rdt * t) / time_max).view(-1, 1) * fp[:, 1:] * shape
+    return ((2.0 / 5.0) * (torch.sum(pans, 1) + f0) * (1 / time_max)).real
+  f0 = torch.exp((c.rdt * t) / time_max) * fp[:, :, 0] / 2.0
+  pans = torch.exp((c.rdt * t) / time_max).view(-1, 1) * fp[:, :, 1:] * shape
+  return ((2.0 / 5.0) * (torch.sum(pans, 2) + f0) * (1 / time_max)).real
+
+
+def dehoog_compute_fixed_s(c: IltConsts, time_max):
+  """DeHoog.compute_fixed_s (inverse_laplace.py:567-585): T and gamma are float32 on both dtype paths."""
+  tmax = torch.Tensor([time_max])
+  T = torch.Tensor([c.scale * tmax])
+  gamma = c.alpha - torch.log(c.tol) / (c.scale * T)
+  return gamma + 1j * torch.pi * torch.arange(c.terms, dtype=c.dtype) / T
+
+
+def dehoog_fixed_line_integrate(c: IltConsts, fp, ti, time_max):
+  """DeHoog.fixed_line_integrate (inverse_laplace.py:587-701): ONE quotient-difference table for the contour
+  ``fp [n]``, the Pade recurrence evaluated at every ``ti`` through z = exp(i pi t / T)."""
+  tv = _to_complex(ti)
+  M, NT = c.M, c.terms
+  tmax = torch.Tensor([time_max])
+  T = torch.Tensor([c.scale * tmax])
+  gamma = c.alpha - torch.log(c.tol) / (c.scale * T)
+  qs, es = [], []
+  q = fp[1:2 * M + 1] / fp[0:2 * M]
+  q[0] = fp[1] / (fp[0] / 2.0)
+  qs.append(q)
+  for r in range(1, M + 1):
+    mr = 2 * (M - r) + 1
+    e = torch.zeros((NT,), dtype=c.cdtype)
+    if r == 1:
+      e[0:mr] = qs[r - 1][1:mr + 1] - qs[r - 1][0:mr]
+    else:
+      e[0:mr] = qs[r - 1][1:mr + 1] - qs[r - 1][0:mr] + es[r - 2][1:mr + 1]
+    es.append(e)
+    if r != M:
+      q = torch.zeros((2 * M,), dtype=c.cdtype)
+      q[0:mr] = qs[r - 1][1:mr + 1] * es[r - 1][1:mr + 1] / es[r - 1][0:mr]
+      qs.append(q)
+  d = torch.empty((NT,), dtype=c.cdtype)
+  d[0] = fp[0] / 2.0
+  for r in range(1, M + 1):
+    d[2 * r - 1] = -qs[r - 1][0]
+    d[2 * r] = -es[r - 1][0]
+  Aim1 = torch.view_as_complex(torch.Tensor([0, 0]))
+  Ai = d[0]
+  Bim1 = torch.view_as_complex(torch.Tensor([1, 0]))
+  Bi = torch.view_as_complex(torch.Tensor([1, 0]))
+  z = torch.exp(1j * torch.pi * ti / T)
+  for i in range(1, 2 * M):
+    Ait = Ai + d[i] * Aim1 * z
+    Aim1, Ai = Ai, Ait
+    Bit = Bi + d[i] * Bim1 * z
+    Bim1, Bi = Bi, Bit
+  brem = (1.0 + (d[2 * M - 1] - d[2 * M]) * z) / 2.0
+  rem = -brem * (1.0 - torch.sqrt(1.0 + d[2 * M] * z / brem**2))
+  A2 = Ai + rem * Aim1
+  B2 = Bi + rem * Bim1
+  return (torch.exp(gamma * tv) / T * (A2 / B2).real).real
+
+
+# --------------------------------------------------------------------------------------
 # laplace_reconstruct (core.py:25-150) for the canonical MLP
 # --------------------------------------------------------------------------------------
 def laplace_reconstruct_oracle(weights,

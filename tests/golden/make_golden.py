@@ -174,8 +174,111 @@ def class_level():
   np.savez_compressed(os.path.join(HERE, "class_level.npz"), **out)
 
 
+def class_level_time_max():
+  """The ``time_max`` / fixed-contour calls of tests/test_ilt.py:56-64, 101-106 with their OUTPUTS stored:
+  FixedTablot.compute_s/line_integrate/line_integrate_multi/forward(time_max=) (inverse_laplace.py:272-304,
+  328-339, 361-368, 393-400), DeHoog.compute_fixed_s / fixed_line_integrate / compute_s(time_max=) /
+  forward(time_max=) (567-735, 897-1042), Fourier.compute_s(time_max=) / forward(time_max=) (1122-1147, 1269-1306).
+  Two contours per dtype: the reference test's own (t up to 10, time_max = max t) and one whose time_max is not
+  float32-representable (shows the ``torch.Tensor([time_max])`` rounding on the double path)."""
+  out = {}
+  fs = lambda so: so / (so**2 + 1)
+  for dtype, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
+    cd = torch.cdouble if dtype == torch.float64 else torch.cfloat
+    kw = dict(ilt_reconstruction_terms=33, torch_float_datatype=dtype, torch_complex_datatype=cd)
+    for case, t in (("a", torch.linspace(0.0001, 10.0, 1000).to(dtype)),
+                    ("b", (torch.linspace(0.05, 7.3, 257, dtype=torch.float64)).to(dtype))):
+      key = f"{tag}_{case}"
+      tmax = torch.max(t)
+      out[f"t_{key}"] = t.numpy()
+      out[f"tmax_{key}"] = float(tmax)
+      # ---- FixedTablot
+      dec = ril.FixedTablot(**kw)
+      c = orc.IltConsts("fixed_tablot", 33, dtype)
+      s, r_over = dec.compute_s(t, time_max=tmax)
+      so, ro = orc.compute_s_time_max(c, t, tmax)
+      assert torch.equal(s, so) and torch.equal(r_over, ro), ("ft s", key)
+      fh = fs(s)
+      y = dec.line_integrate(fh, t, time_max=tmax.item())
+      yo = orc.fixed_tablot_line_integrate_time_max(c, fh, t, tmax.item())
+      yf = dec(fs, t, time_max=tmax)
+      # (line_integrate_multi cannot be recorded: the reference broadcasts [T] against [T, D] there and raises
+      # for any D != T, with and without time_max -- inverse_laplace.py:393-408; the product defines it as
+      # line_integrate applied to every d slice and is tested against that.)
+      print(f"  tmax fixed_tablot {key}: oracle-vs-ref {rel(yo, y):.1e} exact={torch.equal(yo, y)}  "
+            f"fwd-vs-split {rel(yf, y):.1e}")
+      assert rel(yo, y) < 1e-6
+      out.update({f"ft_{key}_s_re": s.real.numpy(), f"ft_{key}_s_im": s.imag.numpy(), f"ft_{key}_y": y.numpy(),
+                  f"ft_{key}_yfwd": yf.numpy(), f"ft_{key}_r_over": r_over.numpy()})
+      # ---- DeHoog: fixed contour
+      dec = ril.DeHoog(**kw)
+      c = orc.IltConsts("dehoog", 33, dtype)
+      sf = dec.compute_fixed_s(tmax)
+      sfo = orc.dehoog_compute_fixed_s(c, tmax)
+      assert torch.equal(sf, sfo), ("dh fixed s", key)
+      fhf = fs(sf)
+      yfix = dec.fixed_line_integrate(fhf, t, tmax)
+      yfixo = orc.dehoog_fixed_line_integrate(c, fhf, t, tmax)
+      s2, T2 = dec.compute_s(t, time_max=tmax)
+      s2o, T2o = orc.compute_s_time_max(c, t, tmax)
+      assert torch.equal(s2, s2o) and torch.equal(T2, T2o), ("dh s tmax", key)
+      y2 = dec.line_integrate(fs(s2), t, T2)
+      y2o = orc.line_integrate_1d(c, fs(s2), t, T2)
+      yfw = dec(fs, t, time_max=tmax)
+      print(f"  tmax dehoog       {key}: fixed oracle-vs-ref {rel(yfixo, yfix):.1e} exact={torch.equal(yfixo, yfix)}; "
+            f"compute_s(time_max) {rel(y2o, y2):.1e} exact={torch.equal(y2o, y2)}; fwd-vs-split {rel(yfw, y2):.1e}; "
+            f"rmse-vs-cos {float(torch.sqrt(torch.mean((torch.cos(t) - yfix)**2))):.3g}")
+      assert rel(yfixo, yfix) < 1e-2 and rel(y2o, y2) < 1e-2
+      out.update({f"dh_{key}_sfix_re": sf.real.numpy(), f"dh_{key}_sfix_im": sf.imag.numpy(),
+                  f"dh_{key}_yfix": yfix.numpy(), f"dh_{key}_s_re": s2.real.numpy(), f"dh_{key}_s_im": s2.imag.numpy(),
+                  f"dh_{key}_T": T2.real.numpy(), f"dh_{key}_y": y2.numpy(), f"dh_{key}_yfwd": yfw.numpy()})
+      # ---- Fourier
+      dec = ril.Fourier(**kw)
+      c = orc.IltConsts("fourier", 33, dtype)
+      s3, T3 = dec.compute_s(t, time_max=tmax)
+      s3o, T3o = orc.compute_s_time_max(c, t, tmax)
+      assert torch.equal(s3, s3o) and torch.equal(T3, T3o), ("fourier s tmax", key)
+      y3 = dec.line_integrate(fs(s3), t, T3)
+      y3o = orc.line_integrate_1d(c, fs(s3), t, T3)
+      y3f = dec(fs, t, time_max=tmax)
+      print(f"  tmax fourier      {key}: oracle-vs-ref {rel(y3o, y3):.1e} exact={torch.equal(y3o, y3)} "
+            f"fwd-vs-split {rel(y3f, y3):.1e}")
+      assert rel(y3o, y3) < 1e-6
+      out.update({f"fo_{key}_s_re": s3.real.numpy(), f"fo_{key}_s_im": s3.imag.numpy(), f"fo_{key}_T": T3.real.numpy(),
+                  f"fo_{key}_y": y3.numpy(), f"fo_{key}_yfwd": y3f.numpy()})
+  np.savez_compressed(os.path.join(HERE, "class_level_tmax.npz"), **out)
+
+
+def collate_cases():
+  """torchlaplace.data_utils.basic_collate_fn (data_utils.py:51-74) on seeded trajectories: interpolation,
+  extrapolation with steps, the ``hopper`` split."""
+  from torchlaplace import data_utils as rdu
+  g = torch.Generator().manual_seed(5)
+  trajs = [torch.randn(24, 3, generator=g) for _ in range(5)]
+  ts = torch.linspace(0.0, 2.3, 24)
+  out = dict(trajs=torch.stack(trajs).numpy(), ts=ts.numpy())
+  cases = dict(interp=dict(), extrap=dict(extrap=True), extrap_steps=dict(extrap=True, observe_step=2, predict_step=3),
+               hopper=dict(extrap=True, data="hopper", data_type="test"))
+  for name, kw in cases.items():
+    d = rdu.basic_collate_fn(list(trajs), ts, **kw)
+    assert d["mask_predicted_data"] is None and d["labels"] is None
+    out[f"{name}_keys"] = ",".join(d.keys())
+    out[f"{name}_mode"] = d["mode"]
+    for k in ("observed_data", "observed_tp", "data_to_predict", "tp_to_predict", "observed_mask"):
+      out[f"{name}_{k}"] = d[k].numpy()
+    print(f"  collate {name}: " + " ".join(f"{k}{tuple(d[k].shape)}" for k in ("observed_data", "tp_to_predict")))
+  np.savez_compressed(os.path.join(HERE, "collate.npz"), **out)
+
+
 def main():
   f32, f64 = torch.float32, torch.float64
+  if len(sys.argv) > 1 and sys.argv[1] == "tmax":  # only the time_max fixture (keeps the other files untouched)
+    print("time_max / fixed-contour cases:")
+    class_level_time_max()
+    return
+  if len(sys.argv) > 1 and sys.argv[1] == "collate":
+    collate_cases()
+    return
   print("laplace_reconstruct cases (reference vs oracle):")
   # the five shape cases of tests/test_laplace_rep_func.py:67-145 (B shrunk where it only adds bytes)
   recon_case("recon_fourier_f32_orig", "fourier", 33, 2, 3, 2, 2, f32, "shared", 1)
@@ -198,6 +301,10 @@ def main():
   recon_case("recon_fourier_f32_h32", "fourier", 17, 8, 10, 1, 2, f32, "shared", 17, H=32)
   print("class-level cases:")
   class_level()
+  print("time_max / fixed-contour cases:")
+  class_level_time_max()
+  print("collate cases:")
+  collate_cases()
 
 
 if __name__ == "__main__":

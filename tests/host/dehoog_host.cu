@@ -64,6 +64,38 @@ int nlh_dehoog_sm(int n, double zr, double zi, const double* a, double* w_out, d
   return 0;
 }
 
+
+// fixed contour (nl_dehoog_fixed.cu composes exactly these parts): a[n] -> table once; per time point z_j the Pade
+// recurrence + its reverse; g_j-weighted sum of dw/dd_i over j; one reverse sweep through the table.
+// out_w[2*nz] = w_j;  out_G[2n] = G_k = sum_j g_j dw_j/da_k (holomorphic);  w_fwd[2*nz]: forward-only parts.
+int nlh_dehoog_fixed(int n, int nz, const double* z, const double* g, const double* a, double* out_w, double* out_G,
+                     double* w_fwd) {
+  const int M = (n - 1) / 2, LD = 2 * M + 2;
+  auto acc = [&](int k) { return Cx<double>{a[2 * k], a[2 * k + 1]}; };
+  std::vector<Cx<double>> tabv((size_t)(2 * M + 2) * LD), thr((size_t)3 * LD), adjv((size_t)5 * LD), fwd((size_t)3 * LD);
+  Scratch<double> tab{tabv.data(), 1, 0}, dbar{thr.data(), 1, 0}, adj{adjv.data(), 1, 0}, fw{fwd.data(), 1, 0};
+  dehoog_qd_store<double>(M, acc, tab);
+  dehoog_qd_coeffs<double>(M, acc, fw);
+  const Scratch<double> dd = tab.at((2 * M + 1) * LD), dd2 = fw.at(2 * LD);
+  for (int i = 0; i <= 2 * M; ++i) adj[i] = Cx<double>{0.0, 0.0};
+  for (int j = 0; j < nz; ++j) {
+    const Cx<double> zj{z[2 * j], z[2 * j + 1]};
+    Cx<double> w = dehoog_pade_fwd_bwd<double>(M, zj, [&](int i) { return dd[i]; }, dbar, dbar.at(LD));
+    out_w[2 * j] = w.re;
+    out_w[2 * j + 1] = w.im;
+    Cx<double> w2 = dehoog_pade<double>(M, zj, [&](int i) { return dd2[i]; });
+    w_fwd[2 * j] = w2.re;
+    w_fwd[2 * j + 1] = w2.im;
+    for (int i = 0; i <= 2 * M; ++i) adj[i] = cadd(adj[i], cscale(dbar[i], g[j]));
+  }
+  auto emit = [&](int k, Cx<double> G) {
+    out_G[2 * k] = G.re;
+    out_G[2 * k + 1] = G.im;
+  };
+  dehoog_qd_reverse<double>(M, acc, emit, tab, adj, adj.at(LD));
+  return 0;
+}
+
 // head forward/backward:  in (oa, ob, gre, gim) -> out (fre, fim, goa, gob)
 int nlh_head(int head, double oa, double ob, double gre, double gim, double* out) {
   HeadOut<double> h = head_forward<double>(head, oa, ob);

@@ -20,7 +20,7 @@ from tests import helpers as hp
 
 def test_library_loads_and_exports_every_header_symbol():
   lib = _lib.load()
-  assert lib.nl_abi_version() == 2
+  assert lib.nl_abi_version() == 3
   header = open(os.path.join(hp.ROOT, "include", "nl_b200.h")).read()
   declared = set(re.findall(r"\b(nl_[a-z_0-9]+)\s*\(", header))
   declared -= {"nl_workspace_bytes"} - set(_lib.EXPORTS)

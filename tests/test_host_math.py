@@ -67,6 +67,38 @@ def test_dehoog_forward_and_reverse_sweep(hostlib, terms):
 
 
 
+@pytest.mark.parametrize("terms", [9, 33, 65])
+def test_dehoog_fixed_contour_parts(hostlib, terms):
+  """The parts nl_dehoog_fixed.cu composes (table once per contour, Pade recurrence + reverse per time point,
+  weighted sum of dw/dd_i, one reverse sweep) against autograd through the oracle's restatement of
+  DeHoog.fixed_line_integrate (inverse_laplace.py:587-701)."""
+  c = orc.IltConsts("dehoog", terms, torch.float64)
+  tmax = 7.3
+  t = torch.tensor([0.4, 2.2, 5.0, 7.3], dtype=torch.float64)
+  s = orc.dehoog_compute_fixed_s(c, tmax)
+  torch.manual_seed(terms)
+  fp = (s / (s**2 + 1) + 0.02 * torch.randn(s.shape, dtype=torch.cdouble)).clone().requires_grad_(True)
+  gout = torch.tensor([0.7, -1.3, 0.2, 2.0], dtype=torch.float64)
+  y = orc.dehoog_fixed_line_integrate(c, fp, t, tmax)
+  (y * gout).sum().backward()
+  T = float(torch.Tensor([c.scale * torch.Tensor([tmax])]))
+  gamma = float(c.alpha - torch.log(c.tol) / (c.scale * torch.Tensor([T])))
+  ang = math.pi * t.numpy() / T
+  z = np.stack([np.cos(ang), np.sin(ang)], 1).reshape(-1).copy()
+  pref = np.exp(gamma * t.numpy()) / T
+  g = (gout.numpy() * pref).copy()
+  a = torch.view_as_real(fp.detach()).numpy().copy().reshape(-1)
+  w, G, w2 = np.zeros(2 * t.numel()), np.zeros(2 * terms), np.zeros(2 * t.numel())
+  assert hostlib.nlh_dehoog_fixed(terms, t.numel(), _p(z), _p(g), _p(a), _p(w), _p(G), _p(w2)) == 0
+  tol = 1e-9 if terms <= 33 else 1e-6
+  yk = pref * w[0::2]
+  assert np.abs(yk - y.detach().numpy()).max() <= tol * np.abs(y.detach().numpy()).max()
+  assert np.array_equal(w, w2)  # forward-only parts: same arithmetic
+  gr = fp.grad
+  assert np.linalg.norm(G[0::2] - gr.real.numpy()) <= 100 * tol * np.linalg.norm(gr.real.numpy())
+  assert np.linalg.norm(-G[1::2] - gr.imag.numpy()) <= 100 * tol * np.linalg.norm(gr.imag.numpy())
+
+
 def test_head_chain_rule(hostlib):
   rng = np.random.RandomState(0)
   for head in (0, 1):
