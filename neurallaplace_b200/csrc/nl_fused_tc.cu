@@ -120,6 +120,7 @@ struct TcArgs {
   float2* fout;
   const float2* dfin;
   long long f_plane;     // T * B
+  const unsigned char* w3lo;  // De Hoog forward: [nch] third (lo) W3 operand images of the three-term split
   unsigned char* stash;  // optional [ntiles][h1_hi | h1_lo | h2_hi | h2_lo] operand images (16 KB each), see kStashTile
   long long* prof;  // optional: per-phase clock totals of thread 0 (NL_TC_PROFILE builds)
 };
@@ -130,7 +131,9 @@ struct TcSmem {
   int S1b, W1p, b2, b3, coef, u, G1, xacc, misc, nfloats;  // float offsets inside `small`
 };
 
-__host__ __device__ inline TcSmem tc_smem(bool bwd, int NP, int nch, int nkc, int w3_slots, int n, bool h2sep = false) {
+// nimg: operand images per matrix -- 2 (hi | lo) or 3 (hi | mid | lo: the De Hoog forward, see split3)
+__host__ __device__ inline TcSmem tc_smem(bool bwd, int NP, int nch, int nkc, int w3_slots, int n, bool h2sep = false,
+                                          int nimg = 2) {
   TcSmem L;
   L.dO_img = bwd ? image_bytes(kRows, NP > kH ? NP : kH) : 0;  // also hosts Z2g / Z1g (64 columns)
   L.H1_img = image_bytes(kRows, bwd ? kH1Cols : kH);
@@ -139,10 +142,10 @@ __host__ __device__ inline TcSmem tc_smem(bool bwd, int NP, int nch, int nkc, in
   L.W3_img = image_bytes(NP, kH);
   size_t o = 0;
   L.dO = o; o += 2 * L.dO_img;
-  L.H1 = o; o += 2 * L.H1_img;
-  L.H2 = o; o += 2 * L.H2_img;
-  L.W2 = o; o += 2 * L.W2_img;
-  L.W3 = o; o += 2 * L.W3_img * w3_slots;
+  L.H1 = o; o += nimg * L.H1_img;
+  L.H2 = o; o += nimg * L.H2_img;
+  L.W2 = o; o += nimg * L.W2_img;
+  L.W3 = o; o += nimg * L.W3_img * w3_slots;
   L.small = o;
   int f = 0;
   L.S1b = f; f += kH;
@@ -208,9 +211,10 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, uint32_t 
 }
 
 // W3 / b3 -> per-chunk bf16 hi/lo operand images (row jj of chunk ch <-> W3 row of (d, k, theta|phi))
+// w3lo (optional): third image of the three-term split, [nch][image] (the first two are the same bytes either way)
 __global__ void pack_w3_kernel(const float* __restrict__ W3, const float* __restrict__ b3, int D, int n, int nkc,
                                int kc, int NP, int nch, unsigned char* __restrict__ w3pack,
-                               float* __restrict__ b3pack) {
+                               float* __restrict__ b3pack, unsigned char* __restrict__ w3lo = nullptr) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nch * NP) return;
   const int ch = idx / NP, jj = idx - ch * NP;
@@ -225,6 +229,13 @@ __global__ void pack_w3_kernel(const float* __restrict__ W3, const float* __rest
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = valid ? __ldg(W3 + (size_t)row * kH + c0 + i) : 0.f;
     store_chunk8(w_hi, w_lo, NP, jj, c0, v);
+    if (w3lo) {
+      uint32_t h[4], m[4], l[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) split3(v[2 * i], v[2 * i + 1], &h[i], &m[i], &l[i]);
+      *reinterpret_cast<uint4*>(w3lo + (size_t)ch * img + (size_t)(c0 >> 3) * ((size_t)NP * 16) + (size_t)jj * 16) =
+          make_uint4(l[0], l[1], l[2], l[3]);
+    }
   }
   b3pack[idx] = valid ? __ldg(b3 + row) : 0.f;
 }
@@ -354,6 +365,10 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
   constexpr int kThreadsTc = 128 * kEWG;
   constexpr int kColsPerWg = kH / kEWG;
   constexpr uint32_t kTmemCols = BWD ? 512 : 256;
+  // De Hoog forward: three-term operand split (hi | mid | lo images, six passes per GEMM): F to float32 accuracy --
+  // the quotient-difference recurrence downstream amplifies noise on F by 10^2..10^3
+  constexpr bool X6 = DH && !BWD;
+  constexpr int kImg = X6 ? 3 : 2;
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar_main;
   __shared__ __align__(8) uint64_t bar_aux[3];  // weight-gradient GEMMs: 0 = dW3, 1 = dW2, 2 = D1
@@ -368,7 +383,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
   const int acc_slots = BWD ? (n_resident < nch ? n_resident + 1 : n_resident) : 0;
   const bool stash = !BWD && A.stash != nullptr;
   const bool h2sep = stash && !ALIAS;  // (A.h2sep selects the instantiation on the host)
-  const TcSmem L = tc_smem(BWD, NP, nch, A.nkc, A.w3_slots, n, h2sep);
+  const TcSmem L = tc_smem(BWD, NP, nch, A.nkc, A.w3_slots, n, h2sep, kImg);
   const TcTmem TM = tc_tmem(BWD, NP, acc_slots);
   unsigned char* dO_hi = smem + L.dO;
   unsigned char* dO_lo = dO_hi + L.dO_img;
@@ -394,7 +409,8 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
   const int wg = tid >> 7;        // warpgroup
   const int r = tid & 127;        // row of the tile == TMEM lane
   const int ldw1 = 2 * n + K;
-  const uint32_t w3_bytes = (uint32_t)(2 * L.W3_img);  // hi + lo image of one chunk
+  const uint32_t w3_bytes = (uint32_t)(2 * L.W3_img);     // hi + lo image of one chunk in the global pack
+  const uint32_t w3_slot = (uint32_t)(kImg * L.W3_img);   // one chunk in shared memory
 
   // ---- tile range of this CTA (contiguous => the time index changes rarely)
   const long long per = A.ntiles / gridDim.x, rem = A.ntiles % gridDim.x;
@@ -410,7 +426,8 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
       float v[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = __ldg(A.W2 + tid * kH + c0 + i);
-      store_chunk8(W2_hi, W2_lo, kH, tid, c0, v);
+      if (X6) store_chunk8x3(W2_hi, L.W2_img, kH, tid, c0, v);
+      else    store_chunk8(W2_hi, W2_lo, kH, tid, c0, v);
     }
     sb2[tid] = __ldg(A.b2 + tid);
     for (int j = 0; j < K; ++j) sW1p[tid * 8 + j] = __ldg(A.W1 + (size_t)tid * ldw1 + 2 * n + j);
@@ -440,20 +457,36 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
   // ---- W3 staging: chunk use `g` (g-th chunk this CTA touches) lives in slot g % w3_slots
   // (resident mode: w3_slots == nch, every chunk loaded once; streamed: ring of kStages)
   const int nst = A.w3_slots;  // ring depth when streamed (2 or kStages)
+  // one chunk of the global pack -> its shared-memory slot (X6: + the third image from its own array), one phase of `bar`
+  auto w3_load = [&](unsigned char* dst, int ch, uint64_t* bar) {
+    if (!X6) {
+      bulk_load(dst, A.w3pack + (size_t)ch * w3_bytes, w3_bytes, bar);
+    } else {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(w3_slot) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       smem_u32(dst)),
+                   "l"(A.w3pack + (size_t)ch * w3_bytes), "r"(w3_bytes), "r"(smem_u32(bar))
+                   : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       smem_u32(dst + w3_bytes)),
+                   "l"(A.w3lo + (size_t)ch * L.W3_img), "r"((uint32_t)L.W3_img), "r"(smem_u32(bar))
+                   : "memory");
+    }
+  };
   long long w3_issued = 0;  // meaningful in the elected lane of warp 0 only (elect.sync is deterministic)
   auto w3_issue_upto = [&](long long upto) {  // thread 0: start the loads of chunk uses < upto
     if (!streamed) return;
     const long long lim = min(upto, total_chunks);
     for (; w3_issued < lim; ++w3_issued) {
       const int ch = (int)(w3_issued % nch), slot = (int)(w3_issued % nst);
-      bulk_load(W3_base + (size_t)slot * w3_bytes, A.w3pack + (size_t)ch * w3_bytes, w3_bytes, &bar_w3[slot]);
+      w3_load(W3_base + (size_t)slot * w3_slot, ch, &bar_w3[slot]);
     }
   };
   if (!streamed) {
     if (total_chunks > 0 && warp == 0 && elect_one()) {
       // resident: every chunk loaded once; one barrier phase per load keeps the parity bookkeeping trivial
       for (int ch = 0; ch < nch; ++ch) {
-        bulk_load(W3_base + (size_t)ch * w3_bytes, A.w3pack + (size_t)ch * w3_bytes, w3_bytes, &bar_w3[0]);
+        w3_load(W3_base + (size_t)ch * w3_slot, ch, &bar_w3[0]);
         mbar_wait(&bar_w3[0], ch & 1);
       }
     }
@@ -463,7 +496,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
   }
   auto w3_slot_addr = [&](long long g) {
     const int slot = streamed ? (int)(g % nst) : (int)(g % nch);
-    return smem_u32(W3_base + (size_t)slot * w3_bytes);
+    return smem_u32(W3_base + (size_t)slot * w3_slot);
   };
   auto w3_wait = [&](long long g) {  // thread 0: chunk use g has landed
     if (streamed) mbar_wait(&bar_w3[g % nst], (uint32_t)((g / nst) & 1));
@@ -732,7 +765,10 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
     }
     if (!PR) {
 #pragma unroll
-      for (int i = 0; i < kColsPerWg; i += 8) store_chunk8(H1_hi, H1_lo, kRows, r, wg * kColsPerWg + i, &h1[i]);
+      for (int i = 0; i < kColsPerWg; i += 8) {
+        if (X6) store_chunk8x3(H1_hi, L.H1_img, kRows, r, wg * kColsPerWg + i, &h1[i]);
+        else    store_chunk8(H1_hi, H1_lo, kRows, r, wg * kColsPerWg + i, &h1[i]);
+      }
     }
     if (BWD && wg == 0) {
       float q[8];
@@ -751,7 +787,8 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
     // ---- 2. Z2 = h1 . W2^T
     if (warp == 0 && elect_one()) {
       tc_fence_after();
-      issue_gemm(gL2, tmem + TM.S, false);
+      if (X6) issue_gemm6(gL2, tmem + TM.S, false);
+      else    issue_gemm(gL2, tmem + TM.S, false);
       umma_commit(&bar_main);
       if (!BWD && stash && !PR) {
         unsigned char* dst = A.stash + (size_t)tile * kStashTile;
@@ -782,7 +819,10 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
       __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < kColsPerWg; i += 8) store_chunk8(H2_hi, H2_lo, kRows, r, wg * kColsPerWg + i, &h2[i]);
+    for (int i = 0; i < kColsPerWg; i += 8) {
+      if (X6) store_chunk8x3(H2_hi, (BWD || h2sep) ? L.H2_img : L.H1_img, kRows, r, wg * kColsPerWg + i, &h2[i]);
+      else    store_chunk8(H2_hi, H2_lo, kRows, r, wg * kColsPerWg + i, &h2[i]);
+    }
     fence_async_smem();
     tc_fence_before();
     // stash: the h1 image is rewritten by the next tile -> its bulk store must have read it
@@ -796,7 +836,8 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
       tc_fence_after();
       const GemmOp gg = make_gemm(aH2, (uint32_t)((BWD || h2sep) ? L.H2_img : L.H1_img), kRows, 0, w3_slot_addr(g),
                                   (uint32_t)L.W3_img, NP, 0, 128, NP, kH);
-      issue_gemm(gg, tmem + TM.O, false);
+      if (X6) issue_gemm6(gg, tmem + TM.O, false);
+      else    issue_gemm(gg, tmem + TM.O, false);
     };
     if (warp == 0 && elect_one()) {
       tc_fence_after();
@@ -2561,7 +2602,8 @@ struct TcGeom {
   size_t smem;
   bool ok;
 };
-static TcGeom tc_geom(const nl_desc* d, bool bwd, bool stash = false) {
+// nimg = 3: the De Hoog forward (three operand images per matrix, tc::split3)
+static TcGeom tc_geom(const nl_desc* d, bool bwd, bool stash = false, int nimg = 2) {
   TcGeom g{};
   g.nkc = (2 * d->n + 127) / 128;
   g.kc = (d->n + g.nkc - 1) / g.nkc;
@@ -2574,9 +2616,9 @@ static TcGeom tc_geom(const nl_desc* d, bool bwd, bool stash = false) {
   // shared memory: all chunks resident if they fit (forward: within half an SM so that 2 CTAs co-reside)
   const size_t limit = 227 * 1024 - 1024, half = limit / 2;
   auto place = [&](bool h2sep) {
-    const tc::TcSmem Lr = tc::tc_smem(bwd, g.NP, g.nch, g.nkc, g.nch, d->n, h2sep);
-    const tc::TcSmem Ls = tc::tc_smem(bwd, g.NP, g.nch, g.nkc, tc::kStages, d->n, h2sep);
-    const tc::TcSmem L2s = tc::tc_smem(bwd, g.NP, g.nch, g.nkc, 2, d->n, h2sep);
+    const tc::TcSmem Lr = tc::tc_smem(bwd, g.NP, g.nch, g.nkc, g.nch, d->n, h2sep, nimg);
+    const tc::TcSmem Ls = tc::tc_smem(bwd, g.NP, g.nch, g.nkc, tc::kStages, d->n, h2sep, nimg);
+    const tc::TcSmem L2s = tc::tc_smem(bwd, g.NP, g.nch, g.nkc, 2, d->n, h2sep, nimg);
     if (g.nch <= tc::kStages || Lr.total <= (bwd ? limit : half)) {
       g.w3_slots = g.nch;
       g.smem = Lr.total;
@@ -2769,6 +2811,7 @@ struct PrExtra {
 struct DhExtra {
   float2* fout;
   const float2* dfin;
+  unsigned char* w3lo;  // forward: room for the third W3 operand images, dh_w3lo_bytes()
 };
 
 static cudaError_t launch_fused_tc_impl(const nl_desc* d, bool bwd, const void* p, const void* t,
@@ -2788,13 +2831,15 @@ static cudaError_t launch_fused_tc_impl(const nl_desc* d, bool bwd, const void* 
                                         void* saved, PrExtra* pr, DhExtra* dh) {
   TcPlan pl = tc_plan(d, bwd ? 1 : 0);
   if (!pl.ok) return cudaErrorInvalidValue;
-  TcGeom g = (pr && !bwd) ? tc_geom_pr_fwd(d) : tc_geom(d, bwd, !bwd && saved != nullptr);
-  if (!bwd && saved && !g.ok) {  // no room for the separate h2 image: run without the stash (never happens at H = 64)
+  const bool x6 = dh && !bwd;  // De Hoog forward: three-term operand split
+  TcGeom g = (pr && !bwd) ? tc_geom_pr_fwd(d) : tc_geom(d, bwd, !bwd && saved != nullptr, x6 ? 3 : 2);
+  if (!bwd && (saved || x6) && !g.ok) {  // no room (never happens at H = 64)
     return cudaErrorInvalidValue;
   }
-  if (!bwd && saved) {
+  if (!bwd && (saved || x6)) {
     pl.smem = g.smem;
     pl.co_resident = g.smem <= (227 * 1024 - 1024) / 2;
+    pl.ring = g.w3_slots < g.nch;
   }
   const BsGeom bg = (bwd && saved) ? bs_geom(d, g) : BsGeom{};
   tc::TcArgs A{};
@@ -2821,6 +2866,7 @@ static cudaError_t launch_fused_tc_impl(const nl_desc* d, bool bwd, const void* 
     A.fout = dh->fout;
     A.dfin = dh->dfin;
     A.f_plane = (long long)d->T * d->B;
+    A.w3lo = x6 ? dh->w3lo : nullptr;
   }
   if (pr) {
     A.row_scale = pr->row_scale;
@@ -2874,7 +2920,8 @@ static cudaError_t launch_fused_tc_impl(const nl_desc* d, bool bwd, const void* 
   if (!reuse_aux) {
     const int total = g.nch * g.NP, threads = 128;
     tc::pack_w3_kernel<<<(total + threads - 1) / threads, threads, 0, st>>>(
-        (const float*)weights[4], (const float*)weights[5], d->D, d->n, g.nkc, g.kc, g.NP, g.nch, w3pack, b3pack);
+        (const float*)weights[4], (const float*)weights[5], d->D, d->n, g.nkc, g.kc, g.NP, g.nch, w3pack, b3pack,
+        x6 ? dh->w3lo : nullptr);
     cudaError_t e0 = cudaGetLastError();
     if (e0 != cudaSuccess) return e0;
     if (launches) *launches += 1;
@@ -3108,6 +3155,11 @@ static bool dh_desc(const nl_desc* d, nl_desc* dd) {
 static size_t dh_f_bytes(const nl_desc* d) {
   return tc_align((size_t)d->D * d->n * (size_t)d->T * d->B * sizeof(float2), 256);
 }
+// third W3 operand images of the forward's three-term split (workspace of the forward pass)
+static size_t dh_w3lo_bytes(const nl_desc* dd) {
+  const TcGeom g = tc_geom(dd, false, false, 3);
+  return tc_align((size_t)g.nch * tc::image_bytes(g.NP, tc::kH), 256);
+}
 
 TcPlan tc_dh_plan(const nl_desc* d, int pass) {
   nl_desc dd;
@@ -3115,7 +3167,9 @@ TcPlan tc_dh_plan(const nl_desc* d, int pass) {
   TcPlan pl = tc_plan(&dd, pass);
   if (!pl.ok) return pl;
   if (pass != 0 && tc_saved_bytes(&dd) == 0) return TcPlan{};
-  pl.ws_bytes = tc_align(pl.ws_bytes, 256) + dh_f_bytes(d) + dehoog_qd_scratch_bytes(d, pass != 0) + 1024;
+  if (pass == 0 && !(tc_geom(&dd, false, false, 3).ok && tc_geom(&dd, false, true, 3).ok)) return TcPlan{};
+  pl.ws_bytes = tc_align(pl.ws_bytes, 256) + dh_f_bytes(d) + dehoog_qd_scratch_bytes(d, pass != 0) +
+                (pass == 0 ? dh_w3lo_bytes(&dd) : 0) + 1024;
   return pl;
 }
 
@@ -3145,7 +3199,8 @@ cudaError_t launch_fused_tc_dehoog(const nl_desc* d, bool bwd, const void* p, co
   }
   cudaError_t e;
   if (!bwd) {
-    DhExtra dh{F, nullptr};
+    DhExtra dh{F, nullptr, extra};
+    extra += dh_w3lo_bytes(&dd);
     e = launch_fused_tc_impl(&dd, false, p, t, weights, nullptr, nullptr, x, nullptr, nullptr, w, st, launches, saved,
                              nullptr, &dh);
     if (e != cudaSuccess) return e;
@@ -3160,7 +3215,7 @@ cudaError_t launch_fused_tc_dehoog(const nl_desc* d, bool bwd, const void* p, co
   e = launch_dehoog_qd(d, true, t, F, gx, nullptr, dF, extra, st);
   if (e != cudaSuccess) return e;
   if (launches) *launches += 1;
-  DhExtra dh{nullptr, dF};
+  DhExtra dh{nullptr, dF, nullptr};
   return launch_fused_tc_impl(&dd, true, p, t, weights, nullptr, nullptr, nullptr, gx, grads, w, st, launches, saved,
                               nullptr, &dh);
 }

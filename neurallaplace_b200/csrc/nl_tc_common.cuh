@@ -220,6 +220,33 @@ __device__ __forceinline__ void store_chunk8(unsigned char* img_hi, unsigned cha
   *reinterpret_cast<uint4*>(img_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// Three-term split v = hi + mid + lo (bf16 each, 24 mantissa bits: float32 exactly up to its last bit or two).
+// (hi, mid) are bit-identical to the two-term (hi, lo) pair.  Used where 2^-17 of operand representation error
+// is too much: the De Hoog forward, whose quotient-difference recurrence amplifies noise on F by 10^2..10^3.
+__device__ __forceinline__ void split3(float v0, float v1, uint32_t* hi, uint32_t* mid, uint32_t* lo) {
+  uint32_t h, m, l;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(v1), "f"(v0));
+  const float r0 = v0 - __uint_as_float(h << 16), r1 = v1 - __uint_as_float(h & 0xFFFF0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(m) : "f"(r1), "f"(r0));
+  const float q0 = r0 - __uint_as_float(m << 16), q1 = r1 - __uint_as_float(m & 0xFFFF0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(q1), "f"(q0));
+  *hi = h;
+  *mid = m;
+  *lo = l;
+}
+
+// store 8 consecutive columns of row r into the three images img0 + {0, 1, 2} * img_stride
+__device__ __forceinline__ void store_chunk8x3(unsigned char* img0, size_t img_stride, int rows_in_image, int r,
+                                               int c0, const float* v) {
+  uint32_t h[4], m[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) split3(v[2 * i], v[2 * i + 1], &h[i], &m[i], &l[i]);
+  const size_t off = (size_t)(c0 >> 3) * ((size_t)rows_in_image * 16) + (size_t)r * 16;
+  *reinterpret_cast<uint4*>(img0 + off) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(img0 + img_stride + off) = make_uint4(m[0], m[1], m[2], m[3]);
+  *reinterpret_cast<uint4*>(img0 + 2 * img_stride + off) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
 // store 4 consecutive columns [c0, c0+4) of row r (c0 % 4 == 0): half of a 16-byte piece
 __device__ __forceinline__ void store_chunk4(unsigned char* img_hi, unsigned char* img_lo, int rows_in_image, int r,
                                              int c0, const float* v) {
@@ -275,6 +302,28 @@ __device__ __forceinline__ void issue_gemm(const GemmOp& g, uint32_t d_tmem, boo
     else { a_lo = pass <= 1; b_lo = pass == 0 || pass == 2; }
     uint64_t ad = make_sdesc(g.a_hi + (a_lo ? g.a_lo_off : 0), g.a_lbo, g.a_sbo);
     uint64_t bd = make_sdesc(g.b_hi + (b_lo ? g.b_lo_off : 0), g.b_lbo, g.b_sbo);
+#pragma unroll 4
+    for (int ks = 0; ks < g.ksteps; ++ks) {
+      umma_bf16(d_tmem, ad, bd, g.idesc, acc);
+      acc = 1u;
+      ad += a_inc;
+      bd += b_inc;
+    }
+  }
+}
+
+// Six passes over three-term operands (images at hi + {0,1,2} * lo_off): every product down to 2^-24 relative
+//   hi.hi + (hi.mid + mid.hi) + (hi.lo + lo.hi + mid.mid)      ("bf16x6"; smallest terms first)
+__device__ __forceinline__ void issue_gemm6(const GemmOp& g, uint32_t d_tmem, bool accumulate) {
+  const uint64_t a_inc = (uint64_t)(g.a_step >> 4), b_inc = (uint64_t)(g.b_step >> 4);
+  uint32_t acc = accumulate ? 1u : 0u;
+#pragma unroll 1
+  for (int pass = 0; pass < 6; ++pass) {
+    // (a image, b image): (2,0) (0,2) (1,1) (1,0) (0,1) (0,0)
+    const int ai = pass == 0 ? 2 : (pass == 2 || pass == 3) ? 1 : 0;
+    const int bi = pass == 1 ? 2 : (pass == 2 || pass == 4) ? 1 : 0;
+    uint64_t ad = make_sdesc(g.a_hi + ai * g.a_lo_off, g.a_lbo, g.a_sbo);
+    uint64_t bd = make_sdesc(g.b_hi + bi * g.b_lo_off, g.b_lbo, g.b_sbo);
 #pragma unroll 4
     for (int ks = 0; ks < g.ksteps; ++ks) {
       umma_bf16(d_tmem, ad, bd, g.idesc, acc);

@@ -64,30 +64,50 @@ def test_tc_against_oracle(alg, terms, B, T, D, K, sphere, stash, monkeypatch):
 
 DEHOOG_CASES = [
     # terms, B, T, D, K, sphere
-    (33, 130, 7, 1, 2, True),
-    (33, 300, 12, 2, 3, True),
-    (17, 200, 9, 1, 2, True),
-    (65, 150, 4, 1, 2, True),
+    (33, 128, 8, 1, 2, True),
+    (33, 192, 6, 2, 3, True),
+    (17, 128, 9, 1, 2, True),
+    (65, 128, 4, 1, 2, True),
     (33, 160, 5, 1, 7, False),
 ]
 
 
+def _dehoog_protocol(weights, p, t, D, sphere, terms, gout, dev, G, what):
+  """The robust float32 De Hoog comparison of tests/helpers.py (SURVEY section 8d's 4x factor on outlier-proof
+  statistics): returns nothing, asserts."""
+  B = p.shape[0]
+  x32, g32 = hp.oracle_group_grads(weights, p, t, D, "dehoog", sphere, terms, gout, G)
+  x64, g64 = hp.oracle_group_grads([w.double() for w in weights], p.double(), t.double(), D, "dehoog", sphere, terms,
+                                   gout.double(), G)
+  groups, x = [], None
+  for gi in range(G):
+    x, grads = _run_product(weights, p, t, D, "dehoog", sphere, terms, None, gout * hp.group_mask(B, G, gi), dev)
+    groups.append([q.detach().cpu() for q in grads])
+  rm, r90 = hp.pointwise_ratios(x, x32, x64)
+  print(f"\n[{what}] terms={terms} B={B} T={t.numel()} D={D}: pointwise |x - x64| vs reference-f32: median x{rm:.2f} "
+        f"p90 x{r90:.2f}   (normwise: ours {hp.rel(x, x64):.1e} reference-f32 {hp.rel(x32, x64):.1e})")
+  assert rm <= hp.DEHOOG_FACTOR and r90 <= hp.DEHOOG_FACTOR, (rm, r90)
+  for i, (em, er, ratio) in enumerate(hp.group_median_ratios(groups, g32, g64)):
+    print(f"    grad{i}: median-over-groups normwise error ours {em:.2e} reference-f32 {er:.2e}  x{ratio:.2f}")
+    assert em <= hp.DEHOOG_FACTOR * er + 1e-4, (i, em, er)
+
+
 @pytest.mark.parametrize("terms,B,T,D,K,sphere", DEHOOG_CASES)
 def test_tc_dehoog_against_oracle(terms, B, T, D, K, sphere, monkeypatch):
-  """De Hoog with the MLP on the tensor cores (F / dF planes + the per-thread quotient-difference recurrence).
-  The float32 recurrence is ill-conditioned: the oracle's own float32 run is 1e-4..1e-2 off its float64 run on x
-  and up to O(1) on the gradients, and so are the SIMT kernels.  The bf16x3 GEMMs put ~1e-5 of relative noise on
-  F (1e-7 for the float32 FMA paths), which the recurrence amplifies the same way.  The bar is therefore stated
-  against float64: the tensor-core path must stay within one order of magnitude of the float32 implementations'
-  own distance from float64 (oracle in float32, SIMT kernels), per tensor."""
+  """De Hoog with the MLP on the tensor cores (default float32 path from 16 batch rows): the forward evaluates
+  layers 2-3 with a THREE-term operand split (hi|mid|lo, six bf16 passes: F to float32 accuracy), writes F planes,
+  the per-thread quotient-difference recurrence turns them into x; the saved backward reads dL/dF.
+  Bar: SURVEY section 8d -- error against the float64 oracle no more than 4x the reference-float32 error against
+  the float64 oracle -- on the outlier-proof statistics of tests/helpers.py (x pointwise median / p90; gradients
+  median over 8 row groups), the same protocol for the SIMT kernels (float32 FMA)."""
   if not torch.cuda.is_available():
     pytest.skip("no CUDA device")
   dev = torch.device("cuda", 0)
-  monkeypatch.setenv("NL_B200_IMPL", "tc")
   from neurallaplace_b200 import _consts, _ops
   from oracle import nl_oracle as orc
   n = orc.IltConsts("dehoog", terms).n
   c = _consts.get("dehoog", terms, torch.float32)
+  # auto mode picks the tensor-core kernels here, forward and backward, with an activation stash
   assert _ops.selected_impl(c, torch.float32, B, T, K, 64, D, 0, 0 if sphere else 1, 0) == 2
   assert _ops.selected_impl(c, torch.float32, B, T, K, 64, D, 0, 0 if sphere else 1, 1) == 2
   assert _ops.saved_bytes(c, torch.float32, B, T, K, 64, D, 0, 0 if sphere else 1) > 0
@@ -96,20 +116,9 @@ def test_tc_dehoog_against_oracle(terms, B, T, D, K, sphere, monkeypatch):
   p = torch.randn(B, K, generator=g)
   t = torch.linspace(20.0 / T, 20.0, T)
   gout = torch.randn(B, T, D, generator=g)
-  x32, g32 = hp.oracle_run(weights, p, t, D, "dehoog", sphere, terms, None, gout)
-  x64, g64 = hp.oracle_run([w.double() for w in weights], p.double(), t.double(), D, "dehoog", sphere, terms, None,
-                           gout.double())
-  x, grads = _run_product(weights, p, t, D, "dehoog", sphere, terms, None, gout, dev)
+  _dehoog_protocol(weights, p, t, D, sphere, terms, gout, dev, 8, "tc dehoog")
   monkeypatch.setenv("NL_B200_IMPL", "simt")
-  xs, gs = _run_product(weights, p, t, D, "dehoog", sphere, terms, None, gout, dev)
-  floor = 1e-5
-  ex, eo, es = hp.rel(x, x64), hp.rel(x32, x64), hp.rel(xs, x64)
-  print(f"\n[tc dehoog] terms={terms} B={B} T={T} D={D}: x tc {ex:.2e} simt {es:.2e} oracle32 {eo:.2e}")
-  assert ex <= 10 * max(eo, es) + floor, (ex, eo, es)
-  for i, (a, b32, b64, bs) in enumerate(zip(grads, g32, g64, gs)):
-    e, eo, es = hp.rel(a, b64), hp.rel(b32, b64), hp.rel(bs, b64)
-    print(f"    grad{i}: tc {e:.2e} simt {es:.2e} oracle32 {eo:.2e}")
-    assert e <= 10 * max(eo, es) + floor, (i, e, eo, es)
+  _dehoog_protocol(weights, p, t, D, sphere, terms, gout, dev, 8, "simt dehoog")
 
 
 def test_tc_dehoog_without_stash_falls_back_for_backward(monkeypatch):
@@ -127,10 +136,4 @@ def test_tc_dehoog_without_stash_falls_back_for_backward(monkeypatch):
   p = torch.randn(B, K, generator=g)
   t = torch.linspace(0.5, 10.0, T)
   gout = torch.randn(B, T, D, generator=g)
-  x32, g32 = hp.oracle_run(weights, p, t, D, "dehoog", True, terms, None, gout)
-  x64, g64 = hp.oracle_run([w.double() for w in weights], p.double(), t.double(), D, "dehoog", True, terms, None,
-                           gout.double())
-  x, grads = _run_product(weights, p, t, D, "dehoog", True, terms, None, gout, dev)
-  assert hp.rel(x, x64) <= 10 * hp.rel(x32, x64) + 1e-5
-  for a, b32, b64 in zip(grads, g32, g64):
-    assert hp.rel(a, b64) <= 10 * hp.rel(b32, b64) + 1e-4
+  _dehoog_protocol(weights, p, t, D, True, terms, gout, dev, 4, "tc fwd / simt bwd dehoog")

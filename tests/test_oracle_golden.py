@@ -69,3 +69,28 @@ def test_sphere_edge_cases(golden_dir):
   F = orc.sphere_to_complex(torch.from_numpy(z["sph_theta"]), torch.from_numpy(z["sph_phi"]))
   assert torch.allclose(F.real, torch.from_numpy(z["sph_sr"]))
   assert torch.allclose(F.imag, torch.from_numpy(z["sph_si"]))
+
+
+def test_flattened_dehoog_oracle_equals_the_reference_loop():
+  """tests/helpers.fast_dehoog_batched (the (b, d) loop of DeHoog.line_integrate_all_multi flattened into rows of
+  one call) gives the values of the loop form, forward and backward -- it only exists to keep the robust float32
+  De Hoog protocol of the GPU tests fast."""
+  import torch
+  from oracle import nl_oracle as orc
+  from tests import helpers as hp
+  for dtype, tol in ((torch.float64, 1e-13), (torch.float32, 1e-5)):
+    g = torch.Generator().manual_seed(3)
+    w = orc.make_canonical_weights(17, 2, 2, dtype=dtype, seed=1)
+    p = torch.randn(5, 2, generator=g).to(dtype)
+    t = torch.linspace(0.5, 9.0, 6).to(dtype)
+    gout = torch.randn(5, 6, 2, generator=g).to(dtype)
+    x0, g0 = hp.oracle_run(w, p, t, 2, "dehoog", True, 17, None, gout)
+    with hp.fast_dehoog_oracle():
+      x1, g1 = hp.oracle_run(w, p, t, 2, "dehoog", True, 17, None, gout)
+    assert hp.rel(x1, x0) <= tol
+    if dtype == torch.float64:
+      for a, b in zip(g1, g0):
+        assert hp.rel(a, b) <= tol * 1e3
+    # float32: the SAME op chain evaluated over a different row arrangement (another SIMD / scalar split of the
+    # complex divisions) already moves the float32 gradients by tens of percent -- they are noise in the reference
+    # itself, which is why the GPU tests compare float32 De Hoog on outlier-proof statistics against float64.
