@@ -45,6 +45,40 @@ def _workspace(lib, d, which, device):
 # ------------------------------------------------------------------------------------------
 # fused reconstruct
 # ------------------------------------------------------------------------------------------
+def launch_forward(lib, d, pc, tc, weights, beta, eta, x, ws, nbytes, saved):
+  """nl_reconstruct_forward[_save] on the current stream of the tensors' device.  Allocation-free and
+  stream-ordered: also what engine.GraphedReconstruct captures into a CUDA graph."""
+  dev = pc.device
+  with _lib.on(dev):
+    if saved is not None:
+      st = lib.nl_reconstruct_forward_save(ctypes.byref(d), _lib.ptr(pc), _lib.ptr(tc), _lib.ptr_array(weights),
+                                           _lib.ptr(beta), _lib.ptr(eta), _lib.ptr(x), _lib.ptr(saved),
+                                           saved.numel(), _lib.ptr(ws), nbytes, _lib.stream_ptr(dev))
+    else:
+      st = lib.nl_reconstruct_forward(ctypes.byref(d), _lib.ptr(pc), _lib.ptr(tc), _lib.ptr_array(weights),
+                                      _lib.ptr(beta), _lib.ptr(eta), _lib.ptr(x), _lib.ptr(ws), nbytes,
+                                      _lib.stream_ptr(dev))
+  _lib.check(st)
+  _stats["launches"] += lib.nl_last_launch_count()
+
+
+def launch_backward(lib, d, pc, tc, weights, beta, eta, gxc, grads, ws, nbytes, saved):
+  """nl_reconstruct_backward[_saved]; ``grads`` = [dW1, db1, dW2, db2, dW3, db3, dp], every one overwritten."""
+  dev = pc.device
+  with _lib.on(dev):
+    if saved is not None:
+      st = lib.nl_reconstruct_backward_saved(ctypes.byref(d), _lib.ptr(pc), _lib.ptr(tc), _lib.ptr_array(weights),
+                                             _lib.ptr(beta), _lib.ptr(eta), _lib.ptr(gxc), _lib.ptr(saved),
+                                             saved.numel(), _lib.ptr_array(grads), _lib.ptr(ws), nbytes,
+                                             _lib.stream_ptr(dev))
+    else:
+      st = lib.nl_reconstruct_backward(ctypes.byref(d), _lib.ptr(pc), _lib.ptr(tc), _lib.ptr_array(weights),
+                                       _lib.ptr(beta), _lib.ptr(eta), _lib.ptr(gxc), _lib.ptr_array(grads),
+                                       _lib.ptr(ws), nbytes, _lib.stream_ptr(dev))
+  _lib.check(st)
+  _stats["launches"] += lib.nl_last_launch_count()
+
+
 class ReconstructFn(torch.autograd.Function):
   """x = laplace_reconstruct(canonical MLP, p, t) as ONE fused forward and ONE fused backward."""
 
@@ -64,8 +98,8 @@ class ReconstructFn(torch.autograd.Function):
     # Training: keep the two hidden activations for backward (the analogue of autograd's saved tensors,
     # 512 B per (b,t) point) so that backward does not recompute layers 1-2.  NL_B200_STASH=0 disables it.
     # ``stash`` is decided by the caller (grad mode on AND something requires grad): ctx.needs_input_grad stays
-    # True under torch.no_grad() and would make inference pay for the stash.  Above NL_B200_STASH_MAX_GB
-    # (default: 60 % of the free device memory) or when the allocation fails, backward recomputes instead.
+    # True under torch.no_grad() and would make inference pay for the stash.  Above NL_B200_STASH_MAX_GB or when
+    # the allocation fails, backward recomputes instead.
     saved, saved_bytes = None, 0
     if stash and any(ctx.needs_input_grad) and os.environ.get("NL_B200_STASH", "1") != "0":
       saved_bytes = int(lib.nl_saved_bytes(ctypes.byref(d)))
@@ -74,17 +108,7 @@ class ReconstructFn(torch.autograd.Function):
           saved = torch.empty(saved_bytes, dtype=torch.uint8, device=dev)
         except torch.OutOfMemoryError:
           saved = None
-    with _lib.on(dev):
-      if saved is not None:
-        st = lib.nl_reconstruct_forward_save(ctypes.byref(d), _lib.ptr(pc), _lib.ptr(tc), _lib.ptr_array(weights),
-                                             _lib.ptr(beta), _lib.ptr(eta), _lib.ptr(x), _lib.ptr(saved),
-                                             saved_bytes, _lib.ptr(ws), nbytes, _lib.stream_ptr(dev))
-      else:
-        st = lib.nl_reconstruct_forward(ctypes.byref(d), _lib.ptr(pc), _lib.ptr(tc), _lib.ptr_array(weights),
-                                        _lib.ptr(beta), _lib.ptr(eta), _lib.ptr(x), _lib.ptr(ws), nbytes,
-                                        _lib.stream_ptr(dev))
-    _lib.check(st)
-    _stats["launches"] += lib.nl_last_launch_count()
+    launch_forward(lib, d, pc, tc, weights, beta, eta, x, ws, nbytes, saved)
     ctx.save_for_backward(pc, tc, *weights)
     ctx.meta = (consts, D, t_mode, head, impl)
     ctx.saved_act = saved
@@ -103,34 +127,27 @@ class ReconstructFn(torch.autograd.Function):
     d = _desc(consts, pc.dtype, B, T, K, H, D, t_mode, head, impl)
     ws, nbytes = _workspace(lib, d, 1, dev)
     beta, eta = consts.tables_on(dev)
-    grads = [torch.empty_like(w) for w in weights] + [torch.empty_like(pc)]
+    # the six MLP gradients are views of ONE flat buffer (W1|b1|W2|b2|W3|b3): the data-parallel all-reduce and
+    # the fused clip + Adam step then work on it in place, with no pack / unpack copies (parallel.py, optim.py)
+    flat = torch.empty(sum(w.numel() for w in weights), dtype=pc.dtype, device=dev)
+    grads, off = [], 0
+    for w in weights:
+      grads.append(flat[off:off + w.numel()].view(w.shape))
+      off += w.numel()
+    del flat
+    grads.append(torch.empty_like(pc))
     gxc = gx.contiguous()
-    saved = ctx.saved_act
-    with _lib.on(dev):
-      if saved is not None:
-        st = lib.nl_reconstruct_backward_saved(ctypes.byref(d), _lib.ptr(pc), _lib.ptr(tc), _lib.ptr_array(weights),
-                                               _lib.ptr(beta), _lib.ptr(eta), _lib.ptr(gxc), _lib.ptr(saved),
-                                               saved.numel(), _lib.ptr_array(grads), _lib.ptr(ws), nbytes,
-                                               _lib.stream_ptr(dev))
-      else:
-        st = lib.nl_reconstruct_backward(ctypes.byref(d), _lib.ptr(pc), _lib.ptr(tc), _lib.ptr_array(weights),
-                                         _lib.ptr(beta), _lib.ptr(eta), _lib.ptr(gxc), _lib.ptr_array(grads),
-                                         _lib.ptr(ws), nbytes, _lib.stream_ptr(dev))
-    _lib.check(st)
-    _stats["launches"] += lib.nl_last_launch_count()
+    launch_backward(lib, d, pc, tc, weights, beta, eta, gxc, grads, ws, nbytes, ctx.saved_act)
     gW1, gb1, gW2, gb2, gW3, gb3, gp = grads
     return gp, None, gW1, gb1, gW2, gb2, gW3, gb3, None, None, None, None, None, None
 
 
-def _stash_budget(dev):
-  """Largest activation stash (bytes) the training forward may allocate on ``dev``."""
+def _stash_budget(dev):  # pylint: disable=unused-argument
+  """Largest activation stash (bytes) the training forward may allocate: NL_B200_STASH_MAX_GB, default no cap
+  (an allocation that fails falls back to the recomputing backward; querying free memory per call would cost a
+  driver round trip on the hot path)."""
   cap = os.environ.get("NL_B200_STASH_MAX_GB")
-  if cap is not None:
-    return int(float(cap) * (1 << 30))
-  free, _total = torch.cuda.mem_get_info(dev)
-  # memory torch has cached but not in use is reusable too
-  free += torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
-  return int(0.6 * free)
+  return int(float(cap) * (1 << 30)) if cap is not None else (1 << 62)
 
 
 def fused_supported(consts, dtype, B, T, K, H, D, t_mode, head, impl=0):

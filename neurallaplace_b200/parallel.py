@@ -33,14 +33,41 @@ def shard_batch(p, t=None, rank=None, world_size=None):
   return ps, t
 
 
+def flat_gradient_view(params):
+  """The ONE flat tensor the gradients of ``params`` tile, or None.
+
+  The fused backward (``_ops.ReconstructFn.backward``) writes dW1|db1|dW2|db2|dW3|db3 as views of one flat buffer
+  and autograd adopts those views as ``.grad`` without copying, so the data-parallel exchange can run on the
+  buffer in place.  Returns None when any ``.grad`` is missing or the gradients do not tile one storage in
+  parameter order (e.g. they were accumulated over several backward passes into separate tensors)."""
+  grads = [q.grad for q in params]
+  if not grads or any(g is None or not g.is_contiguous() for g in grads):
+    return None
+  g0 = grads[0]
+  base, off = g0.untyped_storage().data_ptr(), g0.storage_offset()
+  first = off
+  for g in grads:
+    if g.untyped_storage().data_ptr() != base or g.storage_offset() != off or g.dtype != g0.dtype:
+      return None
+    off += g.numel()
+  flat = torch.empty(0, dtype=g0.dtype, device=g0.device)
+  flat.set_(g0.untyped_storage(), first, (off - first,), (1,))
+  return flat
+
+
 class GradientAllReducer:
-  """Sum-all-reduce the gradients of a parameter list through one persistent flat buffer."""
+  """Sum-all-reduce the gradients of a parameter list as ONE message.
+
+  When the gradients already tile one flat buffer (what the fused backward produces, see ``flat_gradient_view``)
+  the all-reduce runs on it in place: one NCCL launch per step and nothing else.  Otherwise they are packed
+  into a persistent flat buffer and unpacked afterwards (2 x len(params) small copies)."""
 
   def __init__(self, params, group=None, average=False):
     self.params = [q for q in params if q.requires_grad]
     self.group = group
     self.average = average
     self._flat = None
+    self.in_place = None  # how the last call ran (True: directly on the backward's flat buffer)
 
   def _buffer(self):
     n = sum(q.numel() for q in self.params)
@@ -54,6 +81,13 @@ class GradientAllReducer:
     if not self.params:
       return
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+      return
+    flat = flat_gradient_view(self.params)
+    self.in_place = flat is not None
+    if flat is not None:
+      dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+      if self.average:
+        flat.div_(dist.get_world_size(self.group))
       return
     flat = self._buffer()
     off = 0
@@ -135,9 +169,13 @@ class HostStagedStep:
     if self.reducer is not None:
       self.reducer()
     if grads_host_out is not None:
-      off = 0
-      for q in self.params:
-        k = q.numel()
-        grads_host_out[off:off + k].copy_(q.grad.reshape(-1), non_blocking=True)
-        off += k
+      flat = flat_gradient_view(self.params)
+      if flat is not None:  # one D2H copy of the backward's flat gradient buffer
+        grads_host_out[:flat.numel()].copy_(flat, non_blocking=True)
+      else:
+        off = 0
+        for q in self.params:
+          k = q.numel()
+          grads_host_out[off:off + k].copy_(q.grad.reshape(-1), non_blocking=True)
+          off += k
     return p_d

@@ -4,8 +4,8 @@ set -uo pipefail
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" | tee -a gpurun_out/summary.txt
-timeout 1500 python -m pytest tests -q -m gpu -x --timeout=600 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/summary.txt
-tail -25 gpurun_out/pytest_gpu.log
+timeout 1500 python -m pytest tests -q -m gpu --timeout=600 -s ${PYTEST_EXTRA:-} > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/summary.txt
+grep -E "passed|failed|FAILED|Error" gpurun_out/pytest_gpu.log | tail -25
 timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?" | tee -a gpurun_out/summary.txt
 cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
 tail -8 gpurun_out/smoke.log

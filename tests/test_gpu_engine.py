@@ -1,0 +1,54 @@
+"""GPU (-m gpu): engine.GraphedReconstruct (CUDA-graph replay of the fused forward / backward for fixed shapes)
+gives the values of laplace_reconstruct + autograd, stays correct across replays with new inputs and updated
+weights, and the gradients of the eager path tile one flat buffer (parallel.flat_gradient_view)."""
+import pytest
+import torch
+
+from tests import helpers as hp
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("alg,terms,B,T,D,dtype", [("fourier", 33, 128, 100, 1, torch.float32),
+                                                   ("fourier", 33, 8, 20, 2, torch.float64),
+                                                   ("euler", 33, 300, 7, 2, torch.float32),
+                                                   ("dehoog", 17, 64, 9, 1, torch.float32)])
+def test_graphed_step_matches_the_eager_path(alg, terms, B, T, D, dtype):
+  if not torch.cuda.is_available():
+    pytest.skip("no CUDA device")
+  dev = torch.device("cuda", 0)
+  from neurallaplace_b200 import laplace_reconstruct, parallel
+  from neurallaplace_b200.engine import GraphedReconstruct
+  from oracle import nl_oracle as orc
+  n = orc.IltConsts(alg, terms).n
+  weights = orc.make_canonical_weights(n, D, 2, dtype=dtype, seed=3)
+  f = hp.make_module([w.to(dev) for w in weights], n, D, 2, True, dev)
+  step = GraphedReconstruct(f, B, T, recon_dim=D, ilt_algorithm=alg, ilt_reconstruction_terms=terms)
+  assert step.launches_per_step >= 2
+  g = torch.Generator().manual_seed(B + T)
+  tol = 1e-10 if dtype == torch.float64 else 1e-6
+  for it in range(3):
+    p = torch.randn(B, 2, generator=g).to(dtype).to(dev)
+    t = (torch.rand(T, generator=g) * 10 + 0.1).to(dtype).to(dev)
+    gout = torch.randn(B, T, D, generator=g).to(dtype).to(dev)
+    if it == 2:  # weights change between replays (an optimiser step): the graph reads them in place
+      with torch.no_grad():
+        for q in f.parameters():
+          q.mul_(1.01)
+    x = step.forward(p, t).clone()
+    flat, dp = step.backward(gout)
+    for q in f.parameters():
+      q.grad = None
+    pe = p.clone().requires_grad_(True)
+    xe = laplace_reconstruct(f, pe, t, recon_dim=D, ilt_algorithm=alg, ilt_reconstruction_terms=terms)
+    xe.backward(gout)
+    # same kernels, same inputs.  (De Hoog float32 gradients are only reproducible to the recurrence's noise
+    # when atomics reorder sums; everything else is deterministic.)
+    gt = 5e-2 if alg == "dehoog" else tol
+    assert hp.rel(x, xe) <= tol
+    assert hp.rel(dp, pe.grad) <= gt
+    eager_flat = parallel.flat_gradient_view(list(hp.module_params(f)))
+    assert eager_flat is not None  # the eager backward's gradients tile ONE buffer
+    assert hp.rel(flat, eager_flat) <= gt
+  step.assign_grads()
+  assert all(q.grad.data_ptr() == v.data_ptr() for q, v in zip(hp.module_params(f), step.grads))

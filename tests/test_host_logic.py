@@ -191,6 +191,23 @@ def _gloo_worker(rank, world, port, q):
   red = parallel.GradientAllReducer(m.parameters())
   red()
   ok = all(torch.allclose(q_.grad, torch.full_like(q_, 3.0 * (i + 1))) for i, q_ in enumerate(m.parameters()))
+  ok = ok and red.in_place is False  # separate .grad tensors: packed into the persistent flat buffer
+  # gradients that tile ONE flat buffer (what the fused backward produces): all-reduced in place, no copies
+  params = list(m.parameters())
+  flat = torch.empty(sum(q_.numel() for q_ in params))
+  off = 0
+  for i, q_ in enumerate(params):
+    q_.grad = flat[off:off + q_.numel()].view(q_.shape)
+    q_.grad.fill_(float(rank + 1) * (i + 1))
+    off += q_.numel()
+  ptr = flat.data_ptr()
+  red()
+  ok = ok and red.in_place is True and params[0].grad.data_ptr() == ptr
+  ok = ok and all(torch.allclose(q_.grad, torch.full_like(q_, 3.0 * (i + 1))) for i, q_ in enumerate(params))
+  view = parallel.flat_gradient_view(params)
+  ok = ok and view is not None and view.data_ptr() == ptr and view.numel() == flat.numel()
+  params[1].grad = params[1].grad.clone()  # no longer one buffer
+  ok = ok and parallel.flat_gradient_view(params) is None
   lo, hi = parallel.shard_range(7)
   q.put((rank, ok, lo, hi))
   dist.destroy_process_group()
