@@ -13,7 +13,8 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libnl_b200.so")
+# NL_B200_LIB: another build of the same library (the -DNL_TC_PROFILE variant of scripts/gpu_phase_profile.sh)
+LIB_PATH = os.environ.get("NL_B200_LIB") or os.path.join(_HERE, "lib", "libnl_b200.so")
 
 NL_F32, NL_F64 = 0, 1
 NL_FOURIER, NL_AW, NL_DEHOOG = 0, 1, 2

@@ -13,6 +13,7 @@
 //                                               would lose it near the pole, where r ~ 1/(1-tau)).
 #pragma once
 #include "nl_common.cuh"
+#include "nl_pack2.cuh"
 
 namespace nl {
 namespace fast {
@@ -108,6 +109,86 @@ __device__ __forceinline__ void head_backward(int head, const Head& h, float gre
   const float gr = gre * h.cs + gim * h.sn;
   *goa = gtheta * h.da;
   *gob = gr * fmaf(h.r, h.r, 1.f) * 0.5f * h.db;
+}
+
+
+// ---- packed (two at a time) versions: same formulas, FMA-pipe work as FADD2 / FMUL2 / FFMA2 (nl_pack2.cuh) ----
+// tanh of two hidden units.  The epilogues are bound by the MUFU pipe (16 lanes / clk / SM), so the two share ONE
+// reciprocal: 1/(1+E0) = R (1+E1), 1/(1+E1) = R (1+E0) with R = 1/((1+E0)(1+E1)) -- 3 MUFU operations for two tanh
+// instead of 4.  E is clamped at 2^60 (tanh is exactly +-1 in float long before) so that the product stays finite.
+__device__ __forceinline__ p2::f2 tanh_fast2(p2::f2 z) {
+  using namespace p2;
+  const f2 E = map2(mul2(z, bc(kTwoLog2e)), [](float v) { return ex2a(fminf(v, 60.f)); });
+  const f2 P = add2(bc(1.f), E);
+  float p0, p1;
+  unpk(P, p0, p1);
+  const float R = rcpa(p0 * p1);
+  return fma2(bc(-2.f), pk(R * p1, R * p0), bc(1.f));
+}
+
+// two head pairs (k, k+1) of the sphere head: oa = (o_a[k], o_a[k+1]), ob = (o_b[k], o_b[k+1])
+struct Head2 {
+  p2::f2 fre, fim, sn, cs, r, da, db;
+};
+template <bool NEED_GRAD>
+__device__ __forceinline__ Head2 head_forward2(p2::f2 oa, p2::f2 ob) {
+  using namespace p2;
+  Head2 h;
+  const f2 one = bc(1.f), c2 = bc(kTwoLog2e);
+  // E clamped at 2^30: 1 -+ tanh is below the 6e-8 floor used further down from there on, and the product of the
+  // four (1+E) of the two pairs stays finite -> ONE reciprocal serves all four tanh (MUFU-bound epilogue)
+  const f2 Ea = map2(mul2(oa, c2), [](float v) { return ex2a(fminf(v, 30.f)); });
+  const f2 Eb = map2(mul2(ob, c2), [](float v) { return ex2a(fminf(v, 30.f)); });
+  const f2 pa = add2(one, Ea), pb = add2(one, Eb);
+  const f2 pp = mul2(pa, pb);
+  float pp0, pp1;
+  unpk(pp, pp0, pp1);
+  const float R4 = rcpa(pp0 * pp1);
+  const f2 R = pk(R4 * pp1, R4 * pp0);  // 1 / (pa pb) of each pair
+  const f2 Da = mul2(R, pb), Db = mul2(R, pa);
+  // theta = pi * tanh = pi - 2 pi D_a
+  const f2 theta = fma2(bc(-2.f * (float)kPi), Da, bc((float)kPi));
+  h.sn = map2(theta, [](float v) { return sina(v); });
+  h.cs = map2(theta, [](float v) { return cosa(v); });
+  const f2 d2 = add2(Db, Db);
+  const f2 a1 = map2(d2, [](float v) { return fmaxf(v, 6e-8f); });
+  const f2 b1 = map2(mul2(d2, Eb), [](float v) { return fmaxf(v, 6e-8f); });
+  if (NEED_GRAD) {
+    h.da = mul2(mul2(bc((float)(4.0 * kPi)), Ea), mul2(Da, Da));
+    h.db = mul2(bc((float)(0.5 * kPi)), mul2(a1, b1));
+  }
+  const f2 w = mul2(bc((float)(0.25 * kPi)), zip2(a1, b1, [](float x, float y) { return fminf(x, y); }));
+  const f2 w2 = mul2(w, w);
+  f2 sw = fma2(w2, bc(2.7557319e-6f), bc(-1.9841270e-4f));
+  sw = fma2(w2, sw, bc(8.3333333e-3f));
+  sw = fma2(w2, sw, bc(-1.6666667e-1f));
+  sw = fma2(mul2(w2, w), sw, w);
+  f2 cw = fma2(w2, bc(2.4801587e-5f), bc(-1.3888889e-3f));
+  cw = fma2(w2, cw, bc(4.1666667e-2f));
+  cw = fma2(w2, cw, bc(-0.5f));
+  cw = fma2(w2, cw, one);
+  float a1x, a1y, b1x, b1y, swx, swy, cwx, cwy;
+  unpk(a1, a1x, a1y);
+  unpk(b1, b1x, b1y);
+  unpk(sw, swx, swy);
+  unpk(cw, cwx, cwy);
+  const bool ux = a1x < b1x, uy = a1y < b1y;  // tau_b > 0: r = cot(w) > 1
+  const f2 num = pk(ux ? cwx : swx, uy ? cwy : swy);
+  const float d0 = ux ? swx : cwx, d1 = uy ? swy : cwy;  // in [sin(pi/4 * 6e-8), 1]: the product cannot over/underflow
+  const float Rd = rcpa(d0 * d1);
+  h.r = mul2(num, pk(Rd * d1, Rd * d0));
+  h.fre = mul2(h.r, h.cs);
+  h.fim = mul2(h.r, h.sn);
+  return h;
+}
+
+// dL/dF -> dL/d(o_a), dL/d(o_b) for the two pairs
+__device__ __forceinline__ void head_backward2(const Head2& h, p2::f2 gre, p2::f2 gim, p2::f2* goa, p2::f2* gob) {
+  using namespace p2;
+  const f2 gtheta = mul2(h.r, sub2(mul2(gim, h.cs), mul2(gre, h.sn)));
+  const f2 gr = fma2(gre, h.cs, mul2(gim, h.sn));
+  *goa = mul2(gtheta, h.da);
+  *gob = mul2(mul2(gr, fma2(h.r, h.r, bc(1.f))), mul2(bc(0.5f), h.db));
 }
 
 // atan(t) for t in [0, 1]: t * P(t^2), degree-8 least-squares fit on Chebyshev nodes; max abs error 9e-8 in float.

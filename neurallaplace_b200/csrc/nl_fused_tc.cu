@@ -113,6 +113,7 @@ struct TcArgs {
   const float* row_scale;
   int h1_from_stash, store_h2;
   unsigned char* zstash;
+  int ctas;              // forward: CTAs per SM the launch is sized for (2, or 3 with the aliased h2 image)
   int h2sep;             // forward + stash: h2 has its own image (else it aliases h1 and two more barriers order the bulk stores)
   // De Hoog (DH instantiations): the forward writes F = head(layer 3) instead of reducing it, the saved backward
   // reads dL/dF instead of forming it from grad_x and the reduction coefficients; both [d][k][t][b] float2
@@ -154,7 +155,7 @@ __host__ __device__ inline TcSmem tc_smem(bool bwd, int NP, int nch, int nkc, in
   L.b3 = f; f += (nch * NP <= kMaxB3Smem) ? nch * NP : 0;  // else b3 is read from the global pack
   L.coef = f; f += nkc * NP;
   L.u = f; f += 2 * n + 8;
-  L.G1 = f; f += kH * 8;
+  L.G1 = f; f += bwd ? kH * 8 : 0;
   L.xacc = f; f += 4 * kRows;
   L.misc = f; f += 16;
   L.nfloats = f;
@@ -168,7 +169,7 @@ struct TcTmem {
 __host__ __device__ inline TcTmem tc_tmem(bool bwd, int NP, int acc_slots) {
   TcTmem t;
   t.S = 0;
-  t.O = 64;
+  t.O = bwd ? 64 : 0;  // forward: O overwrites Z2 (h2 has been formed and the CTA has synchronised before L3 is issued)
   t.dW2 = 64 + NP;
   t.D1 = t.dW2 + (bwd ? 80 : 0);
   t.dW3 = t.D1 + (bwd ? 16 : 0);
@@ -359,12 +360,15 @@ __global__ void __launch_bounds__(256) dp_reduce_kernel(const float* __restrict_
 // stores of the stash against the rewrites (used when a separate h2 image would cost the 2-CTA co-residency).
 // PR = true (forward only): per-row time grids -- h1 is not computed here but streamed from the stash (written by
 // point_layer1_kernel), x is scaled by the per-point prefactor.
-template <bool BWD, int KP, bool GENERAL, bool ALIAS = false, bool PR = false, bool DH = false>
-__global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 : 2) fused_tc_kernel(TcArgs A) {
+// MINB = 3 (forward, ALIAS, resident W3 only): compiled for three CTAs per SM (<= 80 registers; TMEM 128 columns,
+// shared memory <= a third of an SM) -- the forward is latency-bound at 16 warps per SM.
+template <bool BWD, int KP, bool GENERAL, bool ALIAS = false, bool PR = false, bool DH = false, int MINB = 2>
+__global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 : MINB) fused_tc_kernel(TcArgs A) {
   constexpr int kEWG = BWD ? kEwgBwd : kEwgFwd;
   constexpr int kThreadsTc = 128 * kEWG;
   constexpr int kColsPerWg = kH / kEWG;
-  constexpr uint32_t kTmemCols = BWD ? 512 : 256;
+  // forward: the layer-3 output reuses the columns of Z2 (read out before L3 is issued): 128 columns per CTA
+  constexpr uint32_t kTmemCols = BWD ? 512 : 128;
   // De Hoog forward: three-term operand split (hi | mid | lo images, six passes per GEMM): F to float32 accuracy --
   // the quotient-difference recurrence downstream amplifies noise on F by 10^2..10^3
   constexpr bool X6 = DH && !BWD;
@@ -430,7 +434,9 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
       else    store_chunk8(W2_hi, W2_lo, kH, tid, c0, v);
     }
     sb2[tid] = __ldg(A.b2 + tid);
-    for (int j = 0; j < K; ++j) sW1p[tid * 8 + j] = __ldg(A.W1 + (size_t)tid * ldw1 + 2 * n + j);
+    // forward: W1p transposed ([j][c]) so that two adjacent hidden units load as one float2 (packed FP32 math)
+    for (int j = 0; j < K; ++j)
+      sW1p[BWD ? tid * 8 + j : j * kH + tid] = __ldg(A.W1 + (size_t)tid * ldw1 + 2 * n + j);
   }
   const bool b3_in_smem = nch * NP <= kMaxB3Smem;
   if (b3_in_smem)
@@ -745,18 +751,34 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
     NL_PROF(0);
 
     // ---- 1. h1 = tanh(S1b + W1p.p) -> smem   (PR: the image was streamed in)
-    float h1[kColsPerWg];
+    float h1[BWD ? kColsPerWg : 1];
+    p2::f2 h1p[BWD ? 1 : kColsPerWg / 2];  // forward: pairs of adjacent hidden units (FFMA2 / FMUL2 / FADD2)
     if (PR) {
       mbar_wait(&bar_h1s, ph_h1s);
       ph_h1s ^= 1;
     }
+    if (BWD) {
 #pragma unroll
-    for (int i = 0; i < kColsPerWg; ++i) {
-      const int c = wg * kColsPerWg + i;
-      float z = sS1b[c];
+      for (int i = 0; i < kColsPerWg; ++i) {
+        const int c = wg * kColsPerWg + i;
+        float z = sS1b[c];
 #pragma unroll
-      for (int j = 0; j < KP; ++j) z = fmaf(sW1p[c * 8 + j], pv[j], z);
-      h1[i] = PR ? 0.f : fast::tanh_fast(z);
+        for (int j = 0; j < KP; ++j) z = fmaf(sW1p[c * 8 + j], pv[j], z);
+        h1[BWD ? i : 0] = fast::tanh_fast(z);
+      }
+    } else if (!PR) {
+#pragma unroll
+      for (int i = 0; i < kColsPerWg / 2; ++i) {
+        const int c = wg * kColsPerWg + 2 * i;
+        const float2 s1 = *reinterpret_cast<const float2*>(sS1b + c);
+        p2::f2 z = p2::pk(s1.x, s1.y);
+#pragma unroll
+        for (int j = 0; j < KP; ++j) {
+          const float2 w = *reinterpret_cast<const float2*>(sW1p + j * kH + c);
+          z = p2::fma2(p2::pk(w.x, w.y), p2::bc(pv[j]), z);
+        }
+        h1p[BWD ? 0 : i] = fast::tanh_fast2(z);
+      }
     }
     if (BWD) wait_d1();  // the previous tile's D1 GEMM reads the [1 p] chunk of the h1 image (and Z1g in the dO image)
     if (ALIAS) {  // aliased images: the bulk store of the previous tile's h2 must have read them
@@ -766,8 +788,9 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
     if (!PR) {
 #pragma unroll
       for (int i = 0; i < kColsPerWg; i += 8) {
-        if (X6) store_chunk8x3(H1_hi, L.H1_img, kRows, r, wg * kColsPerWg + i, &h1[i]);
-        else    store_chunk8(H1_hi, H1_lo, kRows, r, wg * kColsPerWg + i, &h1[i]);
+        if (BWD)     store_chunk8(H1_hi, H1_lo, kRows, r, wg * kColsPerWg + i, &h1[BWD ? i : 0]);
+        else if (X6) store_chunk8x3p(H1_hi, L.H1_img, kRows, r, wg * kColsPerWg + i, &h1p[BWD ? 0 : i / 2]);
+        else         store_chunk8p(H1_hi, H1_lo, kRows, r, wg * kColsPerWg + i, &h1p[BWD ? 0 : i / 2]);
       }
     }
     if (BWD && wg == 0) {
@@ -805,14 +828,23 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
     NL_PROF(2);
 
     // ---- 3. h2 = tanh(Z2 + b2) -> smem
-    float h2[kColsPerWg];
+    float h2[BWD ? kColsPerWg : 1];
+    p2::f2 h2p[BWD ? 1 : kColsPerWg / 2];
 #pragma unroll
     for (int i = 0; i < kColsPerWg; i += 16) {
       float v[16];
       tmem_ld16(lane_addr + TM.S + wg * kColsPerWg + i, v);
       tmem_ld_wait();
+      if (BWD) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) h2[i + j] = fast::tanh_fast(v[j] + sb2[wg * kColsPerWg + i + j]);
+        for (int j = 0; j < 16; ++j) h2[BWD ? i + j : 0] = fast::tanh_fast(v[j] + sb2[wg * kColsPerWg + i + j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+          const float2 bb = *reinterpret_cast<const float2*>(sb2 + wg * kColsPerWg + i + j);
+          h2p[BWD ? 0 : (i + j) / 2] = fast::tanh_fast2(p2::add2(p2::pk(v[j], v[j + 1]), p2::pk(bb.x, bb.y)));
+        }
+      }
     }
     if (ALIAS) {  // aliased images: the bulk store of h1 must have read them
       if (warp == 0 && elect_one()) bulk_wait_read_all();
@@ -820,8 +852,10 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
     }
 #pragma unroll
     for (int i = 0; i < kColsPerWg; i += 8) {
-      if (X6) store_chunk8x3(H2_hi, (BWD || h2sep) ? L.H2_img : L.H1_img, kRows, r, wg * kColsPerWg + i, &h2[i]);
-      else    store_chunk8(H2_hi, H2_lo, kRows, r, wg * kColsPerWg + i, &h2[i]);
+      if (BWD)     store_chunk8(H2_hi, H2_lo, kRows, r, wg * kColsPerWg + i, &h2[BWD ? i : 0]);
+      else if (X6) store_chunk8x3p(H2_hi, h2sep ? L.H2_img : L.H1_img, kRows, r, wg * kColsPerWg + i,
+                                   &h2p[BWD ? 0 : i / 2]);
+      else         store_chunk8p(H2_hi, H2_lo, kRows, r, wg * kColsPerWg + i, &h2p[BWD ? 0 : i / 2]);
     }
     fence_async_smem();
     tc_fence_before();
@@ -882,20 +916,42 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
       const float* bb3 = (!GENERAL || b3_in_smem) ? sb3 + ch * NP : A.b3pack + ch * NP;
       int c_lo = wg * cw;
       const int c_hi = min((wg + 1) * cw, ncols_real);
-      if (!BWD && !DH) {  // forward: eight columns (four head pairs) per TMEM load while they last (measured:
-        // 0.865 -> 0.839 ms against four columns per load; sixteen per load is slower, 0.888 ms)
+      if (!BWD && P.head == NL_HEAD_SPHERE) {
+        // forward, sphere head: eight columns (four head pairs) per TMEM load while they last, two pairs per
+        // packed evaluation (fast::head_forward2: the FMA-pipe work as FFMA2 / FMUL2 / FADD2)
+        p2::f2 xs2 = p2::pk(xsum, 0.f);
+        auto two_pairs = [&](const float* v, int c) {
+          const float4 bq = *reinterpret_cast<const float4*>(bb3 + c);
+          const fast::Head2 h = fast::head_forward2<false>(p2::add2(p2::pk(v[0], v[2]), p2::pk(bq.x, bq.z)),
+                                                           p2::add2(p2::pk(v[1], v[3]), p2::pk(bq.y, bq.w)));
+          if (DH) {
+            float fr0, fr1, fi0, fi1;
+            p2::unpk(h.fre, fr0, fr1);
+            p2::unpk(h.fim, fi0, fi1);
+            const int kk = c >> 1, k = kci * A.kc + kk;
+            float2* dst = A.fout + (size_t)(d * n + k) * A.f_plane + ((size_t)t_idx * A.B + b);
+            if (valid && kk < A.kc && k < n) dst[0] = make_float2(fr0, fi0);
+            if (valid && kk + 1 < A.kc && k + 1 < n) dst[A.f_plane] = make_float2(fr1, fi1);
+          } else {
+            const float4 cq = *reinterpret_cast<const float4*>(cf + c);
+            xs2 = p2::fma2(h.fre, p2::pk(cq.x, cq.z), xs2);
+            xs2 = p2::fma2(h.fim, p2::pk(-cq.y, -cq.w), xs2);
+          }
+        };
         for (; c_lo + 8 <= c_hi; c_lo += 8) {
           float v[8];
           tmem_ld8(lane_addr + TM.O + c_lo, v);
           tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int c = c_lo + 2 * i;
-            const fast::Head h = fast::head_forward(P.head, v[2 * i] + bb3[c], v[2 * i + 1] + bb3[c + 1]);
-            xsum = fmaf(h.fre, cf[c], xsum);
-            xsum = fmaf(-h.fim, cf[c + 1], xsum);
-          }
+          two_pairs(v, c_lo);
+          two_pairs(v + 4, c_lo + 4);
         }
+        for (; c_lo < c_hi; c_lo += 4) {
+          float v[4];
+          tmem_ld4(lane_addr + TM.O + c_lo, v);
+          tmem_ld_wait();
+          two_pairs(v, c_lo);
+        }
+        xsum = p2::lo(xs2) + p2::hi(xs2);
       }
       for (int c0 = c_lo; c0 < c_hi; c0 += 4) {
         float v[4], dv[4];
@@ -985,7 +1041,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
         tmem_ld16(lane_addr + TM.S + wg * kColsPerWg + i, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) z[i + j] = v[j] * (1.f - h2[i + j] * h2[i + j]);
+        for (int j = 0; j < 16; ++j) z[i + j] = v[j] * (1.f - h2[BWD ? i + j : 0] * h2[BWD ? i + j : 0]);
       }
       wait_dw3();  // dW3 of the last chunk reads the dO image
       tc_fence_after();
@@ -1034,7 +1090,7 @@ __global__ void __launch_bounds__(BWD ? 128 * kEwgBwd : 128 * kEwgFwd, BWD ? 1 :
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float zz = v[j] * (1.f - h1[i + j] * h1[i + j]);
+          const float zz = v[j] * (1.f - h1[BWD ? i + j : 0] * h1[BWD ? i + j : 0]);
           z[i + j] = zz;
           const int c = wg * kColsPerWg + i + j;
 #pragma unroll
@@ -2597,6 +2653,7 @@ static long long* g_prof_buf = nullptr;
 static size_t tc_align(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct TcGeom {
+  int ctas;  // forward: CTAs per SM (3: stash forward with the aliased h2 image inside a third of the SM)
   int h2sep;
   int nkc, kc, NP, nch, w3_slots, resident;
   size_t smem;
@@ -2638,6 +2695,18 @@ static TcGeom tc_geom(const nl_desc* d, bool bwd, bool stash = false, int nimg =
     const TcGeom sep = g;
     place(false);
     if (g.smem > half) g = sep;
+  }
+  g.ctas = 2;
+  if (!bwd && stash && nimg == 2) {
+    // three CTAs per SM (24 warps instead of 16: the forward is latency-bound): h2 aliases h1, every chunk resident
+    static const int want3 = [] { const char* v = getenv("NL_B200_FWD_CTAS"); return v ? atoi(v) : 3; }();
+    const tc::TcSmem La = tc::tc_smem(false, g.NP, g.nch, g.nkc, g.nch, d->n, false, nimg);
+    if (want3 == 3 && La.total + 1024 <= (size_t)(228 * 1024) / 3) {
+      g.ctas = 3;
+      g.h2sep = 0;
+      g.w3_slots = g.nch;
+      g.smem = La.total;
+    }
   }
   g.ok = g.smem <= limit;
   return g;
@@ -2743,12 +2812,13 @@ TcPlan tc_plan(const nl_desc* d, int pass) {
 cudaError_t launch_reduce_slabs_f32(const float* slab, long long slab_len, int nslabs, void* const* grads,
                                     const nl_desc* d, cudaStream_t st);
 
-template <bool BWD, int KP, bool GENERAL, bool ALIAS = false, bool PR = false, bool DH = false>
+template <bool BWD, int KP, bool GENERAL, bool ALIAS = false, bool PR = false, bool DH = false, int MINB = 2>
 static cudaError_t launch_tc1_g(const tc::TcArgs& A, int grid, size_t smem, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(tc::fused_tc_kernel<BWD, KP, GENERAL, ALIAS, PR, DH>,
+  cudaError_t e = cudaFuncSetAttribute(tc::fused_tc_kernel<BWD, KP, GENERAL, ALIAS, PR, DH, MINB>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  tc::fused_tc_kernel<BWD, KP, GENERAL, ALIAS, PR, DH><<<grid, 128 * (BWD ? tc::kEwgBwd : tc::kEwgFwd), smem, st>>>(A);
+  tc::fused_tc_kernel<BWD, KP, GENERAL, ALIAS, PR, DH, MINB>
+      <<<grid, 128 * (BWD ? tc::kEwgBwd : tc::kEwgFwd), smem, st>>>(A);
   return cudaGetLastError();
 }
 template <bool BWD, int KP>
@@ -2761,8 +2831,10 @@ static cudaError_t launch_tc1(const tc::TcArgs& A, int grid, size_t smem, cudaSt
   }
   if (!BWD && A.h1_from_stash)  // per-row time grids: h1 streamed from the stash (separate h2 image, resident W3)
     return launch_tc1_g<false, KP, false, false, true>(A, grid, smem, st);
-  if (!BWD && A.stash && !A.h2sep)  // (the stash needs every W3 chunk resident, so this is never the general kernel)
+  if (!BWD && A.stash && !A.h2sep) {  // (the stash needs every W3 chunk resident, so this is never the general kernel)
+    if (A.ctas == 3) return launch_tc1_g<false, KP, false, true, false, false, 3>(A, grid, smem, st);
     return launch_tc1_g<false, KP, false, true>(A, grid, smem, st);
+  }
   return general ? launch_tc1_g<BWD, KP, true>(A, grid, smem, st) : launch_tc1_g<BWD, KP, false>(A, grid, smem, st);
 }
 
@@ -2840,6 +2912,8 @@ static cudaError_t launch_fused_tc_impl(const nl_desc* d, bool bwd, const void* 
     pl.smem = g.smem;
     pl.co_resident = g.smem <= (227 * 1024 - 1024) / 2;
     pl.ring = g.w3_slots < g.nch;
+    if (g.ctas == 3) pl.grid = (int)std::min<long long>((long long)((d->B + tc::kRows - 1) / tc::kRows) * d->T,
+                                                        (long long)device_sm_count() * 3);
   }
   const BsGeom bg = (bwd && saved) ? bs_geom(d, g) : BsGeom{};
   tc::TcArgs A{};
@@ -2862,6 +2936,7 @@ static cudaError_t launch_fused_tc_impl(const nl_desc* d, bool bwd, const void* 
   A.x = (float*)x; A.gx = (const float*)gx;
   A.stash = (unsigned char*)saved;
   A.h2sep = g.h2sep;
+  A.ctas = g.ctas;
   if (dh) {
     A.fout = dh->fout;
     A.dfin = dh->dfin;

@@ -20,6 +20,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "nl_pack2.cuh"
+
 namespace nl {
 namespace tc {
 
@@ -245,6 +247,69 @@ __device__ __forceinline__ void store_chunk8x3(unsigned char* img0, size_t img_s
   *reinterpret_cast<uint4*>(img0 + off) = make_uint4(h[0], h[1], h[2], h[3]);
   *reinterpret_cast<uint4*>(img0 + img_stride + off) = make_uint4(m[0], m[1], m[2], m[3]);
   *reinterpret_cast<uint4*>(img0 + 2 * img_stride + off) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+
+// ---- packed variants (values arrive as FP32 pairs, nl_pack2.cuh): the residual subtraction is one FADD2 ----
+__device__ __forceinline__ void split2p(p2::f2 v, uint32_t* hi, uint32_t* lo) {
+  float v0, v1;
+  p2::unpk(v, v0, v1);
+  uint32_t h;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(v1), "f"(v0));
+  const p2::f2 r = p2::sub2(v, p2::pk(__uint_as_float(h << 16), __uint_as_float(h & 0xFFFF0000u)));
+  float r0, r1;
+  p2::unpk(r, r0, r1);
+  uint32_t l;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(r1), "f"(r0));
+  *hi = h;
+  *lo = l;
+}
+__device__ __forceinline__ void split3p(p2::f2 v, uint32_t* hi, uint32_t* mid, uint32_t* lo) {
+  float v0, v1;
+  p2::unpk(v, v0, v1);
+  uint32_t h, m, l;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(v1), "f"(v0));
+  const p2::f2 r = p2::sub2(v, p2::pk(__uint_as_float(h << 16), __uint_as_float(h & 0xFFFF0000u)));
+  float r0, r1;
+  p2::unpk(r, r0, r1);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(m) : "f"(r1), "f"(r0));
+  const p2::f2 q = p2::sub2(r, p2::pk(__uint_as_float(m << 16), __uint_as_float(m & 0xFFFF0000u)));
+  float q0, q1;
+  p2::unpk(q, q0, q1);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(q1), "f"(q0));
+  *hi = h;
+  *mid = m;
+  *lo = l;
+}
+// 8 consecutive columns given as four pairs
+__device__ __forceinline__ void store_chunk8p(unsigned char* img_hi, unsigned char* img_lo, int rows_in_image, int r,
+                                              int c0, const p2::f2* v) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) split2p(v[i], &h[i], &l[i]);
+  const size_t off = (size_t)(c0 >> 3) * ((size_t)rows_in_image * 16) + (size_t)r * 16;
+  *reinterpret_cast<uint4*>(img_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(img_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+__device__ __forceinline__ void store_chunk8x3p(unsigned char* img0, size_t img_stride, int rows_in_image, int r,
+                                                int c0, const p2::f2* v) {
+  uint32_t h[4], m[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) split3p(v[i], &h[i], &m[i], &l[i]);
+  const size_t off = (size_t)(c0 >> 3) * ((size_t)rows_in_image * 16) + (size_t)r * 16;
+  *reinterpret_cast<uint4*>(img0 + off) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(img0 + img_stride + off) = make_uint4(m[0], m[1], m[2], m[3]);
+  *reinterpret_cast<uint4*>(img0 + 2 * img_stride + off) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+// 4 consecutive columns given as two pairs
+__device__ __forceinline__ void store_chunk4p(unsigned char* img_hi, unsigned char* img_lo, int rows_in_image, int r,
+                                              int c0, p2::f2 v0, p2::f2 v1) {
+  uint32_t h[2], l[2];
+  split2p(v0, &h[0], &l[0]);
+  split2p(v1, &h[1], &l[1]);
+  const size_t off = (size_t)(c0 >> 3) * ((size_t)rows_in_image * 16) + (size_t)r * 16 + (size_t)(c0 & 7) * 2;
+  *reinterpret_cast<uint2*>(img_hi + off) = make_uint2(h[0], h[1]);
+  *reinterpret_cast<uint2*>(img_lo + off) = make_uint2(l[0], l[1]);
 }
 
 // store 4 consecutive columns [c0, c0+4) of row r (c0 % 4 == 0): half of a 16-byte piece

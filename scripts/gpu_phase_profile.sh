@@ -3,16 +3,19 @@
 # /tmp and prints where thread 0 of each CTA spends its cycles.  Not part of the product build.
 set -euo pipefail
 cd "$(dirname "$0")/.."
+# usage: scripts/gpu_phase_profile.sh build   (here, no GPU needed)  |  scripts/gpu_phase_profile.sh   (on the GPU box)
 SRC=neurallaplace_b200/csrc
-mkdir -p /tmp/nlprof
-FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --extended-lambda -DNL_TC_PROFILE ${NL_EXTRA:-}"
-for f in nl_api nl_elementwise nl_fused_simt nl_fused_tc nl_fused_tc2 nl_tc_selftest nl_dehoog_qd nl_optim; do
-  nvcc $FLAGS -c $SRC/$f.cu -o /tmp/nlprof/$f.o 2>/dev/null &
-done; wait
-nvcc -shared -o /tmp/nlprof/libnl_b200.so /tmp/nlprof/*.o -lcudart
-cp neurallaplace_b200/lib/libnl_b200.so /tmp/nlprof/orig.so
-cp /tmp/nlprof/libnl_b200.so neurallaplace_b200/lib/libnl_b200.so
-trap 'cp /tmp/nlprof/orig.so neurallaplace_b200/lib/libnl_b200.so' EXIT
+OUT=neurallaplace_b200/lib/libnl_b200_prof.so
+if [[ "${1:-}" == "build" ]]; then
+  mkdir -p /tmp/nlprof
+  FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --extended-lambda -DNL_TC_PROFILE ${NL_EXTRA:-}"
+  for f in nl_api nl_elementwise nl_fused_simt nl_fused_tc nl_fused_tc2 nl_tc_selftest nl_dehoog_qd nl_dehoog_fixed nl_optim; do
+    nvcc $FLAGS -c $SRC/$f.cu -o /tmp/nlprof/$f.o 2>/dev/null &
+  done; wait
+  nvcc -shared -o $OUT /tmp/nlprof/*.o -lcudart
+  echo "built $OUT"; exit 0
+fi
+export NL_B200_LIB="$PWD/$OUT"
 NL_B200_TC_STREAMS=1 python - <<'PY'
 import ctypes, torch, sys
 sys.path.insert(0, '.')
