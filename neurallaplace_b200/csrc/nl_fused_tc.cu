@@ -1850,8 +1850,8 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
 //   H : h2 -> h1 of the same tile, streamed in one after the other ([ones] / [1 p] chunk rewritten in place)
 // While a stream waits for a GEMM or an image, the other stream's epilogue has the SM.
 struct Bs2Smem {
-  size_t X[2], Hb[2], W2, W3, small, total;
-  size_t X_img, H_img, W2_img, W3_img;
+  size_t X[2], Hb[2], P[2], W2, W3, small, total;
+  size_t X_img, H_img, P_img, W2_img, W3_img;
   int W1p, b3, coef[2], dp[2], nfloats;
 };
 __host__ __device__ inline Bs2Smem bs2_smem(int NP, int nkc, int K) {
@@ -1860,9 +1860,11 @@ __host__ __device__ inline Bs2Smem bs2_smem(int NP, int nkc, int K) {
   L.H_img = image_bytes(kRows, kH2Cols);
   L.W2_img = image_bytes(kH, kH);
   L.W3_img = image_bytes(NP, kH);
+  L.P_img = image_bytes(kRows, 8);  // [1 p] of the tile: B operand of D1, so that D1 does not hold the H image
   size_t o = 0;
   for (int s = 0; s < 2; ++s) { L.X[s] = o; o += 2 * L.X_img; }
   for (int s = 0; s < 2; ++s) { L.Hb[s] = o; o += 2 * L.H_img; }
+  for (int s = 0; s < 2; ++s) { L.P[s] = o; o += 2 * L.P_img; }
   L.W2 = o; o += 2 * L.W2_img;
   L.W3 = o; o += 2 * L.W3_img;
   L.small = o;
@@ -1920,7 +1922,8 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcAr
       for (int i = 0; i < 8; ++i) v[i] = __ldg(A.W2 + tid * kH + c0 + i);
       store_chunk8(W2_hi, W2_lo, kH, tid, c0, v);
     }
-    for (int j = 0; j < K; ++j) sW1p[tid * 8 + j] = __ldg(A.W1 + (size_t)tid * ldw1 + 2 * n + j);
+    // transposed ([q][c]): two adjacent hidden units load as one float2 (packed dp accumulation)
+    for (int j = 0; j < K; ++j) sW1p[j * kH + tid] = __ldg(A.W1 + (size_t)tid * ldw1 + 2 * n + j);
   }
   for (int idx = tid; idx < NP; idx += kBsThreads) sb3[idx] = __ldg(A.b3pack + idx);
   if (warp == 0) tmem_alloc(&tmem_slot, kTmemCols);
@@ -1959,8 +1962,8 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcAr
     const int iw = warp - 2 * kStreamThreads / 32;
     const int s = iw >> 1;
     const bool is_main = (iw & 1) == 0;
-    const uint32_t aX = smem_u32(smem + L.X[s]), aH = smem_u32(smem + L.Hb[s]);
-    const uint32_t x_lo = (uint32_t)L.X_img, h_lo = (uint32_t)L.H_img;
+    const uint32_t aX = smem_u32(smem + L.X[s]), aH = smem_u32(smem + L.Hb[s]), aP = smem_u32(smem + L.P[s]);
+    const uint32_t x_lo = (uint32_t)L.X_img, h_lo = (uint32_t)L.H_img, p_lo = (uint32_t)L.P_img;
     const uint32_t tSO = tmem + s * tm_stream, tdW2 = tSO + so_cols, tdW3 = tdW2 + 80, tD1 = tdW3 + 80;
     const long long tile_lo = s_lo[s], tile_hi = s_lo[s] + s_n[s];
     if (is_main) {
@@ -2000,7 +2003,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcAr
           load_img(tile_lo, 1, &bar_h2[s]);
           bulk_prefetch_l2(A.stash + (size_t)tile_lo * kStashTile, 2 * kStashImg);
         }
-        uint32_t p_dO = 0, p_z2 = 0, p_z1 = 0, p_sdh2 = 0, p_sdh1 = 0, p_h1 = 0, p_a0 = 0, p_a1 = 0, p_a2 = 0;
+        uint32_t p_dO = 0, p_z2 = 0, p_z1 = 0, p_sdh2 = 0, p_sdh1 = 0, p_h1 = 0, p_a0 = 0;
         int cur_t = -1, slot_tiles = 0;
         int t_run = (int)(tile_lo / A.nbt), b_run = (int)(tile_lo % A.nbt);
         for (long long tile = tile_lo; tile < tile_hi; ++tile) {
@@ -2037,19 +2040,15 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcAr
           tc_fence_after();
           issue_gemm(make_gemm(aX, x_lo, kRows, 1, aH, h_lo, kRows, 1, 64, kH1Cols, kRows), tdW2, !restart);
           umma_commit(&bar_aux[s][1]);
-          // D1 (+)= Z1g^T . [1 p]
+          // Z1g stored: the epilogue has waited for dW2 and read h1 for the last time -> the H image is free for the
+          // next tile's h2 (D1 takes [1 p] from its own small image, it no longer holds H)
           mbar_wait_relaxed(&rdy_z1[s], p_z1);
           p_z1 ^= 1;
-          tc_fence_after();
-          issue_gemm(make_gemm(aX, x_lo, kRows, 1, aH + 8 * (kRows * 16), h_lo, kRows, 1, 64, 8, kRows), tD1,
-                     !first_in_slot);
-          umma_commit(&bar_aux[s][2]);
-          // the H image is free for the next tile's h2 once dW2 and D1 have executed
-          mbar_wait_relaxed(&bar_aux[s][1], p_a1);
-          p_a1 ^= 1;
-          mbar_wait_relaxed(&bar_aux[s][2], p_a2);
-          p_a2 ^= 1;
           if (tile + 1 < tile_hi) load_img(tile + 1, 1, &bar_h2[s]);
+          // D1 (+)= Z1g^T . [1 p]
+          tc_fence_after();
+          issue_gemm(make_gemm(aX, x_lo, kRows, 1, aP, p_lo, kRows, 1, 64, 8, kRows), tD1, !first_in_slot);
+          umma_commit(&bar_aux[s][2]);
         }
       }
     }
@@ -2063,6 +2062,8 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcAr
     unsigned char* X_lo = X_hi + L.X_img;
     unsigned char* H_hi = smem + L.Hb[s];
     unsigned char* H_lo = H_hi + L.H_img;
+    unsigned char* P_hi = smem + L.P[s];
+    unsigned char* P_lo = P_hi + L.P_img;
     float* sCoef = sf + L.coef[s];
     float* sdp = sf + L.dp[s];
     const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
@@ -2207,13 +2208,9 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcAr
       ++slot_tiles;
       // bounded accumulation chains: dW3 / dW2 of the previous tile have executed (waited for in its stages 3 / 4)
       if (tile > tile_lo && (tile - tile_lo) % kFlushTiles == 0) drain();
-      // ---- 1. X and the [1 p] chunk of H are still read by D1 of the previous tile
-      wait_d1();
-      if (A.zstash) {  // ... and X by the bulk store that exported the previous Z1g image
-        if ((warp & 7) == 0 && elect_one()) bulk_wait_read_all();
-        st_sync();
-      }
-      if (wg == 0) {  // chunk 8 of the H image = [1 0 ...] while it holds h2 (-> db3)
+      // ---- 1. chunk 8 of the H image = [1 0 ...] while it holds h2 (-> db3).  Its last reader was dW2 of the
+      // previous tile (waited for in that tile's stage 4); D1 reads [1 p] from the P image.
+      if (wg == 0) {
         const size_t off = (size_t)8 * (kRows * 16) + (size_t)r * 16;
         *reinterpret_cast<uint4*>(H_hi + off) = make_uint4(0x00003F80u, 0, 0, 0);
         *reinterpret_cast<uint4*>(H_lo + off) = make_uint4(0, 0, 0, 0);
@@ -2223,30 +2220,82 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcAr
       mbar_wait(&bar_h2[s], ph_h2);  // landed before L3 could run; makes the bulk-async writes visible to this thread
       ph_h2 ^= 1;
       tc_fence_after();
+      // X is still read by D1 of the previous tile (long done by now: it ran under the h2 load and L3) ...
+      wait_d1();
+      if (A.zstash) {  // ... and by the bulk store that exported the previous Z1g image
+        if ((warp & 7) == 0 && elect_one()) bulk_wait_read_all();
+        st_sync();
+      }
 
       // ---- 2. heads forward + backward -> dO image
-      for (int c0 = wg * cw; c0 < min((wg + 1) * cw, ncols_real); c0 += 4) {
-        float v[4], dv[4];
-        tmem_ld4(lane_addr + tSO + c0, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int c = c0 + 2 * i;
-          const fast::Head h = fast::head_forward(A.P.head, v[2 * i] + sb3[c], v[2 * i + 1] + sb3[c + 1]);
-          float gre, gim;
-          if (DH) {
-            const int k = c >> 1;
-            float2 df = make_float2(0.f, 0.f);
-            if (valid && k < A.n) df = __ldg(A.dfin + (size_t)k * A.f_plane + ((size_t)t_idx * A.B + b));
-            gre = df.x;
-            gim = df.y;
-          } else {
-            gre = g * sCoef[c];
-            gim = -g * sCoef[c + 1];
+      {
+        const int c_end = min((wg + 1) * cw, ncols_real);
+        int c0 = wg * cw;
+        if (A.P.head == NL_HEAD_SPHERE) {
+          // two head pairs per packed evaluation (fast::head_forward2 / head_backward2), eight columns per TMEM load
+          const p2::f2 G = p2::bc(g), Gn = p2::bc(-g);
+          auto two_pairs = [&](const float* v, int c) {
+            const float4 bq = *reinterpret_cast<const float4*>(sb3 + c);
+            const fast::Head2 h = fast::head_forward2<true>(p2::add2(p2::pk(v[0], v[2]), p2::pk(bq.x, bq.z)),
+                                                            p2::add2(p2::pk(v[1], v[3]), p2::pk(bq.y, bq.w)));
+            p2::f2 gre, gim;
+            if (DH) {
+              const int k = c >> 1;
+              float2 d0 = make_float2(0.f, 0.f), d1 = make_float2(0.f, 0.f);
+              const float2* src = A.dfin + (size_t)k * A.f_plane + ((size_t)t_idx * A.B + b);
+              if (valid && k < A.n) d0 = __ldg(src);
+              if (valid && k + 1 < A.n) d1 = __ldg(src + A.f_plane);
+              gre = p2::pk(d0.x, d1.x);
+              gim = p2::pk(d0.y, d1.y);
+            } else {
+              const float4 cq = *reinterpret_cast<const float4*>(sCoef + c);
+              gre = p2::mul2(G, p2::pk(cq.x, cq.z));
+              gim = p2::mul2(Gn, p2::pk(cq.y, cq.w));
+            }
+            p2::f2 goa, gob;
+            fast::head_backward2(h, gre, gim, &goa, &gob);
+            float dv[4];
+            p2::unpk(goa, dv[0], dv[2]);
+            p2::unpk(gob, dv[1], dv[3]);
+            store_chunk4(X_hi, X_lo, kRows, r, c, dv);
+          };
+          for (; c0 + 8 <= c_end; c0 += 8) {
+            float v[8];
+            tmem_ld8(lane_addr + tSO + c0, v);
+            tmem_ld_wait();
+            two_pairs(v, c0);
+            two_pairs(v + 4, c0 + 4);
           }
-          fast::head_backward(A.P.head, h, gre, gim, &dv[2 * i], &dv[2 * i + 1]);
+          for (; c0 < c_end; c0 += 4) {
+            float v[4];
+            tmem_ld4(lane_addr + tSO + c0, v);
+            tmem_ld_wait();
+            two_pairs(v, c0);
+          }
         }
-        store_chunk4(X_hi, X_lo, kRows, r, c0, dv);
+        for (; c0 < c_end; c0 += 4) {  // raw head (use_sphere_projection = False)
+          float v[4], dv[4];
+          tmem_ld4(lane_addr + tSO + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int c = c0 + 2 * i;
+            const fast::Head h = fast::head_forward(A.P.head, v[2 * i] + sb3[c], v[2 * i + 1] + sb3[c + 1]);
+            float gre, gim;
+            if (DH) {
+              const int k = c >> 1;
+              float2 df = make_float2(0.f, 0.f);
+              if (valid && k < A.n) df = __ldg(A.dfin + (size_t)k * A.f_plane + ((size_t)t_idx * A.B + b));
+              gre = df.x;
+              gim = df.y;
+            } else {
+              gre = g * sCoef[c];
+              gim = -g * sCoef[c + 1];
+            }
+            fast::head_backward(A.P.head, h, gre, gim, &dv[2 * i], &dv[2 * i + 1]);
+          }
+          store_chunk4(X_hi, X_lo, kRows, r, c0, dv);
+        }
       }
       fence_async_smem();
       tc_fence_before();
@@ -2254,25 +2303,36 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcAr
       if (stid == 0) mbar_arrive(&rdy_dO[s]);
       pend_aux0 = true;
 
-      // ---- 3. Z2g = dH2 (1 - h2^2) -> X (after dW3, which still reads dO there)
+      // ---- 3. Z2g = dH2 (1 - h2^2) -> X.  dW3 still reads dO there: the first half of the columns is formed in
+      // registers while it runs, stores start once it is done
       mbar_wait(&bar_main[s], ph_main);
       ph_main ^= 1;
       tc_fence_after();
-      wait_dw3();
+      {
+        const p2::f2 one = p2::bc(1.f);
+        auto half = [&](int hf, p2::f2 (&z)[8]) {
+          float v[16];
+          tmem_ld16(lane_addr + tSO + wg * kCols + hf, v);
+          tmem_ld_wait();
 #pragma unroll
-      for (int hf = 0; hf < kCols; hf += 16) {
-        float v[16], z[16];
-        tmem_ld16(lane_addr + tSO + wg * kCols + hf, v);
-        tmem_ld_wait();
+          for (int q = 0; q < 16; q += 8) {
+            float hv[8];
+            load_chunk8(H_hi, H_lo, kRows, r, wg * kCols + hf + q, hv);
 #pragma unroll
-        for (int q = 0; q < 16; q += 8) {
-          float hv[8];
-          load_chunk8(H_hi, H_lo, kRows, r, wg * kCols + hf + q, hv);
+            for (int j = 0; j < 8; j += 2) {
+              const p2::f2 hp = p2::pk(hv[j], hv[j + 1]);
+              z[(q + j) / 2] = p2::mul2(p2::pk(v[q + j], v[q + j + 1]), p2::sub2(one, p2::mul2(hp, hp)));
+            }
+          }
+        };
+        p2::f2 z0[8], z1[8];
+        half(0, z0);
+        wait_dw3();
 #pragma unroll
-          for (int j = 0; j < 8; ++j) z[q + j] = v[q + j] * (1.f - hv[j] * hv[j]);
-        }
+        for (int q = 0; q < 16; q += 8) store_chunk8p(X_hi, X_lo, kRows, r, wg * kCols + q, &z0[q / 2]);
+        half(16, z1);
 #pragma unroll
-        for (int q = 0; q < 16; q += 8) store_chunk8(X_hi, X_lo, kRows, r, wg * kCols + hf + q, &z[q]);
+        for (int q = 0; q < 16; q += 8) store_chunk8p(X_hi, X_lo, kRows, r, wg * kCols + 16 + q, &z1[q / 2]);
       }
       if (wg == 0) {  // chunk 8 of the H image = [1 p] for its life as h1 (B operand of dW2 and D1)
         float q[8];
@@ -2280,6 +2340,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcAr
 #pragma unroll
         for (int j = 0; j < kMaxK; ++j) q[1 + j] = (j < KP) ? pv[j < KP ? j : 0] : 0.f;
         store_chunk8(H_hi, H_lo, kRows, r, kH, q);
+        store_chunk8(P_hi, P_lo, kRows, r, 0, q);  // the same eight columns, for D1 (its previous reader was waited for above)
       }
       fence_async_smem();
       tc_fence_before();
@@ -2287,36 +2348,50 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcAr
       if (stid == 0) mbar_arrive(&rdy_z2[s]);
       pend_aux1 = true;
 
-      // ---- 4. Z1g = dH1 (1 - h1^2) -> X (after dW2, which still reads Z2g there) ; dp
+      // ---- 4. Z1g = dH1 (1 - h1^2) -> X ; dp.  dW2 still reads Z2g there: first half formed in registers meanwhile
       mbar_wait(&bar_main[s], ph_main);
       ph_main ^= 1;
       tc_fence_after();
       mbar_wait(&bar_h1[s], ph_h1);
       ph_h1 ^= 1;
-      wait_dw2();
       float dpv[KP];
+      {
+        const p2::f2 one = p2::bc(1.f);
+        p2::f2 dp2[KP];
 #pragma unroll
-      for (int j = 0; j < KP; ++j) dpv[j] = 0.f;
+        for (int j = 0; j < KP; ++j) dp2[j] = p2::bc(0.f);
+        auto half = [&](int hf, p2::f2 (&z)[8]) {
+          float v[16];
+          tmem_ld16(lane_addr + tSO + wg * kCols + hf, v);
+          tmem_ld_wait();
 #pragma unroll
-      for (int hf = 0; hf < kCols; hf += 16) {
-        float v[16], z[16];
-        tmem_ld16(lane_addr + tSO + wg * kCols + hf, v);
-        tmem_ld_wait();
+          for (int q = 0; q < 16; q += 8) {
+            float hv[8];
+            load_chunk8(H_hi, H_lo, kRows, r, wg * kCols + hf + q, hv);
 #pragma unroll
-        for (int q = 0; q < 16; q += 8) {
-          float hv[8];
-          load_chunk8(H_hi, H_lo, kRows, r, wg * kCols + hf + q, hv);
+            for (int j = 0; j < 8; j += 2) {
+              const p2::f2 hp = p2::pk(hv[j], hv[j + 1]);
+              const p2::f2 zz = p2::mul2(p2::pk(v[q + j], v[q + j + 1]), p2::sub2(one, p2::mul2(hp, hp)));
+              z[(q + j) / 2] = zz;
+              const int c = wg * kCols + hf + q + j;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float zz = v[q + j] * (1.f - hv[j] * hv[j]);
-            z[q + j] = zz;
-            const int c = wg * kCols + hf + q + j;
-#pragma unroll
-            for (int qq = 0; qq < KP; ++qq) dpv[qq] = fmaf(zz, sW1p[c * 8 + qq], dpv[qq]);
+              for (int qq = 0; qq < KP; ++qq) {
+                const float2 w = *reinterpret_cast<const float2*>(sW1p + qq * kH + c);
+                dp2[qq] = p2::fma2(zz, p2::pk(w.x, w.y), dp2[qq]);
+              }
+            }
           }
-        }
+        };
+        p2::f2 z0[8], z1[8];
+        half(0, z0);
+        wait_dw2();
 #pragma unroll
-        for (int q = 0; q < 16; q += 8) store_chunk8(X_hi, X_lo, kRows, r, wg * kCols + hf + q, &z[q]);
+        for (int q = 0; q < 16; q += 8) store_chunk8p(X_hi, X_lo, kRows, r, wg * kCols + q, &z0[q / 2]);
+        half(16, z1);
+#pragma unroll
+        for (int q = 0; q < 16; q += 8) store_chunk8p(X_hi, X_lo, kRows, r, wg * kCols + 16 + q, &z1[q / 2]);
+#pragma unroll
+        for (int j = 0; j < KP; ++j) dpv[j] = p2::lo(dp2[j]) + p2::hi(dp2[j]);
       }
 #pragma unroll
       for (int q = 0; q < KP; ++q)
