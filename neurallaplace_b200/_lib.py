@@ -174,10 +174,25 @@ def stream_ptr(device=None):
   return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+class _Same:
+  """No-op context: the tensors' device is already the current one (the common case; saves two driver calls)."""
+
+  def __enter__(self):
+    return self
+
+  def __exit__(self, *a):
+    return False
+
+
+_SAME = _Same()
+
+
 def on(device):
   """Context that makes ``device`` the current CUDA device for a C-ABI call: the library launches on the
   current device (kernel attributes, SM count, launches), so every call site enters this with the device of
   its tensors and passes ``stream_ptr(device)``."""
+  if device.index is None or device.index == torch.cuda.current_device():
+    return _SAME
   return torch.cuda.device(device)
 
 
