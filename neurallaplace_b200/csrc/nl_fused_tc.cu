@@ -1293,7 +1293,8 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
       for (int i = 0; i < 8; ++i) v[i] = __ldg(A.W2 + tid * kH + c0 + i);
       store_chunk8(W2_hi, W2_lo, kH, tid, c0, v);
     }
-    for (int j = 0; j < K; ++j) sW1p[tid * 8 + j] = __ldg(A.W1 + (size_t)tid * ldw1 + 2 * n + j);
+    // transposed ([q][c]): two adjacent hidden units load as one float2 (packed dp accumulation)
+    for (int j = 0; j < K; ++j) sW1p[j * kH + tid] = __ldg(A.W1 + (size_t)tid * ldw1 + 2 * n + j);
   }
   for (int idx = tid; idx < nch * NP; idx += kBsThreads) sb3[idx] = __ldg(A.b3pack + idx);
   // constant "ones" column of the h2 image (chunk 8; the streamed images only cover chunks 0-7) -> db3
@@ -1681,7 +1682,51 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
         const float g = gr * rs;
         const float* cf = sCoef + kci * NP;
         const float* bb3 = sb3 + ch * NP;
-        for (int c0 = wg * cw; c0 < min((wg + 1) * cw, ncols_real); c0 += 4) {
+        const int c_end = min((wg + 1) * cw, ncols_real);
+        int c0 = wg * cw;
+        if (P.head == NL_HEAD_SPHERE) {
+          // two head pairs per packed evaluation (fast::head_forward2 / head_backward2), eight columns per TMEM load
+          const p2::f2 G = p2::bc(g), Gn = p2::bc(-g);
+          auto two_pairs = [&](const float* v, int c) {
+            const float4 bq = *reinterpret_cast<const float4*>(bb3 + c);
+            const fast::Head2 h = fast::head_forward2<true>(p2::add2(p2::pk(v[0], v[2]), p2::pk(bq.x, bq.z)),
+                                                            p2::add2(p2::pk(v[1], v[3]), p2::pk(bq.y, bq.w)));
+            p2::f2 gre, gim;
+            if (DH) {
+              const int kk = c >> 1, k = kci * A.kc + kk;
+              float2 d0 = make_float2(0.f, 0.f), d1 = make_float2(0.f, 0.f);
+              const float2* src = A.dfin + (size_t)(d * A.n + k) * A.f_plane + ((size_t)t_idx * A.B + b);
+              if (valid && kk < A.kc && k < A.n) d0 = __ldg(src);
+              if (valid && kk + 1 < A.kc && k + 1 < A.n) d1 = __ldg(src + A.f_plane);
+              gre = p2::pk(d0.x, d1.x);
+              gim = p2::pk(d0.y, d1.y);
+            } else {
+              const float4 cq = *reinterpret_cast<const float4*>(cf + c);
+              gre = p2::mul2(G, p2::pk(cq.x, cq.z));
+              gim = p2::mul2(Gn, p2::pk(cq.y, cq.w));
+            }
+            p2::f2 goa, gob;
+            fast::head_backward2(h, gre, gim, &goa, &gob);
+            float dv[4];
+            p2::unpk(goa, dv[0], dv[2]);
+            p2::unpk(gob, dv[1], dv[3]);
+            store_chunk4(dO_hi, dO_lo, kRows, r, c, dv);
+          };
+          for (; c0 + 8 <= c_end; c0 += 8) {
+            float v[8];
+            tmem_ld8(lane_addr + TM.O + c0, v);
+            tmem_ld_wait();
+            two_pairs(v, c0);
+            two_pairs(v + 4, c0 + 4);
+          }
+          for (; c0 < c_end; c0 += 4) {
+            float v[4];
+            tmem_ld4(lane_addr + TM.O + c0, v);
+            tmem_ld_wait();
+            two_pairs(v, c0);
+          }
+        }
+        for (; c0 < c_end; c0 += 4) {  // raw head (use_sphere_projection = False)
           float v[4], dv[4];
           tmem_ld4(lane_addr + TM.O + c0, v);
           tmem_ld_wait();
@@ -1721,7 +1766,8 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
       tc_fence_after();
       NL_PROF(7);
       if (tid == 0) NL_TRACE(4);
-      float z[kColsPerWg];
+      p2::f2 z[kColsPerWg / 2];
+      const p2::f2 one2 = p2::bc(1.f);
 #pragma unroll
       for (int i = 0; i < kColsPerWg; i += 16) {
         float v[16];
@@ -1732,7 +1778,10 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
           float hv[8];
           load_chunk8(H2_hi, H2_lo, kRows, r, wg * kColsPerWg + i + q, hv);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) z[i + q + j] = v[q + j] * (1.f - hv[j] * hv[j]);
+          for (int j = 0; j < 8; j += 2) {
+            const p2::f2 hp = p2::pk(hv[j], hv[j + 1]);
+            z[(i + q + j) / 2] = p2::mul2(p2::pk(v[q + j], v[q + j + 1]), p2::sub2(one2, p2::mul2(hp, hp)));
+          }
         }
       }
       if (!zsep) wait_dw3();  // dW3 of the last chunk reads the dO image
@@ -1747,7 +1796,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
         store_chunk8(H1_hi, H1_lo, kRows, r, kH, q);
       }
 #pragma unroll
-      for (int i = 0; i < kColsPerWg; i += 8) store_chunk8(Z_hi, Z_lo, kRows, r, wg * kColsPerWg + i, &z[i]);
+      for (int i = 0; i < kColsPerWg; i += 8) store_chunk8p(Z_hi, Z_lo, kRows, r, wg * kColsPerWg + i, &z[i / 2]);
       fence_async_smem();
       tc_fence_before();
       ep_sync();
@@ -1764,26 +1813,35 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
       mbar_wait(&bar_h1, ph_h1);
       ph_h1 ^= 1;
       float dpv[KP];
+      {
+        p2::f2 dp2[KP];
 #pragma unroll
-      for (int j = 0; j < KP; ++j) dpv[j] = 0.f;
+        for (int j = 0; j < KP; ++j) dp2[j] = p2::bc(0.f);
 #pragma unroll
-      for (int i = 0; i < kColsPerWg; i += 16) {
-        float v[16];
-        tmem_ld16(lane_addr + TM.S + wg * kColsPerWg + i, v);
-        tmem_ld_wait();
+        for (int i = 0; i < kColsPerWg; i += 16) {
+          float v[16];
+          tmem_ld16(lane_addr + TM.S + wg * kColsPerWg + i, v);
+          tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 16; q += 8) {
-          float hv[8];
-          load_chunk8(H1_hi, H1_lo, kRows, r, wg * kColsPerWg + i + q, hv);
+          for (int q = 0; q < 16; q += 8) {
+            float hv[8];
+            load_chunk8(H1_hi, H1_lo, kRows, r, wg * kColsPerWg + i + q, hv);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float zz = v[q + j] * (1.f - hv[j] * hv[j]);
-            z[i + q + j] = zz;
-            const int c = wg * kColsPerWg + i + q + j;
+            for (int j = 0; j < 8; j += 2) {
+              const p2::f2 hp = p2::pk(hv[j], hv[j + 1]);
+              const p2::f2 zz = p2::mul2(p2::pk(v[q + j], v[q + j + 1]), p2::sub2(one2, p2::mul2(hp, hp)));
+              z[(i + q + j) / 2] = zz;
+              const int c = wg * kColsPerWg + i + q + j;
 #pragma unroll
-            for (int qq = 0; qq < KP; ++qq) dpv[qq] = fmaf(zz, sW1p[c * 8 + qq], dpv[qq]);
+              for (int qq = 0; qq < KP; ++qq) {
+                const float2 w = *reinterpret_cast<const float2*>(sW1p + qq * kH + c);
+                dp2[qq] = p2::fma2(zz, p2::pk(w.x, w.y), dp2[qq]);
+              }
+            }
           }
         }
+#pragma unroll
+        for (int j = 0; j < KP; ++j) dpv[j] = p2::lo(dp2[j]) + p2::hi(dp2[j]);
       }
       // dp of this tile: the warpgroups' partial sums meet in shared memory (ordered by the barrier below) and
       // warpgroup 0 writes their sum to the per-tile scratch -- plain stores, summed over t by dp_reduce_kernel.
@@ -1793,7 +1851,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
         if (q < K) sdp[(wg * kRows + r) * K + q] = dpv[q];
       wait_dw3();  // dW3 of the last chunk reads the dO image
 #pragma unroll
-      for (int i = 0; i < kColsPerWg; i += 8) store_chunk8(Z1_hi, Z1_lo, kRows, r, wg * kColsPerWg + i, &z[i]);
+      for (int i = 0; i < kColsPerWg; i += 8) store_chunk8p(Z1_hi, Z1_lo, kRows, r, wg * kColsPerWg + i, &z[i / 2]);
       fence_async_smem();
       tc_fence_before();
       ep_sync();

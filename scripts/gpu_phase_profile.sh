@@ -40,10 +40,11 @@ for k, nm in ((0, "forward"), (12, "backward")):
         if v[i]: print("   %-28s %5.1f%%" % (names[i], 100.0*v[i]/tot))
 tr = (ctypes.c_longlong * 64)()
 if hasattr(lib, "nl_debug_tc_trace") and lib.nl_debug_tc_trace(tr) == 0:
-    tnames = {0: "E tile start (after slot)", 1: "E after wait_d1", 2: "E after L3+h2 wait", 3: "E dO stored+arrive", 4: "E dH2 done",
-             5: "E Z2g stored+arrive", 6: "E dH1 done", 7: "E Z1g stored+arrive", 10: "I16 L3 issue", 11: "I16 L3 issued",
-             12: "I16 dH2 issue", 13: "I16 dH1 issue", 14: "I17 dW3 issue", 15: "I17 D1 issue", 16: "I17 D1 issued",
-             17: "I17 dW2(prev) issue", 18: "I17 dW2(prev) issued"}
+    tnames = {0: "E tile start", 1: "E L3 done + h2 landed", 2: "E D1(prev) done, heads start", 3: "E dO stored+arrive",
+              4: "E dH2 done", 5: "E Z2g stored+arrive", 6: "E dH1 done + h1 landed", 7: "E Z1g stored+arrive",
+              8: "Iaux h1 load issued", 9: "Iaux next h2 load issued", 10: "Imain L3 issue", 11: "Imain L3 issued",
+              12: "Imain dH2 issue", 19: "Imain dH2 issued", 13: "Imain dH1 issue", 14: "Iaux dW3 issue",
+              15: "Iaux D1 issue", 16: "Iaux D1 issued", 17: "Iaux dW2 issue", 18: "Iaux dW2 issued"}
     ev = []
     for k in range(3):
         for sl, nm in tnames.items():
@@ -52,6 +53,6 @@ if hasattr(lib, "nl_debug_tc_trace") and lib.nl_debug_tc_trace(tr) == 0:
     ev.sort()
     if ev:
         t0 = ev[0][0]
-        print("event trace of CTA 0 (saved backward), clocks relative to the first event")
+        print("event trace of CTA 0, stream 0 (saved backward, two tiles in flight), clocks relative to the first event")
         for v, nm in ev: print("   %8d  %s" % (v - t0, nm))
 PY
