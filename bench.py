@@ -303,7 +303,9 @@ def run_b200(a):
   torch.cuda.set_device(local)
   dev = torch.device("cuda", local)
   if world > 1:
-    dist.init_process_group("nccl", device_id=dev)
+    import datetime
+    # a mismatched collective must fail in a minute, not after NCCL's default 10 (GPU-minutes are budgeted)
+    dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=90))
   _lib.require_cuda()
   if a.alg == "cme":  # the reference's CME table is not redistributable: synthetic table of the same schema
     from neurallaplace_b200 import _iltcme
@@ -392,6 +394,10 @@ def run_b200(a):
   sustained = None
   if a.sustain_s > 0:
     n_sus = max(a.steps, int(a.sustain_s * 1e3 / max(ms_total / a.steps, 1e-3)) + 1)
+    if world > 1:  # every rank must run the SAME number of steps (each ends with a collective)
+      n_t = torch.tensor([n_sus], dtype=torch.int64, device=dev)
+      dist.broadcast(n_t, src=0)
+      n_sus = int(n_t.item())
     sampler.samples = []
     barrier()
     sampler.active = True

@@ -2,7 +2,7 @@
 # sweep of BASELINE.json configs[4] (terms x d_obs x family) -> gpurun_out/sweep.jsonl
 set -uo pipefail
 mkdir -p gpurun_out; : > gpurun_out/sweep.jsonl
-run() { timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline "$@" >> gpurun_out/sweep.jsonl 2>> gpurun_out/sweep.err || echo "{\"failed\": \"$*\"}" >> gpurun_out/sweep.jsonl; }
+run() { timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-peaks --sustain-s 0 "$@" >> gpurun_out/sweep.jsonl 2>> gpurun_out/sweep.err || echo "{\"failed\": \"$*\"}" >> gpurun_out/sweep.jsonl; }
 for terms in 33 65 129; do for d in 1 2 4 16; do run --alg fourier --terms $terms --dobs $d; done; done
 for alg in cme euler fixed_tablot stehfest dehoog; do run --alg $alg --terms 33 --dobs 1; done
 run --alg dehoog --terms 33 --dobs 1 --kernel simt
