@@ -52,3 +52,39 @@ def test_graphed_step_matches_the_eager_path(alg, terms, B, T, D, dtype):
     assert hp.rel(flat, eager_flat) <= gt
   step.assign_grads()
   assert all(q.grad.data_ptr() == v.data_ptr() for q, v in zip(hp.module_params(f), step.grads))
+
+
+def test_tensors_on_a_non_current_device():
+  """every C-ABI call runs with the tensors' device current and on that device's stream -- a call with
+  cuda:1 tensors while cuda:0 is the current device gives the values of the same call on cuda:0 (fused path,
+  split path, class API, fused optimiser step).  Needs two GPUs."""
+  if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+    pytest.skip("needs two CUDA devices")
+  from neurallaplace_b200 import inverse_laplace as il
+  from neurallaplace_b200 import laplace_reconstruct
+  from neurallaplace_b200.optim import FlatClipAdam
+  from oracle import nl_oracle as orc
+  torch.cuda.set_device(0)
+  d0, d1 = torch.device("cuda", 0), torch.device("cuda", 1)
+  g = torch.Generator().manual_seed(1)
+  weights = orc.make_canonical_weights(33, 1, 2, seed=5)
+  p = torch.randn(160, 2, generator=g)
+  t = torch.linspace(0.2, 9.0, 40)
+  gout = torch.randn(160, 40, 1, generator=g)
+  res = []
+  for dev in (d0, d1):
+    f = hp.make_module([w.to(dev) for w in weights], 33, 1, 2, True, dev)
+    pd = p.to(dev).requires_grad_(True)
+    x = laplace_reconstruct(f, pd, t.to(dev), recon_dim=1)
+    x.backward(gout.to(dev))
+    assert x.device == dev and pd.grad.device == dev
+    opt = FlatClipAdam(list(f.parameters()), lr=1e-2, max_norm=1.0)
+    opt.step()
+    res.append((x.detach().cpu(), pd.grad.cpu(), [q.detach().cpu().clone() for q in f.parameters()]))
+    s, T = il.Fourier(33)(lambda so: so / (so**2 + 1), t.to(dev)), None
+    res[-1] += (s.cpu(),)
+  assert torch.cuda.current_device() == 0
+  (x0, g0, w0, y0), (x1, g1, w1, y1) = res
+  assert torch.equal(x0, x1) and hp.rel(g1, g0) <= 1e-5 and hp.rel(y1, y0) <= 1e-6
+  for a, b in zip(w1, w0):
+    assert hp.rel(a, b) <= 1e-5
