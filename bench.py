@@ -302,6 +302,10 @@ def run_b200(a):
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
   torch.cuda.set_device(local)
   dev = torch.device("cuda", local)
+  # host staging buffers on the GPU's NUMA node (matters for the end-to-end leg at N > 1)
+  # (opt-in: measured on 8 B200, 16 host cores: binding made the end-to-end step slower, 2.73 vs 2.52 ms -- the
+  # ranks are short of host cores, not of memory bandwidth)
+  numa_bound = parallel.bind_host_to_gpu(local) if os.environ.get("NL_BENCH_NUMA", "0") == "1" else False
   if world > 1:
     import datetime
     # a mismatched collective must fail in a minute, not after NCCL's default 10 (GPU-minutes are budgeted)
@@ -441,7 +445,11 @@ def run_b200(a):
 
   # ---- end to end: host (pinned) buffers in, host buffers out, copies inside the timed region, through the
   # package's host-staged step (parallel.HostStagedStep: uploads / downloads on copy streams)
-  staged = parallel.HostStagedStep(f, a.dobs, a.alg, a.terms, reducer=reducer, device=dev)
+  if graphed is not None:
+    from neurallaplace_b200.engine import GraphedHostStep
+    staged = GraphedHostStep(graphed)
+  else:
+    staged = parallel.HostStagedStep(f, a.dobs, a.alg, a.terms, reducer=reducer, device=dev)
 
   def e2e_step():
     return staged(p_pin, t_pin, g_pin, x_pin, grads_pin)
@@ -537,7 +545,7 @@ def run_b200(a):
                    "kernel_family": {1: "simt (CUDA-core FFMA/DFMA)", 2: "tcgen05"}.get(impl_f, "?"),
                    "host_path": ("engine.GraphedReconstruct (CUDA-graph replay of the two C-ABI calls)"
                                  if graphed is not None else "laplace_reconstruct + autograd"),
-                   "fwd_ms": fwd_ms, "bwd_ms": bwd_ms},
+                   "host_numa_bound": bool(numa_bound), "fwd_ms": fwd_ms, "bwd_ms": bwd_ms},
         "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms},
         "gpu_launches": launches,

@@ -13,6 +13,22 @@ import torch
 import torch.distributed as dist
 
 
+def bind_host_to_gpu(device_index):
+  """Pin the calling thread to the CPU cores next to GPU ``device_index`` (NVML's ideal-CPU affinity), so that the
+  pinned staging buffers it allocates afterwards are first-touched on that GPU's NUMA node.  With one process per
+  GPU and host-resident minibatches, eight ranks otherwise stage 2 x 16.8 MB per 2 ms step through whichever
+  node the processes happened to start on (measured on 8 B200: end-to-end step 2.60 ms against 2.09 ms on one
+  GPU).  Returns True when the affinity was applied; never raises (NVML may be absent)."""
+  try:
+    import pynvml
+    pynvml.nvmlInit()
+    h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+    pynvml.nvmlDeviceSetCpuAffinity(h)
+    return True
+  except Exception:  # pylint: disable=broad-except
+    return False
+
+
 def shard_range(n_rows, rank=None, world_size=None):
   """Contiguous [lo, hi) slice of the batch owned by ``rank`` (balanced to within one row)."""
   if world_size is None:

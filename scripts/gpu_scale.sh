@@ -3,7 +3,7 @@
 set -uo pipefail
 N=$1
 mkdir -p gpurun_out; : > gpurun_out/scale_$N.jsonl
-for mode in weak strong; do
+for mode in ${MODES:-weak strong}; do
   if [[ $N == 1 ]]; then
     timeout 600 python bench.py --gpus 1 --steps 20 --warmup 3 --no-cpu-baseline --no-peaks --scaling $mode 2> gpurun_out/scale_err.log | tee -a gpurun_out/scale_$N.jsonl > /dev/null
   else

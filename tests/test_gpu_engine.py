@@ -88,3 +88,35 @@ def test_tensors_on_a_non_current_device():
   assert torch.equal(x0, x1) and hp.rel(g1, g0) <= 1e-5 and hp.rel(y1, y0) <= 1e-6
   for a, b in zip(w1, w0):
     assert hp.rel(a, b) <= 1e-5
+
+
+def test_graphed_host_step_matches_host_staged_step():
+  """engine.GraphedHostStep (pinned host buffers in / out around the graph replays) against
+  parallel.HostStagedStep (the eager path): same x, same flat gradient, over several steps."""
+  if not torch.cuda.is_available():
+    pytest.skip("no CUDA device")
+  dev = torch.device("cuda", 0)
+  from neurallaplace_b200 import parallel
+  from neurallaplace_b200.engine import GraphedHostStep, GraphedReconstruct
+  from oracle import nl_oracle as orc
+  B, T = 256, 64
+  weights = orc.make_canonical_weights(33, 1, 2, seed=9)
+  f = hp.make_module([w.to(dev) for w in weights], 33, 1, 2, True, dev)
+  n_par = sum(q.numel() for q in f.parameters())
+  g = torch.Generator().manual_seed(4)
+  step_g = GraphedHostStep(GraphedReconstruct(f, B, T, recon_dim=1))
+  step_e = parallel.HostStagedStep(f, 1, device=dev)
+  for _ in range(3):
+    p = torch.randn(B, 2, generator=g).pin_memory()
+    t = (torch.rand(T, generator=g) * 10 + 0.1).pin_memory()
+    gx = torch.randn(B, T, 1, generator=g).pin_memory()
+    xo_g, xo_e = torch.empty(B, T, 1).pin_memory(), torch.empty(B, T, 1).pin_memory()
+    go_g, go_e = torch.empty(n_par).pin_memory(), torch.empty(n_par).pin_memory()
+    dp = step_g(p, t, gx, xo_g, go_g)
+    torch.cuda.synchronize()
+    dp = dp.clone()
+    pe = step_e(p, t, gx, xo_e, go_e)
+    torch.cuda.synchronize()
+    assert hp.rel(xo_g, xo_e) <= 1e-6
+    assert hp.rel(go_g, go_e) <= 1e-5
+    assert hp.rel(dp, pe.grad) <= 1e-5
