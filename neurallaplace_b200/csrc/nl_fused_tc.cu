@@ -115,6 +115,7 @@ struct TcArgs {
   unsigned char* zstash;
   int ctas;              // forward: CTAs per SM the launch is sized for (2, or 3 with the aliased h2 image)
   int h2sep;             // forward + stash: h2 has its own image (else it aliases h1 and two more barriers order the bulk stores)
+  int baton;             // saved backward, two tiles in flight: the streams take turns in the head stage
   // De Hoog (DH instantiations): the forward writes F = head(layer 3) instead of reducing it, the saved backward
   // reads dL/dF instead of forming it from grad_x and the reduction coefficients; both [d][k][t][b] float2
   // (the quotient-difference recurrence runs in between, nl_dehoog_qd.cu)
@@ -1687,7 +1688,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
         if (P.head == NL_HEAD_SPHERE) {
           // two head pairs per packed evaluation (fast::head_forward2 / head_backward2), eight columns per TMEM load
           const p2::f2 G = p2::bc(g), Gn = p2::bc(-g);
-          auto two_pairs = [&](const float* v, int c) {
+          auto two_pairs = [&](const float* v, int c, float* dv) {
             const float4 bq = *reinterpret_cast<const float4*>(bb3 + c);
             const fast::Head2 h = fast::head_forward2<true>(p2::add2(p2::pk(v[0], v[2]), p2::pk(bq.x, bq.z)),
                                                             p2::add2(p2::pk(v[1], v[3]), p2::pk(bq.y, bq.w)));
@@ -1707,23 +1708,31 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
             }
             p2::f2 goa, gob;
             fast::head_backward2(h, gre, gim, &goa, &gob);
-            float dv[4];
             p2::unpk(goa, dv[0], dv[2]);
             p2::unpk(gob, dv[1], dv[3]);
-            store_chunk4(dO_hi, dO_lo, kRows, r, c, dv);
           };
-          for (; c0 + 8 <= c_end; c0 += 8) {
-            float v[8];
-            tmem_ld8(lane_addr + TM.O + c0, v);
-            tmem_ld_wait();
-            two_pairs(v, c0);
-            two_pairs(v + 4, c0 + 4);
-          }
-          for (; c0 < c_end; c0 += 4) {
-            float v[4];
+          if ((c0 & 4) && c0 < c_end) {  // this warpgroup's range starts in the middle of a 16-byte piece
+            float v[4], dv[4];
             tmem_ld4(lane_addr + TM.O + c0, v);
             tmem_ld_wait();
-            two_pairs(v, c0);
+            two_pairs(v, c0, dv);
+            store_chunk4(dO_hi, dO_lo, kRows, r, c0, dv);
+            c0 += 4;
+          }
+          for (; c0 + 8 <= c_end; c0 += 8) {  // whole pieces: one conflict-free 16-byte store per image
+            float v[8], dv[8];
+            tmem_ld8(lane_addr + TM.O + c0, v);
+            tmem_ld_wait();
+            two_pairs(v, c0, dv);
+            two_pairs(v + 4, c0 + 4, dv + 4);
+            store_chunk8(dO_hi, dO_lo, kRows, r, c0, dv);
+          }
+          for (; c0 < c_end; c0 += 4) {
+            float v[4], dv[4];
+            tmem_ld4(lane_addr + TM.O + c0, v);
+            tmem_ld_wait();
+            two_pairs(v, c0, dv);
+            store_chunk4(dO_hi, dO_lo, kRows, r, c0, dv);
           }
         }
         for (; c0 < c_end; c0 += 4) {  // raw head (use_sphere_projection = False)
@@ -1945,6 +1954,10 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcAr
   unsigned char* smem = smem_bs2;
   __shared__ __align__(8) uint64_t bar_l3[2], bar_main[2], bar_aux[2][3], bar_h1[2], bar_h2[2];
   __shared__ __align__(8) uint64_t rdy_dO[2], rdy_z2[2], rdy_z1[2], seq_dh2[2], seq_dh1[2];
+  // The two streams pass a baton around the head stage (the longest CUDA-core stage): left alone they fall into
+  // LOCKSTEP -- both in the head stage, then both waiting for their GEMMs (timeline in profiles/) -- and the second
+  // tile in flight overlaps nothing.  With the baton one stream's GEMM round trips run under the other's heads.
+  __shared__ __align__(8) uint64_t baton[2];
   __shared__ uint32_t tmem_slot;
 
   const int n = A.n, K = A.K, NP = A.NP;
@@ -1997,6 +2010,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcAr
       mbar_init(&rdy_z1[s], 1);
       mbar_init(&seq_dh2[s], 1);
       mbar_init(&seq_dh1[s], 1);
+      mbar_init(&baton[s], 1);
     }
     fence_mbar_init();
   }
@@ -2127,7 +2141,8 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcAr
     const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t tSO = s * tm_stream, tdW2 = tSO + so_cols, tdW3 = tdW2 + 80, tD1 = tdW3 + 80;
     auto st_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + s), "n"(kStreamThreads) : "memory"); };
-    uint32_t ph_main = 0, ph_l3 = 0, ph_h1 = 0, ph_h2 = 0;
+    uint32_t ph_main = 0, ph_l3 = 0, ph_h1 = 0, ph_h2 = 0, ph_baton = 0;
+    const bool use_baton = A.baton != 0;
     uint32_t ph_aux0 = 0, ph_aux1 = 0, ph_aux2 = 0;
     bool pend_aux0 = false, pend_aux1 = false, pend_aux2 = false;
     auto wait_dw3 = [&]() {
@@ -2246,6 +2261,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcAr
       }
       const bool valid = b < A.B;
       float pv[KP];
+      if (stid == 0) NL_TRACE(s * 10 + 0);
 #pragma unroll
       for (int j = 0; j < KP; ++j) pv[j] = pv_n[j];
       const float g = g_n;
@@ -2278,6 +2294,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcAr
       mbar_wait(&bar_h2[s], ph_h2);  // landed before L3 could run; makes the bulk-async writes visible to this thread
       ph_h2 ^= 1;
       tc_fence_after();
+      if (stid == 0) NL_TRACE(s * 10 + 1);
       // X is still read by D1 of the previous tile (long done by now: it ran under the h2 load and L3) ...
       wait_d1();
       if (A.zstash) {  // ... and by the bulk store that exported the previous Z1g image
@@ -2285,14 +2302,18 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcAr
         st_sync();
       }
 
-      // ---- 2. heads forward + backward -> dO image
+      // ---- 2. heads forward + backward -> dO image (one stream at a time: baton)
+      if (use_baton && !(s == 0 && tile == tile_lo)) {
+        mbar_wait(&baton[s], ph_baton);
+        ph_baton ^= 1;
+      }
       {
         const int c_end = min((wg + 1) * cw, ncols_real);
         int c0 = wg * cw;
         if (A.P.head == NL_HEAD_SPHERE) {
           // two head pairs per packed evaluation (fast::head_forward2 / head_backward2), eight columns per TMEM load
           const p2::f2 G = p2::bc(g), Gn = p2::bc(-g);
-          auto two_pairs = [&](const float* v, int c) {
+          auto two_pairs = [&](const float* v, int c, float* dv) {
             const float4 bq = *reinterpret_cast<const float4*>(sb3 + c);
             const fast::Head2 h = fast::head_forward2<true>(p2::add2(p2::pk(v[0], v[2]), p2::pk(bq.x, bq.z)),
                                                             p2::add2(p2::pk(v[1], v[3]), p2::pk(bq.y, bq.w)));
@@ -2312,23 +2333,31 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcAr
             }
             p2::f2 goa, gob;
             fast::head_backward2(h, gre, gim, &goa, &gob);
-            float dv[4];
             p2::unpk(goa, dv[0], dv[2]);
             p2::unpk(gob, dv[1], dv[3]);
-            store_chunk4(X_hi, X_lo, kRows, r, c, dv);
           };
-          for (; c0 + 8 <= c_end; c0 += 8) {
-            float v[8];
-            tmem_ld8(lane_addr + tSO + c0, v);
-            tmem_ld_wait();
-            two_pairs(v, c0);
-            two_pairs(v + 4, c0 + 4);
-          }
-          for (; c0 < c_end; c0 += 4) {
-            float v[4];
+          if ((c0 & 4) && c0 < c_end) {  // this warpgroup's range starts in the middle of a 16-byte piece
+            float v[4], dv[4];
             tmem_ld4(lane_addr + tSO + c0, v);
             tmem_ld_wait();
-            two_pairs(v, c0);
+            two_pairs(v, c0, dv);
+            store_chunk4(X_hi, X_lo, kRows, r, c0, dv);
+            c0 += 4;
+          }
+          for (; c0 + 8 <= c_end; c0 += 8) {  // whole pieces: one conflict-free 16-byte store per image
+            float v[8], dv[8];
+            tmem_ld8(lane_addr + tSO + c0, v);
+            tmem_ld_wait();
+            two_pairs(v, c0, dv);
+            two_pairs(v + 4, c0 + 4, dv + 4);
+            store_chunk8(X_hi, X_lo, kRows, r, c0, dv);
+          }
+          for (; c0 < c_end; c0 += 4) {
+            float v[4], dv[4];
+            tmem_ld4(lane_addr + tSO + c0, v);
+            tmem_ld_wait();
+            two_pairs(v, c0, dv);
+            store_chunk4(X_hi, X_lo, kRows, r, c0, dv);
           }
         }
         for (; c0 < c_end; c0 += 4) {  // raw head (use_sphere_projection = False)
@@ -2358,7 +2387,11 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcAr
       fence_async_smem();
       tc_fence_before();
       st_sync();
-      if (stid == 0) mbar_arrive(&rdy_dO[s]);
+      if (stid == 0) {
+        mbar_arrive(&rdy_dO[s]);
+        if (use_baton) mbar_arrive(&baton[1 - s]);
+      }
+      if (stid == 0) NL_TRACE(s * 10 + 2);
       pend_aux0 = true;
 
       // ---- 3. Z2g = dH2 (1 - h2^2) -> X.  dW3 still reads dO there: the first half of the columns is formed in
@@ -2366,6 +2399,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcAr
       mbar_wait(&bar_main[s], ph_main);
       ph_main ^= 1;
       tc_fence_after();
+      if (stid == 0) NL_TRACE(s * 10 + 3);
       {
         const p2::f2 one = p2::bc(1.f);
         auto half = [&](int hf, p2::f2 (&z)[8]) {
@@ -2386,6 +2420,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcAr
         p2::f2 z0[8], z1[8];
         half(0, z0);
         wait_dw3();
+        if (stid == 0) NL_TRACE(s * 10 + 4);
 #pragma unroll
         for (int q = 0; q < 16; q += 8) store_chunk8p(X_hi, X_lo, kRows, r, wg * kCols + q, &z0[q / 2]);
         half(16, z1);
@@ -2404,6 +2439,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcAr
       tc_fence_before();
       st_sync();
       if (stid == 0) mbar_arrive(&rdy_z2[s]);
+      if (stid == 0) NL_TRACE(s * 10 + 5);
       pend_aux1 = true;
 
       // ---- 4. Z1g = dH1 (1 - h1^2) -> X ; dp.  dW2 still reads Z2g there: first half formed in registers meanwhile
@@ -2412,6 +2448,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcAr
       tc_fence_after();
       mbar_wait(&bar_h1[s], ph_h1);
       ph_h1 ^= 1;
+      if (stid == 0) NL_TRACE(s * 10 + 6);
       float dpv[KP];
       {
         const p2::f2 one = p2::bc(1.f);
@@ -2443,6 +2480,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcAr
         p2::f2 z0[8], z1[8];
         half(0, z0);
         wait_dw2();
+        if (stid == 0) NL_TRACE(s * 10 + 7);
 #pragma unroll
         for (int q = 0; q < 16; q += 8) store_chunk8p(X_hi, X_lo, kRows, r, wg * kCols + q, &z0[q / 2]);
         half(16, z1);
@@ -2458,6 +2496,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcAr
       tc_fence_before();
       st_sync();
       if (stid == 0) mbar_arrive(&rdy_z1[s]);
+      if (stid == 0) NL_TRACE(s * 10 + 8);
       if (A.zstash && (warp & 7) == 0 && elect_one()) {  // per-row time grids: Z1g image -> HBM (point_dw1_kernel)
         unsigned char* dst = A.zstash + (size_t)tile * 2 * kStashImg;
         bulk_store(dst, X_hi, kStashImg);
@@ -3152,6 +3191,10 @@ static cudaError_t launch_fused_tc_impl(const nl_desc* d, bool bwd, const void* 
       A.dp_part = dp_part;
       e = cudaMemsetAsync(g1buf, 0, (size_t)d->T * tc::kH * 8 * 4, st);
       if (e != cudaSuccess) return e;
+    }
+    {
+      static const int baton = [] { const char* v = getenv("NL_B200_BS2_BATON"); return v ? atoi(v) : 1; }();
+      A.baton = baton;
     }
     if (bg.ok && bg.two)
       e = d->K <= 2 ? launch_bs2<2>(A, pl.grid, bg.smem_two, st) : launch_bs2<tc::kMaxK>(A, pl.grid, bg.smem_two, st);

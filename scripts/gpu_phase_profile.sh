@@ -40,11 +40,11 @@ for k, nm in ((0, "forward"), (12, "backward")):
         if v[i]: print("   %-28s %5.1f%%" % (names[i], 100.0*v[i]/tot))
 tr = (ctypes.c_longlong * 64)()
 if hasattr(lib, "nl_debug_tc_trace") and lib.nl_debug_tc_trace(tr) == 0:
-    tnames = {0: "E tile start", 1: "E L3 done + h2 landed", 2: "E D1(prev) done, heads start", 3: "E dO stored+arrive",
-              4: "E dH2 done", 5: "E Z2g stored+arrive", 6: "E dH1 done + h1 landed", 7: "E Z1g stored+arrive",
-              8: "Iaux h1 load issued", 9: "Iaux next h2 load issued", 10: "Imain L3 issue", 11: "Imain L3 issued",
-              12: "Imain dH2 issue", 19: "Imain dH2 issued", 13: "Imain dH1 issue", 14: "Iaux dW3 issue",
-              15: "Iaux D1 issue", 16: "Iaux D1 issued", 17: "Iaux dW2 issue", 18: "Iaux dW2 issued"}
+    tnames = {}
+    for st in (0, 1):
+        for sl, nm in enumerate(["tile start", "L3 done + h2 landed", "dO stored+arrive", "dH2 done", "dW3 done (X free)",
+                                 "Z2g stored+arrive", "dH1 done + h1 landed", "dW2 done (X free)", "Z1g stored+arrive"]):
+            tnames[st * 10 + sl] = "S%d %s" % (st, nm)
     ev = []
     for k in range(3):
         for sl, nm in tnames.items():
