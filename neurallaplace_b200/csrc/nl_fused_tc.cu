@@ -59,8 +59,13 @@ namespace tc {
     if (blockIdx.x == 0 && A.prof && tile >= tile_lo + 4 && tile < tile_lo + 7)                           \
       A.prof[12 + (slot) + 20 * (int)(tile - tile_lo - 4)] = clock64();                                   \
   } while (0)
+#define NL_TILECLOCK(s_, j_)                                                                               \
+  do {                                                                                                   \
+    if (blockIdx.x == 0 && A.prof && (s_) == 0 && (j_) < 256) A.prof[12 + 64 + (int)(j_)] = clock64();      \
+  } while (0)
 #else
 #define NL_TRACE(slot) do { } while (0)
+#define NL_TILECLOCK(s_, j_) do { } while (0)
 #endif
 
 constexpr int kH = 64;
@@ -1916,6 +1921,10 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
 //   X : dO -> Z2g -> Z1g      (each rewrite waits for the weight-gradient GEMM that still reads it)
 //   H : h2 -> h1 of the same tile, streamed in one after the other ([ones] / [1 p] chunk rewritten in place)
 // While a stream waits for a GEMM or an image, the other stream's epilogue has the SM.
+// (Tried and removed, round 2: a role-specialised variant -- 8 "head" warps doing the head stage of every tile, 4 warps
+// per stream for Z2g / Z1g -- was parity-green but slower, 1.33 vs 1.25 ms: with two tiles in flight the period is one
+// stream's serial loop  heads -> dH2 -> dW3 -> Z2g -> dH1 -> dW2 -> Z1g -> h2 load -> L3  (17-19 k clk, half of it GEMM
+// round trips), whoever runs the stages; a third tile in flight needs another X + H image pair, +80 KB.)
 struct Bs2Smem {
   size_t X[2], Hb[2], P[2], W2, W3, small, total;
   size_t X_img, H_img, P_img, W2_img, W3_img;
@@ -2392,6 +2401,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcAr
         if (use_baton) mbar_arrive(&baton[1 - s]);
       }
       if (stid == 0) NL_TRACE(s * 10 + 2);
+      if (stid == 0) NL_TILECLOCK(s, tile - tile_lo);
       pend_aux0 = true;
 
       // ---- 3. Z2g = dH2 (1 - h2^2) -> X.  dW3 still reads dO there: the first half of the columns is formed in
@@ -3123,8 +3133,8 @@ static cudaError_t launch_fused_tc_impl(const nl_desc* d, bool bwd, const void* 
   }
 #ifdef NL_TC_PROFILE
   if (!g_prof_buf) {
-    cudaMalloc(&g_prof_buf, (2 * 12 + 64) * sizeof(long long));
-    cudaMemset(g_prof_buf, 0, (2 * 12 + 64) * sizeof(long long));
+    cudaMalloc(&g_prof_buf, (2 * 12 + 64 + 256) * sizeof(long long));
+    cudaMemset(g_prof_buf, 0, (2 * 12 + 64 + 256) * sizeof(long long));
   }
   A.prof = g_prof_buf + (bwd ? 12 : 0);
 #endif
@@ -3476,6 +3486,13 @@ cudaError_t launch_fused_tc_dehoog(const nl_desc* d, bool bwd, const void* p, co
 #ifdef NL_TC_PROFILE
 // profiling build only (scripts/gpu_phase_profile.sh): per-phase clock totals of thread 0, summed over CTAs
 // event trace of one tile of CTA 0 (saved backward): 64 raw clock64 stamps
+// per-tile clock of stream 0 of CTA 0 (two-tile saved backward kernels): out256[j] = clock64 when its j-th dO image was stored
+extern "C" int nl_debug_tc_tileclock(long long* out256) {
+  if (!nl::g_prof_buf) return -1;
+  cudaDeviceSynchronize();
+  cudaMemcpy(out256, nl::g_prof_buf + 24 + 64, 256 * sizeof(long long), cudaMemcpyDeviceToHost);
+  return 0;
+}
 extern "C" int nl_debug_tc_trace(long long* out64) {
   if (!nl::g_prof_buf) return -1;
   cudaDeviceSynchronize();

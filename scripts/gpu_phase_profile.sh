@@ -55,4 +55,11 @@ if hasattr(lib, "nl_debug_tc_trace") and lib.nl_debug_tc_trace(tr) == 0:
         t0 = ev[0][0]
         print("event trace of CTA 0, stream 0 (saved backward, two tiles in flight), clocks relative to the first event")
         for v, nm in ev: print("   %8d  %s" % (v - t0, nm))
+tc = (ctypes.c_longlong * 256)()
+if hasattr(lib, "nl_debug_tc_tileclock") and lib.nl_debug_tc_tileclock(tc) == 0:
+    v = [x for x in tc if x]
+    if len(v) > 2:
+        d = [v[i + 1] - v[i] for i in range(len(v) - 1)]
+        print("stream 0 of CTA 0: %d tiles, total %d clk, clocks between consecutive dO stores:" % (len(v), v[-1] - v[0]))
+        print("   " + " ".join(str(x) for x in d))
 PY
