@@ -1967,6 +1967,9 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcAr
   // LOCKSTEP -- both in the head stage, then both waiting for their GEMMs (timeline in profiles/) -- and the second
   // tile in flight overlaps nothing.  With the baton one stream's GEMM round trips run under the other's heads.
   __shared__ __align__(8) uint64_t baton[2];
+  // "h1 and dH1 consumed": the Z1g stage has read everything it needs from the H image and from TMEM (before it waits
+  // for dW2 and stores), so the next tile's h2 load and L3 run under the Z1g stores instead of after them
+  __shared__ __align__(8) uint64_t hfree[2];
   __shared__ uint32_t tmem_slot;
 
   const int n = A.n, K = A.K, NP = A.NP;
@@ -2020,6 +2023,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcAr
       mbar_init(&seq_dh2[s], 1);
       mbar_init(&seq_dh1[s], 1);
       mbar_init(&baton[s], 1);
+      mbar_init(&hfree[s], 1);
     }
     fence_mbar_init();
   }
@@ -2084,7 +2088,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcAr
           load_img(tile_lo, 1, &bar_h2[s]);
           bulk_prefetch_l2(A.stash + (size_t)tile_lo * kStashTile, 2 * kStashImg);
         }
-        uint32_t p_dO = 0, p_z2 = 0, p_z1 = 0, p_sdh2 = 0, p_sdh1 = 0, p_h1 = 0, p_a0 = 0;
+        uint32_t p_dO = 0, p_z2 = 0, p_z1 = 0, p_sdh2 = 0, p_sdh1 = 0, p_h1 = 0, p_a0 = 0, p_a1 = 0, p_hf = 0;
         int cur_t = -1, slot_tiles = 0;
         int t_run = (int)(tile_lo / A.nbt), b_run = (int)(tile_lo % A.nbt);
         for (long long tile = tile_lo; tile < tile_hi; ++tile) {
@@ -2121,11 +2125,15 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcAr
           tc_fence_after();
           issue_gemm(make_gemm(aX, x_lo, kRows, 1, aH, h_lo, kRows, 1, 64, kH1Cols, kRows), tdW2, !restart);
           umma_commit(&bar_aux[s][1]);
-          // Z1g stored: the epilogue has waited for dW2 and read h1 for the last time -> the H image is free for the
-          // next tile's h2 (D1 takes [1 p] from its own small image, it no longer holds H)
+          // dW2 has executed and the epilogue has read h1 for the last time (hfree: before its Z1g stores) -> the H
+          // image is free for the next tile's h2 (D1 takes [1 p] from its own small image, it does not hold H)
+          mbar_wait_relaxed(&bar_aux[s][1], p_a1);
+          p_a1 ^= 1;
+          mbar_wait_relaxed(&hfree[s], p_hf);
+          p_hf ^= 1;
+          if (tile + 1 < tile_hi) load_img(tile + 1, 1, &bar_h2[s]);
           mbar_wait_relaxed(&rdy_z1[s], p_z1);
           p_z1 ^= 1;
-          if (tile + 1 < tile_hi) load_img(tile + 1, 1, &bar_h2[s]);
           // D1 (+)= Z1g^T . [1 p]
           tc_fence_after();
           issue_gemm(make_gemm(aX, x_lo, kRows, 1, aP, p_lo, kRows, 1, 64, 8, kRows), tD1, !first_in_slot);
@@ -2489,11 +2497,14 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcAr
         };
         p2::f2 z0[8], z1[8];
         half(0, z0);
+        half(16, z1);
+        tc_fence_before();
+        st_sync();
+        if (stid == 0) mbar_arrive(&hfree[s]);
         wait_dw2();
         if (stid == 0) NL_TRACE(s * 10 + 7);
 #pragma unroll
         for (int q = 0; q < 16; q += 8) store_chunk8p(X_hi, X_lo, kRows, r, wg * kCols + q, &z0[q / 2]);
-        half(16, z1);
 #pragma unroll
         for (int q = 0; q < 16; q += 8) store_chunk8p(X_hi, X_lo, kRows, r, wg * kCols + 16 + q, &z1[q / 2]);
 #pragma unroll
