@@ -23,8 +23,15 @@
 
 namespace nl {
 
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
+// float32: 256 threads, CUDA-core FFMA GEMMs with rows <-> lanes.  float64: 512 threads and the two GEMM shapes on the
+// tensor pipe (DMMA, mma.sync.m8n8k4.f64): with 32 rows per tile (shared memory) the FFMA-style loop issues 9 loads per
+// 8 DFMA and eight warps cannot hide their latency (measured 1.7 TFLOP/s of GEMM work, 5 % of the FP64 peak).
+template <typename R>
+struct SimtCfg {
+  static constexpr int kThreads = sizeof(R) == 8 ? 512 : 256;
+  static constexpr int kWarps = kThreads / 32;
+  static constexpr int kPad = sizeof(R) == 8 ? 4 : 1;  // row padding of the shared-memory matrices (see smem_layout)
+};
 constexpr int kKCU = 32;  // s points per feature chunk of layer 1
 
 template <typename R>
@@ -51,21 +58,27 @@ struct SmemLayout {
   size_t H1, H2, G, S1, O, U, Coef, Ctx, Pm, X, total;  // offsets in units of R
 };
 
-__host__ __device__ inline SmemLayout smem_layout(int rmax, int H, int n, int K, bool bwd, bool fourier_coef,
-                                                  int ctx_reals) {
+// pad = 1 (float32): odd row strides, conflict-free for the rows <-> lanes access of the FFMA loops.
+// pad = 4 (float64): row strides == 4 (mod 16) doubles, i.e. 32 B (mod 128 B): the DMMA A fragment (8 rows x 4
+// consecutive doubles per warp load) then covers 256 B in two wavefronts.
+__host__ __device__ inline SmemLayout smem_layout(int rmax, int nslots, int H, int n, int K, bool bwd,
+                                                  bool fourier_coef, int ctx_reals, int pad = 1) {
+  // rmax rows (points) per tile; nslots time slots per tile (shared time grid: TT <= rmax / BB, per-row grids: one
+  // per row).  S1 is also the backward's per-slot G1 buffer.
   SmemLayout L;
-  L.ldh = H + 1;
-  L.ldo = 2 * n + 1;
-  L.ldu = 2 * kKCU + 1;
+  auto ld_of = [pad](int cols) { return pad == 1 ? cols + 1 : ((cols + 15) / 16) * 16 + 4; };
+  L.ldh = ld_of(H);
+  L.ldo = ld_of(2 * n);
+  L.ldu = ld_of(2 * kKCU);
   size_t o = 0;
   L.H1 = o; o += (size_t)rmax * L.ldh;
   L.H2 = o; o += (size_t)rmax * L.ldh;
   L.G = o;  o += bwd ? (size_t)rmax * L.ldh : 0;
-  L.S1 = o; o += (size_t)rmax * L.ldh;
+  L.S1 = o; o += (size_t)nslots * L.ldh;
   L.O = o;  o += (size_t)rmax * L.ldo;
-  L.U = o;  o += (size_t)rmax * L.ldu;
-  L.Coef = o; o += fourier_coef ? (size_t)rmax * n * 2 : 0;
-  L.Ctx = o; o += (size_t)rmax * ctx_reals;
+  L.U = o;  o += (size_t)nslots * L.ldu;
+  L.Coef = o; o += fourier_coef ? (size_t)nslots * n * 2 : 0;
+  L.Ctx = o; o += (size_t)nslots * ctx_reals;
   L.Pm = o; o += (size_t)rmax * K;
   L.X = o;  o += (size_t)rmax * 2;
   L.total = o;
@@ -74,8 +87,9 @@ __host__ __device__ inline SmemLayout smem_layout(int rmax, int H, int n, int K,
 
 // C[r][c] = sum_k A[r][k] * W[c*sc + k*sk]; rows r = lane + 32*i, columns split over warps.
 template <typename R, int RP, int CB, typename Epi>
-__device__ __forceinline__ void gemm_rows(const R* __restrict__ sA, int lda, int Kdim, int rows,
-                                          const R* __restrict__ W, int64_t sc, int64_t sk, int NC, Epi epi) {
+__device__ __forceinline__ void gemm_rows_simt(const R* __restrict__ sA, int lda, int Kdim, int rows,
+                                               const R* __restrict__ W, int64_t sc, int64_t sk, int NC, Epi epi) {
+  constexpr int kWarps = SimtCfg<R>::kWarps;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int c0 = warp * CB; c0 < NC; c0 += kWarps * CB) {
     R acc[RP][CB];
@@ -90,7 +104,7 @@ __device__ __forceinline__ void gemm_rows(const R* __restrict__ sA, int lda, int
       for (int k = 0; k < Kdim; ++k) {
         R a[RP];
 #pragma unroll
-        for (int i = 0; i < RP; ++i) a[i] = sA[(lane + 32 * i) * lda + k];
+        for (int i = 0; i < RP; ++i) a[i] = (lane + 32 * i < rows) ? sA[(lane + 32 * i) * lda + k] : R(0);
 #pragma unroll
         for (int j = 0; j < CB; ++j) {
           R w = __ldg(Wc + j * sc + k * sk);
@@ -102,7 +116,7 @@ __device__ __forceinline__ void gemm_rows(const R* __restrict__ sA, int lda, int
       for (int k = 0; k < Kdim; ++k) {
         R a[RP];
 #pragma unroll
-        for (int i = 0; i < RP; ++i) a[i] = sA[(lane + 32 * i) * lda + k];
+        for (int i = 0; i < RP; ++i) a[i] = (lane + 32 * i < rows) ? sA[(lane + 32 * i) * lda + k] : R(0);
 #pragma unroll
         for (int j = 0; j < CB; ++j) {
           if (j < cb) {
@@ -127,10 +141,11 @@ __device__ __forceinline__ void gemm_rows(const R* __restrict__ sA, int lda, int
 
 // out[j*ldo + c] += sum_{r<rows} A1[r*ld1 + j] * A2[r*ld2 + c]   (weight gradients; lanes <-> c)
 template <typename R>
-__device__ __forceinline__ void gemm_tn_accum(const R* __restrict__ sA1, int ld1, int NJ,
-                                              const R* __restrict__ sA2, int ld2, int NC, int rows, R* out,
-                                              int64_t ldo) {
+__device__ __forceinline__ void gemm_tn_accum_simt(const R* __restrict__ sA1, int ld1, int NJ,
+                                                   const R* __restrict__ sA2, int ld2, int NC, int rows, R* out,
+                                                   int64_t ldo) {
   constexpr int JB = 8, CP = 2;
+  constexpr int kWarps = SimtCfg<R>::kWarps;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int j0 = warp * JB; j0 < NJ; j0 += kWarps * JB) {
     const int jb = min(JB, NJ - j0);
@@ -168,10 +183,128 @@ __device__ __forceinline__ void gemm_tn_accum(const R* __restrict__ sA1, int ld1
   }
 }
 
+
+// ---- float64 on the tensor pipe ---------------------------------------------------------------------------------
+// D(8x8) += A(8x4) . B(4x8), one double of A and of B and two of D per lane:
+//   A[row = lane / 4][k = lane % 4],  B[k = lane % 4][col = lane / 4],  D[row = lane / 4][col = 2 (lane % 4) + {0, 1}]
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+// gemm_rows on DMMA: the tile's (at most 32) rows are four 8-row blocks, the NC columns blocks of 8; a work item is
+// MTP row blocks x one column block (the B fragment -- the weights, read through L1 -- is reused MTP times) and the
+// items are dealt to the warps.  Rows past `rows` hold stale shared memory: they only reach their own (discarded)
+// output rows.
+template <int MT, int MTP, typename Epi>
+__device__ __forceinline__ void gemm_rows_dmma_t(const double* __restrict__ sA, int lda, int Kdim, int rows,
+                                                 const double* __restrict__ W, int64_t sc, int64_t sk, int NC,
+                                                 Epi epi) {
+  constexpr int kWarps = SimtCfg<double>::kWarps;
+  constexpr int kGroups = MT / MTP;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lr = lane >> 2, lk = lane & 3;
+  const int nb_n = (NC + 7) >> 3;
+  for (int item = warp; item < nb_n * kGroups; item += kWarps) {
+    const int nb = item / kGroups, mg = item - nb * kGroups;
+    if (mg * MTP * 8 >= rows) continue;
+    const int cb = nb * 8 + lr;
+    const bool cok = cb < NC;
+    const double* wp = W + (int64_t)(cok ? cb : 0) * sc;
+    const int rbase = mg * MTP * 8 + lr;
+    const double* ap = sA + rbase * lda;
+    double acc[MTP][2];
+#pragma unroll
+    for (int m = 0; m < MTP; ++m) acc[m][0] = acc[m][1] = 0.0;
+#pragma unroll 2
+    for (int k0 = 0; k0 < Kdim; k0 += 4) {
+      const int k = k0 + lk;
+      const bool kok = k < Kdim;
+      const double b = (cok && kok) ? __ldg(wp + (int64_t)k * sk) : 0.0;
+#pragma unroll
+      for (int m = 0; m < MTP; ++m) {
+        // (rows past `rows` are not read: the per-slot matrices only hold `rows` of them)
+        const double a = (kok && rbase + m * 8 < rows) ? ap[m * 8 * lda + k] : 0.0;
+        dmma884(acc[m][0], acc[m][1], a, b);
+      }
+    }
+    const int c = nb * 8 + 2 * lk;
+#pragma unroll
+    for (int m = 0; m < MTP; ++m) {
+      const int r = rbase + m * 8;
+      if (r < rows) {
+        if (c < NC) epi(r, c, acc[m][0]);
+        if (c + 1 < NC) epi(r, c + 1, acc[m][1]);
+      }
+    }
+  }
+}
+// MT = 8-row blocks per tile (4 or 8)
+template <int MT, typename Epi>
+__device__ __forceinline__ void gemm_rows_dmma(const double* __restrict__ sA, int lda, int Kdim, int rows,
+                                               const double* __restrict__ W, int64_t sc, int64_t sk, int NC, Epi epi) {
+  constexpr int kWarps = SimtCfg<double>::kWarps;
+  const int nb_n = (NC + 7) >> 3;
+  const int mt_used = (rows + 7) >> 3;
+  // enough items for every warp, as many row blocks per item as that allows (B fragment reuse)
+  if (nb_n >= kWarps || mt_used <= 1) gemm_rows_dmma_t<MT, MT>(sA, lda, Kdim, rows, W, sc, sk, NC, epi);
+  else if (2 * nb_n >= kWarps || mt_used <= 2) gemm_rows_dmma_t<MT, MT / 2>(sA, lda, Kdim, rows, W, sc, sk, NC, epi);
+  else gemm_rows_dmma_t<MT, MT / 4>(sA, lda, Kdim, rows, W, sc, sk, NC, epi);
+}
+
+// gemm_tn_accum on DMMA: out[j][c] += sum_r A1[r][j] A2[r][c]; work items are 8 x 8 blocks of `out`, the reduction runs
+// over the tile's rows four at a time.  Every element of `out` is read-modify-written by exactly one lane (fixed
+// assignment): deterministic, like the FFMA version.
+__device__ __forceinline__ void gemm_tn_accum_dmma(const double* __restrict__ sA1, int ld1, int NJ,
+                                                   const double* __restrict__ sA2, int ld2, int NC, int rows,
+                                                   double* out, int64_t ldo) {
+  constexpr int kWarps = SimtCfg<double>::kWarps;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lr = lane >> 2, lk = lane & 3;
+  const int jb_n = (NJ + 7) >> 3, cb_n = (NC + 7) >> 3;
+  for (int item = warp; item < jb_n * cb_n; item += kWarps) {
+    const int jb = item / cb_n, cb = item - jb * cb_n;
+    const int j = jb * 8 + lr, c = cb * 8 + lr;
+    const bool jok = j < NJ, cok = c < NC;
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll 4
+    for (int r0 = 0; r0 < rows; r0 += 4) {
+      const int r = r0 + lk;
+      const bool rok = r < rows;
+      const double a = (rok && jok) ? sA1[r * ld1 + j] : 0.0;
+      const double b = (rok && cok) ? sA2[r * ld2 + c] : 0.0;
+      dmma884(a0, a1, a, b);
+    }
+    const int co = cb * 8 + 2 * lk;
+    if (jok) {
+      double* o = out + (int64_t)j * ldo + co;
+      if (co < NC) o[0] += a0;
+      if (co + 1 < NC) o[1] += a1;
+    }
+  }
+}
+
+template <typename R, int RP, int CB, typename Epi>
+__device__ __forceinline__ void gemm_rows(const R* __restrict__ sA, int lda, int Kdim, int rows,
+                                          const R* __restrict__ W, int64_t sc, int64_t sk, int NC, Epi epi) {
+  if constexpr (sizeof(R) == 8) {
+    gemm_rows_dmma<4 * RP>(sA, lda, Kdim, rows, W, sc, sk, NC, epi);
+  } else {
+    gemm_rows_simt<R, RP, CB>(sA, lda, Kdim, rows, W, sc, sk, NC, epi);
+  }
+}
+template <typename R>
+__device__ __forceinline__ void gemm_tn_accum(const R* __restrict__ sA1, int ld1, int NJ, const R* __restrict__ sA2,
+                                              int ld2, int NC, int rows, R* out, int64_t ldo) {
+  if constexpr (sizeof(R) == 8) gemm_tn_accum_dmma(sA1, ld1, NJ, sA2, ld2, NC, rows, out, ldo);
+  else gemm_tn_accum_simt<R>(sA1, ld1, NJ, sA2, ld2, NC, rows, out, ldo);
+}
+
 // out[c] += sum_{r<rows} A[r*ld + c]
 template <typename R>
 __device__ __forceinline__ void colsum_accum(const R* __restrict__ sA, int ld, int NC, int rows, R* out) {
-  for (int c = threadIdx.x; c < NC; c += kThreads) {
+  for (int c = threadIdx.x; c < NC; c += SimtCfg<R>::kThreads) {
     R s = R(0);
     for (int r = 0; r < rows; ++r) s += sA[r * ld + c];
     out[c] += s;
@@ -188,15 +321,17 @@ struct SlotCtx {
 };
 
 template <typename R, int RP, bool BWD>
-__global__ void __launch_bounds__(kThreads, 1) fused_simt_kernel(FusedArgs<R> A) {
+__global__ void __launch_bounds__(SimtCfg<R>::kThreads, 1) fused_simt_kernel(FusedArgs<R> A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   R* sm = reinterpret_cast<R*>(smem_raw);
   constexpr int RMAX = 32 * RP;
+  constexpr int kThreads = SimtCfg<R>::kThreads, kWarps = SimtCfg<R>::kWarps;
   const IltParams<R> P = A.P;
   const int H = A.H, n = A.n, K = A.K, D = A.D;
   const bool dehoog = P.family == NL_DEHOOG;
   const bool fourier_coef = P.family == NL_FOURIER;
-  const SmemLayout L = smem_layout(RMAX, H, n, K, BWD, fourier_coef, (int)(sizeof(SlotCtx<R>) / sizeof(R)));
+  const SmemLayout L = smem_layout(RMAX, A.t_mode == NL_T_PER_ROW ? RMAX : A.TT, H, n, K, BWD, fourier_coef,
+                                   (int)(sizeof(SlotCtx<R>) / sizeof(R)), SimtCfg<R>::kPad);
   R* sH1 = sm + L.H1;
   R* sH2 = sm + L.H2;
   R* sG = sm + L.G;
@@ -501,8 +636,15 @@ SimtPlan simt_plan(const nl_desc* d, int pass) {
   const int ctx_reals = 8;
   const size_t limit = 227 * 1024;
   int rp = 0;
-  for (int cand = (d->dtype == NL_F64 ? 1 : 2); cand >= 1; --cand) {
-    SmemLayout L = smem_layout(32 * cand, d->H, d->n, d->K, bwd, d->family == NL_FOURIER, ctx_reals);
+  // rows per tile: 64 when the shared-memory matrices fit (float64: shared time grids only -- the per-slot matrices
+  // then hold rmax / BB slots instead of rmax), else 32
+  for (int cand = 2; cand >= 1; --cand) {
+    const int rmax_c = 32 * cand;
+    const int BBc = std::max(1, std::min(d->B, rmax_c));
+    const int TTc = std::max(1, std::min(d->T, rmax_c / BBc));
+    const int nslots = d->t_mode == NL_T_PER_ROW ? rmax_c : TTc;
+    SmemLayout L = smem_layout(rmax_c, nslots, d->H, d->n, d->K, bwd, d->family == NL_FOURIER, ctx_reals,
+                               d->dtype == NL_F64 ? SimtCfg<double>::kPad : SimtCfg<float>::kPad);
     if (L.total * rs <= limit) {
       rp = cand;
       pl.smem = L.total * rs;
@@ -537,11 +679,11 @@ static cudaError_t launch_rp(const FusedArgs<R>& A, bool bwd, int grid, size_t s
   if (bwd) {
     e = cudaFuncSetAttribute(fused_simt_kernel<R, RP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    fused_simt_kernel<R, RP, true><<<grid, kThreads, smem, st>>>(A);
+    fused_simt_kernel<R, RP, true><<<grid, SimtCfg<R>::kThreads, smem, st>>>(A);
   } else {
     e = cudaFuncSetAttribute(fused_simt_kernel<R, RP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    fused_simt_kernel<R, RP, false><<<grid, kThreads, smem, st>>>(A);
+    fused_simt_kernel<R, RP, false><<<grid, SimtCfg<R>::kThreads, smem, st>>>(A);
   }
   return cudaGetLastError();
 }
