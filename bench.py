@@ -454,14 +454,17 @@ def run_b200(a):
   def e2e_step():
     return staged(p_pin, t_pin, g_pin, x_pin, grads_pin)
 
-  for _ in range(4):  # the copy streams grow their own allocator pools during the first steps
+  for _ in range(8):  # the copy streams grow their own allocator pools during the first steps
     e2e_step()
   barrier()
   e2e_steps = max(3, min(a.steps, 10))
-  # three spans of e2e_steps steps, the median span is reported: the span crosses the host (pinned-buffer copies, ~60
-  # Python-issued launches per step), and a single host hiccup inside one span doubled its time in 2 of 14 runs
-  e2e_spans = []
-  for _ in range(3):
+  # five spans of e2e_steps steps, the median span is reported (all five are in the JSON line): this leg is bound by
+  # the host -- the Python layer needs about as long to issue a step (~60 calls) as the GPU to run it -- so a host
+  # hiccup inside a span shows up in full (one span in ~10 was 2x, rarely 8x, the others of the same run normal)
+  e2e_spans, e2e_diag = [], []
+  for _ in range(5):
+    ms0 = torch.cuda.memory_stats(dev)
+    t_host0 = time.perf_counter()
     es, ee = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     es.record()
     for _ in range(e2e_steps):
@@ -470,7 +473,13 @@ def run_b200(a):
     ee.record()
     barrier()
     e2e_spans.append(es.elapsed_time(ee) / e2e_steps)
-  e2e_ms = sorted(e2e_spans)[1]
+    ms1 = torch.cuda.memory_stats(dev)
+    e2e_diag.append({"host_s": round(time.perf_counter() - t_host0, 5),
+                     "cudaMalloc": ms1.get("num_device_alloc", 0) - ms0.get("num_device_alloc", 0),
+                     "cudaFree": ms1.get("num_device_free", 0) - ms0.get("num_device_free", 0),
+                     "alloc_retries": ms1.get("num_alloc_retries", 0) - ms0.get("num_alloc_retries", 0),
+                     "reserved_gb": round(ms1.get("reserved_bytes.all.current", 0) / 2**30, 2)})
+  e2e_ms = sorted(e2e_spans)[len(e2e_spans) // 2]
   h2d = p_pin.numel() * p_pin.element_size() + t_pin.numel() * t_pin.element_size() + g_pin.numel() * g_pin.element_size()
   d2h = x_pin.numel() * x_pin.element_size() + grads_pin.numel() * grads_pin.element_size()
 
@@ -552,8 +561,8 @@ def run_b200(a):
                                  if graphed is not None else "laplace_reconstruct + autograd"),
                    "host_numa_bound": bool(numa_bound), "fwd_ms": fwd_ms, "bwd_ms": bwd_ms},
         "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms, "steps_per_span": e2e_steps, "spans": 3, "span_ms_per_step": e2e_spans,
-                "reported": "median span"},
+                "ms_per_step": e2e_ms, "steps_per_span": e2e_steps, "spans": len(e2e_spans), "span_ms_per_step": e2e_spans,
+                "reported": "median span", "span_diag": e2e_diag},
         "gpu_launches": launches,
         "clocks": clocks_timed,
         "sustained": sustained,

@@ -2162,14 +2162,23 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcAr
     const bool use_baton = A.baton != 0;
     uint32_t ph_aux0 = 0, ph_aux1 = 0, ph_aux2 = 0;
     bool pend_aux0 = false, pend_aux1 = false, pend_aux2 = false;
+    // Only the stream's first warp polls an mbarrier; the other seven wait at the stream's named barrier.  A
+    // try_wait returns after ~100 clk whether or not it carries a suspend-time hint, and every poll is a
+    // shared-memory wavefront: with all 16 epilogue warps polling ncu counted 39 M try_wait warp-instructions per
+    // launch (1 200 per tile, a seventh of the kernel's shared-memory traffic, a fifth of its issued instructions
+    // with the loop around them) in a kernel whose tensor core is fed from shared memory.
+    const bool lead = (stid >> 5) == 0;
+    auto lwait = [&](uint64_t* bar, uint32_t ph) {
+      if (lead) mbar_wait(bar, ph);
+    };
     auto wait_dw3 = [&]() {
-      if (pend_aux0) { mbar_wait(&bar_aux[s][0], ph_aux0); ph_aux0 ^= 1; pend_aux0 = false; }
+      if (pend_aux0) { lwait(&bar_aux[s][0], ph_aux0); st_sync(); ph_aux0 ^= 1; pend_aux0 = false; }
     };
     auto wait_dw2 = [&]() {
-      if (pend_aux1) { mbar_wait(&bar_aux[s][1], ph_aux1); ph_aux1 ^= 1; pend_aux1 = false; }
+      if (pend_aux1) { lwait(&bar_aux[s][1], ph_aux1); st_sync(); ph_aux1 ^= 1; pend_aux1 = false; }
     };
     auto wait_d1 = [&]() {
-      if (pend_aux2) { mbar_wait(&bar_aux[s][2], ph_aux2); ph_aux2 ^= 1; pend_aux2 = false; }
+      if (pend_aux2) { lwait(&bar_aux[s][2], ph_aux2); st_sync(); ph_aux2 ^= 1; pend_aux2 = false; }
     };
     const long long tile_lo = s_lo[s], tile_hi = s_lo[s] + s_n[s];
 
@@ -2306,24 +2315,26 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcAr
         *reinterpret_cast<uint4*>(H_hi + off) = make_uint4(0x00003F80u, 0, 0, 0);
         *reinterpret_cast<uint4*>(H_lo + off) = make_uint4(0, 0, 0, 0);
       }
-      mbar_wait(&bar_l3[s], ph_l3);
+      // L3 has run (its h2 image landed before it could); X is still read by D1 of the previous tile (long done by
+      // now: it ran under the h2 load and L3) and by the bulk store that exported the previous Z1g image; the baton
+      // (one stream at a time in the head stage).  One wait of the leader warp for all of them, one barrier.
+      const bool take_baton = use_baton && !(s == 0 && tile == tile_lo);
+      if (lead) {
+        mbar_wait(&bar_l3[s], ph_l3);
+        mbar_wait(&bar_h2[s], ph_h2);
+        if (pend_aux2) mbar_wait(&bar_aux[s][2], ph_aux2);
+        if (A.zstash && elect_one()) bulk_wait_read_all();
+        if (take_baton) mbar_wait(&baton[s], ph_baton);
+      }
+      st_sync();
       ph_l3 ^= 1;
-      mbar_wait(&bar_h2[s], ph_h2);  // landed before L3 could run; makes the bulk-async writes visible to this thread
       ph_h2 ^= 1;
+      if (pend_aux2) { ph_aux2 ^= 1; pend_aux2 = false; }
+      if (take_baton) ph_baton ^= 1;
       tc_fence_after();
       if (stid == 0) NL_TRACE(s * 10 + 1);
-      // X is still read by D1 of the previous tile (long done by now: it ran under the h2 load and L3) ...
-      wait_d1();
-      if (A.zstash) {  // ... and by the bulk store that exported the previous Z1g image
-        if ((warp & 7) == 0 && elect_one()) bulk_wait_read_all();
-        st_sync();
-      }
 
-      // ---- 2. heads forward + backward -> dO image (one stream at a time: baton)
-      if (use_baton && !(s == 0 && tile == tile_lo)) {
-        mbar_wait(&baton[s], ph_baton);
-        ph_baton ^= 1;
-      }
+      // ---- 2. heads forward + backward -> dO image (one stream at a time: baton, taken above)
       {
         const int c_end = min((wg + 1) * cw, ncols_real);
         int c0 = wg * cw;
@@ -2414,7 +2425,8 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcAr
 
       // ---- 3. Z2g = dH2 (1 - h2^2) -> X.  dW3 still reads dO there: the first half of the columns is formed in
       // registers while it runs, stores start once it is done
-      mbar_wait(&bar_main[s], ph_main);
+      lwait(&bar_main[s], ph_main);
+      st_sync();
       ph_main ^= 1;
       tc_fence_after();
       if (stid == 0) NL_TRACE(s * 10 + 3);
@@ -2461,11 +2473,12 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved2_kernel(TcAr
       pend_aux1 = true;
 
       // ---- 4. Z1g = dH1 (1 - h1^2) -> X ; dp.  dW2 still reads Z2g there: first half formed in registers meanwhile
-      mbar_wait(&bar_main[s], ph_main);
+      lwait(&bar_main[s], ph_main);
+      lwait(&bar_h1[s], ph_h1);
+      st_sync();
       ph_main ^= 1;
-      tc_fence_after();
-      mbar_wait(&bar_h1[s], ph_h1);
       ph_h1 ^= 1;
+      tc_fence_after();
       if (stid == 0) NL_TRACE(s * 10 + 6);
       float dpv[KP];
       {

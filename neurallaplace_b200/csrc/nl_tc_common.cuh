@@ -50,10 +50,29 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 // Bounded wait: a protocol bug must abort the kernel (trap), never hang the GPU.
+// try_wait carries a suspend-time hint: without one the hardware returns "not yet" after a short system-dependent time
+// and the loop polls -- ncu counted 39 M try_wait warp-instructions per launch of the two-tile saved backward (1 200 per
+// tile, ~20 % of its issued instructions with the loop around them), each of them a shared-memory wavefront competing
+// with the tensor core's operand reads (the kernel is shared-memory-bandwidth bound).  With the hint the warp sleeps in
+// hardware until the phase completes.
+#ifndef NL_MBAR_HINT_NS
+#define NL_MBAR_HINT_NS 20000u
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
-  for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+  for (uint32_t spin = 0; spin < (1u << 20); ++spin) {
+#if NL_MBAR_HINT_NS > 0
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity), "r"(NL_MBAR_HINT_NS)
+        : "memory");
+#else
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
@@ -63,6 +82,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(done)
         : "r"(addr), "r"(parity)
         : "memory");
+#endif
     if (done) return;
   }
   __trap();
