@@ -1502,17 +1502,23 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
     // =============================== epilogue warpgroups ===============================
     const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     auto ep_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kEpi) : "memory"); };
+    // one warp polls an mbarrier, the other epilogue warps wait at the named barrier: every try_wait poll is a
+    // shared-memory wavefront (see fused_tc_bwd_saved2_kernel)
+    auto ewait = [&](uint64_t* bar, uint32_t ph) {
+      if (warp == 0) mbar_wait(bar, ph);
+      ep_sync();
+    };
     uint32_t ph_main = 0, ph_l3 = 0, ph_h1 = 0, ph_h2a = 0, ph_h2b = 0;
     uint32_t ph_aux0 = 0, ph_aux1 = 0, ph_aux2 = 0;
     bool pend_aux0 = false, pend_aux1 = false, pend_aux2 = false;
     auto wait_dw3 = [&]() {
-      if (pend_aux0) { mbar_wait(&bar_aux[0], ph_aux0); ph_aux0 ^= 1; pend_aux0 = false; }
+      if (pend_aux0) { ewait(&bar_aux[0], ph_aux0); ph_aux0 ^= 1; pend_aux0 = false; }
     };
     auto wait_dw2 = [&]() {
-      if (pend_aux1) { mbar_wait(&bar_aux[1], ph_aux1); ph_aux1 ^= 1; pend_aux1 = false; }
+      if (pend_aux1) { ewait(&bar_aux[1], ph_aux1); ph_aux1 ^= 1; pend_aux1 = false; }
     };
     auto wait_d1 = [&]() {
-      if (pend_aux2) { mbar_wait(&bar_aux[2], ph_aux2); ph_aux2 ^= 1; pend_aux2 = false; }
+      if (pend_aux2) { ewait(&bar_aux[2], ph_aux2); ph_aux2 ^= 1; pend_aux2 = false; }
     };
 
     float* slab = A.slab + (long long)blockIdx.x * A.slab_len;
@@ -1663,14 +1669,14 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
       for (int ch = 0; ch < nch; ++ch) {
         const int d = ch / A.nkc, kci = ch % A.nkc;
         if (ch == 0) {
-          mbar_wait(&bar_l3, ph_l3);
+          ewait(&bar_l3, ph_l3);
           ph_l3 ^= 1;
           // landed before L3 could run; waiting here (never blocks) makes the bulk-async writes of the h2 image
           // visible to this thread's loads in stage 3 and keeps this thread's parity in step with the loads
-          if (hb == 0) { mbar_wait(&bar_h2[0], ph_h2a); ph_h2a ^= 1; }
-          else         { mbar_wait(&bar_h2[1], ph_h2b); ph_h2b ^= 1; }
+          if (hb == 0) { ewait(&bar_h2[0], ph_h2a); ph_h2a ^= 1; }
+          else         { ewait(&bar_h2[1], ph_h2b); ph_h2b ^= 1; }
         } else {
-          mbar_wait(&bar_main, ph_main);
+          ewait(&bar_main, ph_main);
           ph_main ^= 1;
           wait_dw3();  // dW3(ch-1) still reads the dO image
         }
@@ -1775,7 +1781,7 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
       }
 
       // ---- 3. Z2g = dH2 (1 - h2^2) -> its own image (zsep) or the dO image
-      mbar_wait(&bar_main, ph_main);
+      ewait(&bar_main, ph_main);
       ph_main ^= 1;
       tc_fence_after();
       NL_PROF(7);
@@ -1819,12 +1825,12 @@ __global__ void __launch_bounds__(kBsThreads, 1) fused_tc_bwd_saved_kernel(TcArg
       if (tid == 0) NL_TRACE(5);
 
       // ---- 4. Z1g = dH1 (1 - h1^2) -> dO image ; dp
-      mbar_wait(&bar_main, ph_main);
+      ewait(&bar_main, ph_main);
       ph_main ^= 1;
       tc_fence_after();
       NL_PROF(9);
       if (tid == 0) NL_TRACE(6);
-      mbar_wait(&bar_h1, ph_h1);
+      ewait(&bar_h1, ph_h1);
       ph_h1 ^= 1;
       float dpv[KP];
       {
