@@ -524,7 +524,8 @@ def run_b200(a):
       mode = {"name": "bf16x3 (float32 parity: 3 bf16 passes per GEMM, fp32 accumulate in TMEM)", "passes": 3,
               "frac_of_mode_peak": 3 * achieved / peak_tf}
     else:
-      mode = {"name": "CUDA-core FFMA (float32)" if a.dtype == "f32" else "CUDA-core DFMA (float64)", "passes": 1,
+      mode = {"name": "CUDA-core FFMA (float32)" if a.dtype == "f32" else
+              "FP64 tensor pipe (DMMA mma.sync.m8n8k4) for the GEMMs, DFMA epilogue (float64)", "passes": 1,
               "frac_of_mode_peak": None}
     # transcendental (MUFU) share.  Algorithmic count, SURVEY section 8(d): 2H hidden tanh + per (d, k) two head tanh
     # + tan, sin, cos = 2H + 5 D n per point forward (293 at d_obs 1 / 33 terms).  Implementation count of the
@@ -548,6 +549,12 @@ def run_b200(a):
       traffic = tr.get(key, {}).get(dom)
     except Exception:  # pylint: disable=broad-except
       pass
+    if a.dtype == "f64":
+      # float64 runs on the FP64 tensor pipe (DMMA) / DFMA: judged against the FP64 matmul peak measured in this run
+      # (SURVEY 7.2), not the bf16 one
+      p64 = measure_matmul_peaks(dev).get("fp64_tflops")
+      if p64:
+        peak_tf, peak_src = float(p64), "FP64 matmul peak measured in this run (torch.matmul 4096^3, best of 5)"
     line = {
         "metric": "ILT reconstructed batch*time points/sec fwd+bwd", "value": value, "unit": "points/s",
         "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_total / a.steps,
@@ -556,7 +563,8 @@ def run_b200(a):
                    "weak" else a.batch, "time_points": a.time,
                    "terms": a.terms, "s_points": n, "d_obs": a.dobs, "parallelism": f"dp{world} (batch-sharded)",
                    "l2": "flushed (512 MB write) between timed steps",
-                   "kernel_family": {1: "simt (CUDA-core FFMA/DFMA)", 2: "tcgen05"}.get(impl_f, "?"),
+                   "kernel_family": {1: "simt (CUDA-core FFMA)" if a.dtype == "f32" else "dmma (FP64 tensor pipe + DFMA)",
+                                     2: "tcgen05"}.get(impl_f, "?"),
                    "host_path": ("engine.GraphedReconstruct (CUDA-graph replay of the two C-ABI calls)"
                                  if graphed is not None else "laplace_reconstruct + autograd"),
                    "host_numa_bound": bool(numa_bound), "fwd_ms": fwd_ms, "bwd_ms": bwd_ms},
@@ -581,8 +589,10 @@ def run_b200(a):
                      "note": ("De Hoog: the step is dominated by the per-thread quotient-difference recurrence "
                               "(dehoog_qd kernels: CUDA cores, IEEE divisions), the tensor-core MLP kernels take "
                               "~3 ms of it; see DESIGN.md section 4.9") if a.alg == "dehoog" else
-                             ("latency-bound: no unit saturated (ncu: issue slots 40-60 %, XU 13-53 %, tensor pipe "
-                              "16-32 %); see DESIGN.md section 6 and profiles/")},
+                             ("backward: the tensor core is fed from shared memory (small-N SS-mode MMAs) and shares that "
+                              "port with the epilogue -- ncu: shared-memory wavefronts LSU 36 % + tensor 47 % of peak, "
+                              "tensor pipe active 37 %, issue slots 45 %; forward: issue slots 59 %, XU (MUFU) 53 %; "
+                              "see DESIGN.md section 6 and profiles/r02c_*")},
     }
     if not a.no_peaks:  # the matmul peaks of the other precision modes, measured in the same run
       line["roofline"]["peaks_measured"] = measure_matmul_peaks(dev)
