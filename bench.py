@@ -452,6 +452,8 @@ def run_b200(a):
     staged = parallel.HostStagedStep(f, a.dobs, a.alg, a.terms, reducer=reducer, device=dev)
 
   def e2e_step():
+    if graphed is None:  # the next step's upstream gradient is uploaded one step ahead (input prefetch)
+      return staged(p_pin, t_pin, g_pin, x_pin, grads_pin, next_grad_x_host=g_pin)
     return staged(p_pin, t_pin, g_pin, x_pin, grads_pin)
 
   for _ in range(8):  # the copy streams grow their own allocator pools during the first steps

@@ -161,15 +161,29 @@ class HostStagedStep:
     self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
     self.upload = torch.cuda.Stream(self.device)
     self.download = torch.cuda.Stream(self.device)
+    self._prefetched = None  # (host tensor, its device copy in flight on the upload stream)
 
-  def __call__(self, p_host, t_host, grad_x_host, x_host_out, grads_host_out=None):
+  def prefetch(self, grad_x_host):
+    """Start uploading the NEXT step's upstream gradient now (input prefetch, like a data loader's): called right
+    after a step, the copy runs under that step's backward too instead of under the next forward alone.  With
+    eight ranks sharing the host links a 16.8 MB upload no longer fits under the 0.7 ms forward (measured on
+    8 B200: 2.73 ms per end-to-end step against 1.9 ms of kernels)."""
+    with torch.cuda.stream(self.upload):
+      self._prefetched = (grad_x_host, grad_x_host.to(self.device, non_blocking=True))
+
+  def __call__(self, p_host, t_host, grad_x_host, x_host_out, grads_host_out=None, next_grad_x_host=None):
     """Runs forward + backward of sum(grad_x * x); writes x into ``x_host_out`` and the flattened MLP gradients
     into ``grads_host_out`` (both pinned).  Returns the device ``p`` (its ``.grad`` holds dL/dp).
+    ``next_grad_x_host``: the upstream gradient of the FOLLOWING call, uploaded ahead of time (see ``prefetch``).
     The copies are asynchronous: synchronise (``torch.cuda.synchronize``) before reading the host buffers."""
     dev = self.device
     main = torch.cuda.current_stream(dev)
-    with torch.cuda.stream(self.upload):
-      g_d = grad_x_host.to(dev, non_blocking=True)
+    if self._prefetched is not None and self._prefetched[0] is grad_x_host:
+      g_d = self._prefetched[1]
+    else:
+      with torch.cuda.stream(self.upload):
+        g_d = grad_x_host.to(dev, non_blocking=True)
+    self._prefetched = None
     p_d = p_host.to(dev, non_blocking=True).requires_grad_(True)
     t_d = t_host.to(dev, non_blocking=True)
     for q in self.params:
@@ -181,6 +195,8 @@ class HostStagedStep:
     x.record_stream(self.download)
     main.wait_stream(self.upload)
     g_d.record_stream(main)
+    if next_grad_x_host is not None:  # issued before the backward's launches: the copy engine starts at once
+      self.prefetch(next_grad_x_host)
     x.backward(g_d)
     if self.reducer is not None:
       self.reducer()

@@ -120,3 +120,33 @@ def test_graphed_host_step_matches_host_staged_step():
     assert hp.rel(xo_g, xo_e) <= 1e-6
     assert hp.rel(go_g, go_e) <= 1e-5
     assert hp.rel(dp, pe.grad) <= 1e-5
+
+
+def test_host_staged_step_prefetch_of_the_next_upstream_gradient():
+  """parallel.HostStagedStep with next_grad_x_host (upload one step ahead): same results as without, step by step,
+  including a step whose gradient was NOT the prefetched buffer (the prefetch is then dropped)."""
+  if not torch.cuda.is_available():
+    pytest.skip("no CUDA device")
+  dev = torch.device("cuda", 0)
+  from neurallaplace_b200 import parallel
+  from oracle import nl_oracle as orc
+  B, T = 192, 48
+  weights = orc.make_canonical_weights(33, 1, 2, seed=3)
+  f = hp.make_module([w.to(dev) for w in weights], 33, 1, 2, True, dev)
+  n_par = sum(q.numel() for q in f.parameters())
+  g = torch.Generator().manual_seed(8)
+  p = torch.randn(B, 2, generator=g).pin_memory()
+  t = (torch.rand(T, generator=g) * 10 + 0.1).pin_memory()
+  gxs = [torch.randn(B, T, 1, generator=g).pin_memory() for _ in range(4)]
+  plain, ahead = parallel.HostStagedStep(f, 1, device=dev), parallel.HostStagedStep(f, 1, device=dev)
+  order = [0, 1, 3, 2]  # step 2 announces buffer 2 but step 3 then brings buffer 3: the prefetch must be ignored
+  for i, k in enumerate(order):
+    announced = gxs[[1, 2, 2, 0][i]]
+    xo_a, xo_b = torch.empty(B, T, 1).pin_memory(), torch.empty(B, T, 1).pin_memory()
+    go_a, go_b = torch.empty(n_par).pin_memory(), torch.empty(n_par).pin_memory()
+    pa = plain(p, t, gxs[k], xo_a, go_a)
+    torch.cuda.synchronize()
+    pb = ahead(p, t, gxs[k], xo_b, go_b, next_grad_x_host=announced)
+    torch.cuda.synchronize()
+    assert torch.equal(xo_a, xo_b)
+    assert hp.rel(go_b, go_a) <= 1e-6 and hp.rel(pb.grad, pa.grad) <= 1e-6
