@@ -456,8 +456,14 @@ def run_b200(a):
       return staged(p_pin, t_pin, g_pin, x_pin, grads_pin, next_grad_x_host=g_pin)
     return staged(p_pin, t_pin, g_pin, x_pin, grads_pin)
 
-  for _ in range(8):  # the copy streams grow their own allocator pools during the first steps
-    e2e_step()
+  # The copy streams grow their own allocator pools while the host runs ahead of the device: a cudaMalloc inside a
+  # timed span stalls the host until the queued steps have drained (measured: one 20 MB cudaMalloc = 60-80 ms, a
+  # 2-10x span).  Warm up with as many un-synchronised steps as the timed spans issue, twice, so the pools reach
+  # their steady-state size first; span_diag still reports any cudaMalloc that happens inside a span.
+  for _ in range(2):
+    for _ in range(3 * max(3, min(a.steps, 10))):
+      e2e_step()
+    torch.cuda.synchronize()
   barrier()
   e2e_steps = max(3, min(a.steps, 10))
   # five spans of e2e_steps steps, the median span is reported (all five are in the JSON line): this leg is bound by
