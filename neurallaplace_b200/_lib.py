@@ -169,8 +169,14 @@ def ptr(t):
   return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)  # pylint: disable=protected-access
+
+
 def stream_ptr(device=None):
   """Current torch stream of ``device`` (default: the current device) as the ABI's ``void* cuda_stream``."""
+  if _raw_stream is not None:  # one C call instead of building a torch.cuda.Stream object (hot path of small steps)
+    idx = torch.cuda.current_device() if device is None or device.index is None else device.index
+    return ctypes.c_void_p(_raw_stream(idx))
   return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 

@@ -42,6 +42,39 @@ def _workspace(lib, d, which, device):
   return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device), nbytes
 
 
+class _Plan:
+  """What a fused call needs besides its tensors, for one (constants, dtype, shape, mode, device) combination:
+  the descriptor, the workspace sizes of both passes, the stash size and whether the fused kernels cover the shape.
+  The library's answers are pure functions of the descriptor (and of the device's SM count), so they are asked once:
+  at the reference demos' size (B=128, T=100) the Python layer, not the GPU, sets the step time."""
+  __slots__ = ("d", "ws_fwd", "ws_bwd", "saved_bytes", "supported")
+
+
+_plans = {}
+_NO_PLAN_CACHE = os.environ.get("NL_B200_NO_PLAN_CACHE", "0") == "1"  # (A/B of the host path)
+
+
+def _plan(consts, dtype, B, T, K, H, D, t_mode, head, impl, device):
+  env = (os.environ.get("NL_B200_IMPL", "auto"), os.environ.get("NL_B200_STASH", "1"))
+  key = (id(consts), dtype, B, T, K, H, D, t_mode, head, impl, device.index, env)
+  hit = _plans.get(key)
+  if hit is not None and hit[0] is consts and not _NO_PLAN_CACHE:
+    return hit[1]
+  lib = _lib.load()
+  pl = _Plan()
+  pl.d = _desc(consts, dtype, B, T, K, H, D, t_mode, head, impl)
+  with _lib.on(device):
+    pl.ws_fwd = int(lib.nl_workspace_bytes(ctypes.byref(pl.d), 0))
+    pl.ws_bwd = int(lib.nl_workspace_bytes(ctypes.byref(pl.d), 1))
+    pl.saved_bytes = int(lib.nl_saved_bytes(ctypes.byref(pl.d))) if env[1] != "0" else 0
+    pl.supported = (lib.nl_selected_impl(ctypes.byref(pl.d), 0) != 0 and
+                    lib.nl_selected_impl(ctypes.byref(pl.d), 1) != 0)
+  if len(_plans) > 256:
+    _plans.clear()
+  _plans[key] = (consts, pl)  # (the constants object is kept alive so that its id cannot be reused)
+  return pl
+
+
 # ------------------------------------------------------------------------------------------
 # fused reconstruct
 # ------------------------------------------------------------------------------------------
@@ -89,10 +122,11 @@ class ReconstructFn(torch.autograd.Function):
     B, K = p.shape
     T = t.shape[-1] if t_mode == _lib.NL_T_PER_ROW else t.numel()
     H = W1.shape[0]
-    d = _desc(consts, p.dtype, B, T, K, H, D, t_mode, head, impl)
-    ws, nbytes = _workspace(lib, d, 0, dev)
+    pl = _plan(consts, p.dtype, B, T, K, H, D, t_mode, head, impl, dev)
+    d, nbytes = pl.d, pl.ws_fwd
+    ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
     beta, eta = consts.tables_on(dev)
-    weights = [w.contiguous() for w in (W1, b1, W2, b2, W3, b3)]
+    weights = [w if w.is_contiguous() else w.contiguous() for w in (W1, b1, W2, b2, W3, b3)]
     x = torch.empty((B, T, D), dtype=p.dtype, device=dev)
     pc, tc = p.contiguous(), t.contiguous()
     # Training: keep the two hidden activations for backward (the analogue of autograd's saved tensors,
@@ -101,8 +135,8 @@ class ReconstructFn(torch.autograd.Function):
     # True under torch.no_grad() and would make inference pay for the stash.  Above NL_B200_STASH_MAX_GB or when
     # the allocation fails, backward recomputes instead.
     saved, saved_bytes = None, 0
-    if stash and any(ctx.needs_input_grad) and os.environ.get("NL_B200_STASH", "1") != "0":
-      saved_bytes = int(lib.nl_saved_bytes(ctypes.byref(d)))
+    if stash and any(ctx.needs_input_grad):
+      saved_bytes = pl.saved_bytes  # (0 under NL_B200_STASH=0)
       if saved_bytes and saved_bytes <= _stash_budget(dev):
         try:
           saved = torch.empty(saved_bytes, dtype=torch.uint8, device=dev)
@@ -124,8 +158,9 @@ class ReconstructFn(torch.autograd.Function):
     B, K = pc.shape
     T = tc.shape[-1] if t_mode == _lib.NL_T_PER_ROW else tc.numel()
     H = weights[0].shape[0]
-    d = _desc(consts, pc.dtype, B, T, K, H, D, t_mode, head, impl)
-    ws, nbytes = _workspace(lib, d, 1, dev)
+    pl = _plan(consts, pc.dtype, B, T, K, H, D, t_mode, head, impl, dev)
+    d, nbytes = pl.d, pl.ws_bwd
+    ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
     beta, eta = consts.tables_on(dev)
     # the six MLP gradients are views of ONE flat buffer (W1|b1|W2|b2|W3|b3): the data-parallel all-reduce and
     # the fused clip + Adam step then work on it in place, with no pack / unpack copies (parallel.py, optim.py)
@@ -150,10 +185,10 @@ def _stash_budget(dev):  # pylint: disable=unused-argument
   return int(float(cap) * (1 << 30)) if cap is not None else (1 << 62)
 
 
-def fused_supported(consts, dtype, B, T, K, H, D, t_mode, head, impl=0):
-  lib = _lib.load()
-  d = _desc(consts, dtype, B, T, K, H, D, t_mode, head, impl)
-  return lib.nl_selected_impl(ctypes.byref(d), 0) != 0 and lib.nl_selected_impl(ctypes.byref(d), 1) != 0
+def fused_supported(consts, dtype, B, T, K, H, D, t_mode, head, impl=0, device=None):
+  if device is None:
+    device = torch.device("cuda", torch.cuda.current_device())
+  return _plan(consts, dtype, B, T, K, H, D, t_mode, head, impl, device).supported
 
 
 def saved_bytes(consts, dtype, B, T, K, H, D, t_mode, head, impl=0):

@@ -184,7 +184,7 @@ def laplace_reconstruct(
     H, K = l1.out_features, pd.shape[1]
     if (kind == want and laplace_rep_func.output_dim == recon_dim and laplace_rep_func.latent_dim == K and
         l1.weight.dtype == dtype and
-        _ops.fused_supported(consts, dtype, batch_dim, time_dim, K, H, recon_dim, t_mode, head)):
+        _ops.fused_supported(consts, dtype, batch_dim, time_dim, K, H, recon_dim, t_mode, head, 0, dev)):
       ws = [w if w.device == dev else w.to(dev) for w in (l1.weight, l1.bias, l2.weight, l2.bias, l3.weight, l3.bias)]
       if hasattr(laplace_rep_func, "nfe"):
         laplace_rep_func.nfe += 1
