@@ -17,6 +17,7 @@
 //
 // Math: SURVEY.md App. A/B; reference core.py:104-150, inverse_laplace.py, transformations.py.
 #include <algorithm>
+#include <cstdlib>
 
 #include "nl_dehoog.cuh"
 #include "nl_kernels.h"
@@ -89,7 +90,7 @@ __host__ __device__ inline SmemLayout smem_layout(int rmax, int nslots, int H, i
 template <typename R, int RP, int CB, typename Epi>
 __device__ __forceinline__ void gemm_rows_simt(const R* __restrict__ sA, int lda, int Kdim, int rows,
                                                const R* __restrict__ W, int64_t sc, int64_t sk, int NC, Epi epi) {
-  constexpr int kWarps = SimtCfg<R>::kWarps;
+  const int kWarps = (int)(blockDim.x >> 5);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int c0 = warp * CB; c0 < NC; c0 += kWarps * CB) {
     R acc[RP][CB];
@@ -145,7 +146,7 @@ __device__ __forceinline__ void gemm_tn_accum_simt(const R* __restrict__ sA1, in
                                                    const R* __restrict__ sA2, int ld2, int NC, int rows, R* out,
                                                    int64_t ldo) {
   constexpr int JB = 8, CP = 2;
-  constexpr int kWarps = SimtCfg<R>::kWarps;
+  const int kWarps = (int)(blockDim.x >> 5);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int j0 = warp * JB; j0 < NJ; j0 += kWarps * JB) {
     const int jb = min(JB, NJ - j0);
@@ -201,7 +202,7 @@ template <int MT, int MTP, typename Epi>
 __device__ __forceinline__ void gemm_rows_dmma_t(const double* __restrict__ sA, int lda, int Kdim, int rows,
                                                  const double* __restrict__ W, int64_t sc, int64_t sk, int NC,
                                                  Epi epi) {
-  constexpr int kWarps = SimtCfg<double>::kWarps;
+  const int kWarps = (int)(blockDim.x >> 5);
   constexpr int kGroups = MT / MTP;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int lr = lane >> 2, lk = lane & 3;
@@ -244,7 +245,7 @@ __device__ __forceinline__ void gemm_rows_dmma_t(const double* __restrict__ sA, 
 template <int MT, typename Epi>
 __device__ __forceinline__ void gemm_rows_dmma(const double* __restrict__ sA, int lda, int Kdim, int rows,
                                                const double* __restrict__ W, int64_t sc, int64_t sk, int NC, Epi epi) {
-  constexpr int kWarps = SimtCfg<double>::kWarps;
+  const int kWarps = (int)(blockDim.x >> 5);
   const int nb_n = (NC + 7) >> 3;
   const int mt_used = (rows + 7) >> 3;
   // enough items for every warp, as many row blocks per item as that allows (B fragment reuse)
@@ -259,7 +260,7 @@ __device__ __forceinline__ void gemm_rows_dmma(const double* __restrict__ sA, in
 __device__ __forceinline__ void gemm_tn_accum_dmma(const double* __restrict__ sA1, int ld1, int NJ,
                                                    const double* __restrict__ sA2, int ld2, int NC, int rows,
                                                    double* out, int64_t ldo) {
-  constexpr int kWarps = SimtCfg<double>::kWarps;
+  const int kWarps = (int)(blockDim.x >> 5);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int lr = lane >> 2, lk = lane & 3;
   const int jb_n = (NJ + 7) >> 3, cb_n = (NC + 7) >> 3;
@@ -304,7 +305,7 @@ __device__ __forceinline__ void gemm_tn_accum(const R* __restrict__ sA1, int ld1
 // out[c] += sum_{r<rows} A[r*ld + c]
 template <typename R>
 __device__ __forceinline__ void colsum_accum(const R* __restrict__ sA, int ld, int NC, int rows, R* out) {
-  for (int c = threadIdx.x; c < NC; c += SimtCfg<R>::kThreads) {
+  for (int c = threadIdx.x; c < NC; c += (int)blockDim.x) {
     R s = R(0);
     for (int r = 0; r < rows; ++r) s += sA[r * ld + c];
     out[c] += s;
@@ -325,7 +326,8 @@ __global__ void __launch_bounds__(SimtCfg<R>::kThreads, 1) fused_simt_kernel(Fus
   extern __shared__ __align__(16) unsigned char smem_raw[];
   R* sm = reinterpret_cast<R*>(smem_raw);
   constexpr int RMAX = 32 * RP;
-  constexpr int kThreads = SimtCfg<R>::kThreads, kWarps = SimtCfg<R>::kWarps;
+  // (launched with SimtCfg<R>::kThreads threads, or half of that with two CTAs per SM: SimtPlan::threads)
+  const int kThreads = (int)blockDim.x, kWarps = kThreads >> 5;
   const IltParams<R> P = A.P;
   const int H = A.H, n = A.n, K = A.K, D = A.D;
   const bool dehoog = P.family == NL_DEHOOG;
@@ -652,13 +654,30 @@ SimtPlan simt_plan(const nl_desc* d, int pass) {
     }
   }
   if (rp == 0) return pl;
+  pl.threads = d->dtype == NL_F64 ? SimtCfg<double>::kThreads : SimtCfg<float>::kThreads;
+  int ctas = 1;
+  if (d->dtype == NL_F64) {
+    // float64: TWO CTAs of 256 threads and 32-row tiles per SM instead of one of 512 threads and 64 rows when the
+    // shared memory allows it (same warps and rows in flight, but the phases of the two CTAs -- GEMMs on the DMMA
+    // pipe, float64 transcendentals, slab updates -- overlap instead of alternating)
+    static const int want2 = [] { const char* v = getenv("NL_B200_F64_CTAS"); return v ? atoi(v) : 1; }();
+    const int BB1 = std::max(1, std::min(d->B, 32)), TT1 = std::max(1, std::min(d->T, 32 / BB1));
+    SmemLayout L1 = smem_layout(32, d->t_mode == NL_T_PER_ROW ? 32 : TT1, d->H, d->n, d->K, bwd,
+                                d->family == NL_FOURIER, ctx_reals, SimtCfg<double>::kPad);
+    if (want2 == 2 && (L1.total * rs + 1024) * 2 <= (size_t)228 * 1024) {
+      rp = 1;
+      pl.smem = L1.total * rs;
+      pl.threads = SimtCfg<double>::kThreads / 2;
+      ctas = 2;
+    }
+  }
   const int rmax = 32 * rp;
   pl.rp = rp;
   pl.BB = std::max(1, std::min(d->B, rmax));
   pl.TT = std::max(1, std::min(d->T, rmax / pl.BB));
   const int64_t nbt = (d->B + pl.BB - 1) / pl.BB, ntt = (d->T + pl.TT - 1) / pl.TT;
   const int64_t ntiles = nbt * ntt;
-  pl.grid = (int)std::min<int64_t>(ntiles, device_sm_count());
+  pl.grid = (int)std::min<int64_t>(ntiles, (int64_t)device_sm_count() * ctas);
   if (pl.grid < 1) pl.grid = 1;
   const int64_t ldw1 = 2 * d->n + d->K;
   pl.slab_len = (size_t)d->H * ldw1 + d->H + (size_t)d->H * d->H + d->H + (size_t)2 * d->D * d->n * d->H +
@@ -674,16 +693,16 @@ SimtPlan simt_plan(const nl_desc* d, int pass) {
 }
 
 template <typename R, int RP>
-static cudaError_t launch_rp(const FusedArgs<R>& A, bool bwd, int grid, size_t smem, cudaStream_t st) {
+static cudaError_t launch_rp(const FusedArgs<R>& A, bool bwd, int grid, int threads, size_t smem, cudaStream_t st) {
   cudaError_t e;
   if (bwd) {
     e = cudaFuncSetAttribute(fused_simt_kernel<R, RP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    fused_simt_kernel<R, RP, true><<<grid, SimtCfg<R>::kThreads, smem, st>>>(A);
+    fused_simt_kernel<R, RP, true><<<grid, threads, smem, st>>>(A);
   } else {
     e = cudaFuncSetAttribute(fused_simt_kernel<R, RP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    fused_simt_kernel<R, RP, false><<<grid, SimtCfg<R>::kThreads, smem, st>>>(A);
+    fused_simt_kernel<R, RP, false><<<grid, threads, smem, st>>>(A);
   }
   return cudaGetLastError();
 }
@@ -739,8 +758,8 @@ cudaError_t launch_fused_simt(const nl_desc* d, bool bwd, const void* p, const v
     if (e != cudaSuccess) return e;
   }
   auto run = [&](const FusedArgs<R>& args, bool backward) {
-    return pl.rp == 2 ? launch_rp<R, 2>(args, backward, pl.grid, pl.smem, st)
-                      : launch_rp<R, 1>(args, backward, pl.grid, pl.smem, st);
+    return pl.rp == 2 ? launch_rp<R, 2>(args, backward, pl.grid, pl.threads, pl.smem, st)
+                      : launch_rp<R, 1>(args, backward, pl.grid, pl.threads, pl.smem, st);
   };
   if (d->family == NL_DEHOOG) {
     // forward: MLP -> F plane, recurrence -> x.   backward: MLP -> F plane (recomputed), recurrence forward +
@@ -763,8 +782,8 @@ cudaError_t launch_fused_simt(const nl_desc* d, bool bwd, const void* p, const v
       Af.BB = plf.BB; Af.TT = plf.TT;
       Af.nbt = (d->B + plf.BB - 1) / plf.BB;
       Af.ntt = (d->T + plf.TT - 1) / plf.TT;
-      e = plf.rp == 2 ? launch_rp<R, 2>(Af, false, plf.grid, plf.smem, st)
-                      : launch_rp<R, 1>(Af, false, plf.grid, plf.smem, st);
+      e = plf.rp == 2 ? launch_rp<R, 2>(Af, false, plf.grid, plf.threads, plf.smem, st)
+                      : launch_rp<R, 1>(Af, false, plf.grid, plf.threads, plf.smem, st);
     } else {
       e = run(Af, false);
     }

@@ -28,6 +28,7 @@ struct SimtPlan {
   int rp;            // rows per lane (tile rows = 32*rp)
   int BB, TT;        // tile geometry
   int grid;          // persistent CTAs
+  int threads;       // threads per CTA
   size_t smem;       // dynamic shared memory bytes
   size_t slab_len;   // reals per CTA gradient slab (backward)
   size_t ws_bytes;   // workspace bytes

@@ -224,3 +224,30 @@ def test_two_rank_gloo_gradient_allreduce():
   for pr in procs:
     pr.join(timeout=60)
   assert res == [(0, True, 0, 4), (1, True, 4, 7)]
+
+
+def test_plan_cache_matches_direct_queries_and_follows_the_environment(monkeypatch):
+  """_ops._plan (what every fused call uses instead of asking the library again): same answers as the direct queries,
+  one object per shape, and a different plan when NL_B200_IMPL / NL_B200_STASH change (they are part of the key)."""
+  import torch
+  from neurallaplace_b200 import _consts, _ops
+  lib = _lib.load()
+  c = _consts.get("fourier", 33, torch.float32)
+  dev = torch.device("cuda", 0)  # (only its index is used: the queries are host-side)
+  monkeypatch.delenv("NL_B200_IMPL", raising=False)
+  monkeypatch.delenv("NL_B200_STASH", raising=False)
+  monkeypatch.setattr(_lib, "on", lambda device: _lib._SAME)  # no CUDA device here: the size queries are host-side
+  pl = _ops._plan(c, torch.float32, 4096, 1024, 2, 64, 1, 0, 0, 0, dev)
+  d = _ops._desc(c, torch.float32, 4096, 1024, 2, 64, 1, 0, 0, 0)
+  assert pl.ws_fwd == lib.nl_workspace_bytes(ctypes.byref(d), 0)
+  assert pl.ws_bwd == lib.nl_workspace_bytes(ctypes.byref(d), 1)
+  assert pl.saved_bytes == lib.nl_saved_bytes(ctypes.byref(d)) > 4096 * 1024 * 512
+  assert pl.supported and _ops.fused_supported(c, torch.float32, 4096, 1024, 2, 64, 1, 0, 0, 0, dev)
+  assert _ops._plan(c, torch.float32, 4096, 1024, 2, 64, 1, 0, 0, 0, dev) is pl
+  assert _ops._plan(c, torch.float32, 4096, 512, 2, 64, 1, 0, 0, 0, dev) is not pl
+  monkeypatch.setenv("NL_B200_STASH", "0")
+  assert _ops._plan(c, torch.float32, 4096, 1024, 2, 64, 1, 0, 0, 0, dev).saved_bytes == 0
+  monkeypatch.delenv("NL_B200_STASH")
+  monkeypatch.setenv("NL_B200_IMPL", "simt")
+  ps = _ops._plan(c, torch.float32, 4096, 1024, 2, 64, 1, 0, 0, 0, dev)
+  assert ps is not pl and ps.d.impl == 1 and ps.saved_bytes == 0
