@@ -657,14 +657,16 @@ SimtPlan simt_plan(const nl_desc* d, int pass) {
   pl.threads = d->dtype == NL_F64 ? SimtCfg<double>::kThreads : SimtCfg<float>::kThreads;
   int ctas = 1;
   if (d->dtype == NL_F64) {
-    // float64: TWO CTAs of 256 threads and 32-row tiles per SM instead of one of 512 threads and 64 rows when the
-    // shared memory allows it (same warps and rows in flight, but the phases of the two CTAs -- GEMMs on the DMMA
-    // pipe, float64 transcendentals, slab updates -- overlap instead of alternating)
-    static const int want2 = [] { const char* v = getenv("NL_B200_F64_CTAS"); return v ? atoi(v) : 1; }();
+    // float64 FORWARD: two CTAs of 256 threads and 32-row tiles per SM instead of one of 512 threads and 64 rows when
+    // the shared memory allows it (same warps and rows in flight, but the phases of the two CTAs -- GEMMs on the DMMA
+    // pipe, float64 transcendentals -- overlap instead of alternating): 3.56 -> 3.35 ms at B=1024 x T=1024.  The
+    // backward is slower that way (10.1 -> 12.1 ms: twice the slab read-modify-write passes per point) and keeps one.
+    // NL_B200_F64_CTAS: 1 = never, 2 = forward only (default), 3 = both passes.
+    static const int want2 = [] { const char* v = getenv("NL_B200_F64_CTAS"); return v ? atoi(v) : 2; }();
     const int BB1 = std::max(1, std::min(d->B, 32)), TT1 = std::max(1, std::min(d->T, 32 / BB1));
     SmemLayout L1 = smem_layout(32, d->t_mode == NL_T_PER_ROW ? 32 : TT1, d->H, d->n, d->K, bwd,
                                 d->family == NL_FOURIER, ctx_reals, SimtCfg<double>::kPad);
-    if (want2 == 2 && (L1.total * rs + 1024) * 2 <= (size_t)228 * 1024) {
+    if ((want2 == 3 || (want2 == 2 && !bwd)) && (L1.total * rs + 1024) * 2 <= (size_t)228 * 1024) {
       rp = 1;
       pl.smem = L1.total * rs;
       pl.threads = SimtCfg<double>::kThreads / 2;
