@@ -25,6 +25,8 @@ def test_every_boundary_name_resolves_to_the_b200_implementation():
   assert torchlaplace.core.laplace_reconstruct is nb.laplace_reconstruct
   assert set(torchlaplace.core.ILT_ALGORITHMS) == {"fourier", "dehoog", "cme", "euler", "fixed_tablot", "stehfest"}
   assert isinstance(torchlaplace.__version__, str)
+  import torchlaplace.version  # (reference: torchlaplace/__init__.py:2)
+  assert torchlaplace.version.__version__ == torchlaplace.__version__
   # signature of the reference (core.py:25-36)
   sig = inspect.signature(torchlaplace.laplace_reconstruct)
   assert list(sig.parameters) == ["laplace_rep_func", "p", "t", "recon_dim", "ilt_algorithm", "use_sphere_projection",
